@@ -1,0 +1,145 @@
+// imc_rng.h — counter-based random draws for host and device.
+//
+// The reference draws from Julia's global task-local RNG (Random.seed!, MixedPrecisionIMC.jl:86),
+// which makes every history depend on loop order.  The engine replaces it with Philox4x32-10
+// (Salmon et al., SC'11) keyed by the deck SEED and counted by (particle id, time step, stream,
+// block), so a particle's draws do not depend on which GPU or thread tracks it (BASELINE.json
+// north_star "RNG").  Replay mode bypasses Philox and reads pre-drawn numbers from a tape.
+//
+// Draw conversions follow Julia's conventions: rand(T) is a multiple of 2^-11 / 2^-24 / 2^-53
+// in [0,1); randexp(T) for T < Float64 is drawn wider and converted (here: -log of a 32-bit
+// uniform in Float32; Julia draws Float64 — statistically equivalent, not bit-equivalent; the
+// Julia stream itself is not reproducible across Julia versions).
+#pragma once
+#include "imc_num.h"
+#include "imc_math.h"
+
+namespace imc {
+
+struct Philox {
+  static IMC_HD void mulhilo(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
+#if defined(__CUDA_ARCH__)
+    *lo = a * b;
+    *hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    *lo = (uint32_t)p;
+    *hi = (uint32_t)(p >> 32);
+#endif
+  }
+  // Philox4x32-10 block function
+  static IMC_HD void block(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(0xD2511F53u, c0, &hi0, &lo0);
+      mulhilo(0xCD9E8D57u, c2, &hi1, &lo1);
+      uint32_t n0 = hi1 ^ c1 ^ k0;
+      uint32_t n2 = hi0 ^ c3 ^ k1;
+      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+
+enum : uint32_t { STREAM_SOURCE = 0u, STREAM_TRACK = 1u };
+
+// One particle's draw stream for one time step.  Words are consumed in order; a new Philox
+// block is generated every 4 words.  counter = (id_lo, id_hi, step, stream<<28 | block).
+struct PhiloxStream {
+  uint32_t key[2];
+  uint32_t ctr[4];
+  uint32_t buf[4];
+  uint32_t used;  // words consumed from buf (4 = empty)
+  IMC_HD void init(uint64_t seed, uint64_t id, uint32_t step, uint32_t stream) {
+    key[0] = (uint32_t)seed;
+    key[1] = (uint32_t)(seed >> 32);
+    ctr[0] = (uint32_t)id;
+    ctr[1] = (uint32_t)(id >> 32);
+    ctr[2] = step;
+    ctr[3] = stream << 28;
+    buf[0] = buf[1] = buf[2] = buf[3] = 0u;
+    used = 4;
+  }
+  IMC_HD uint32_t next_u32() {
+    if (used == 4) {
+      Philox::block(ctr, key, buf);
+      ctr[3] += 1;
+      used = 0;
+    }
+    // avoid dynamic register-array indexing
+    uint32_t w = used == 0 ? buf[0] : used == 1 ? buf[1] : used == 2 ? buf[2] : buf[3];
+    used += 1;
+    return w;
+  }
+  IMC_HD uint64_t next_u64() {
+    uint64_t lo = next_u32();
+    uint64_t hi = next_u32();
+    return (hi << 32) | lo;
+  }
+};
+
+// word -> uniform / exponential conversions (shared by every RNG back-end)
+template <class P> IMC_HD Num<P> uniform_from_word(uint64_t w);
+template <> IMC_HD Num<F16> uniform_from_word<F16>(uint64_t w) { return Num<F16>((float)((uint32_t)w >> 21) * 4.8828125e-04f); }
+template <> IMC_HD Num<F32> uniform_from_word<F32>(uint64_t w) { return Num<F32>((float)((uint32_t)w >> 8) * 5.9604644775390625e-08f); }
+template <> IMC_HD Num<F64> uniform_from_word<F64>(uint64_t w) { return Num<F64>((double)(w >> 11) * 1.1102230246251565e-16); }
+
+IMC_HD double randexp64_from_word(uint64_t w) {
+  double u = ((double)(w >> 11) + 1.0) * 1.1102230246251565e-16;  // (0, 1]
+  return -dm::log_d(u);
+}
+IMC_HD float randexp32_from_word(uint32_t w) {
+  float u = (float)w * 2.3283064365386963e-10f + 1.1641532182693481e-10f;  // (0, 1]
+  if (u > 1.0f) u = 1.0f;
+  return -dm::log_f(u);
+}
+
+// RNG back-end 1: Philox.  Draw<P> API: uniform() -> rand(T); randexp() -> randexp(T);
+// randexp64() -> randexp() in Float64 (MC_RW, imc_transport.jl:279).
+template <class P>
+struct PhiloxDraw {
+  PhiloxStream s;
+  IMC_HD void init(uint64_t seed, uint64_t id, uint32_t step, uint32_t stream) { s.init(seed, id, step, stream); }
+  IMC_HD Num<P> uniform() {
+    if constexpr (P::id == 2) return uniform_from_word<P>(s.next_u64());
+    else return uniform_from_word<P>((uint64_t)s.next_u32());
+  }
+  IMC_HD Num<P> randexp() {
+    if constexpr (P::id == 2) return Num<P>(randexp64_from_word(s.next_u64()));
+    else return Num<P>(P::rnd(randexp32_from_word(s.next_u32())));
+  }
+  IMC_HD double randexp64() { return randexp64_from_word(s.next_u64()); }
+  IMC_HD bool exhausted() const { return false; }
+};
+
+// RNG back-end 2: tape (replay mode).  Pre-drawn Float64 numbers, draw-major layout
+// tape[k * stride + slot]; uniforms must already be T-representable (they are rand(T) values),
+// exponentials are Float64 and are converted to T here exactly as randexp(T) does.
+template <class P>
+struct TapeDraw {
+  const double* uni; const double* ex;
+  size_t stride, slot;
+  int n_uni, n_exp, iu, ie;
+  bool over;
+  IMC_HD void init(const double* uni_, int n_uni_, const double* ex_, int n_exp_, size_t stride_, size_t slot_) {
+    uni = uni_; ex = ex_; n_uni = n_uni_; n_exp = n_exp_; stride = stride_; slot = slot_;
+    iu = 0; ie = 0; over = false;
+  }
+  IMC_HD Num<P> uniform() {
+    if (iu >= n_uni) { over = true; return Num<P>::from_d(0.5); }
+    return Num<P>::from_d(uni[(size_t)(iu++) * stride + slot]);
+  }
+  IMC_HD double randexp64() {
+    if (ie >= n_exp) { over = true; return 1.0; }
+    return ex[(size_t)(ie++) * stride + slot];
+  }
+  IMC_HD Num<P> randexp() { return Num<P>::from_d(randexp64()); }
+  IMC_HD bool exhausted() const { return over; }
+};
+
+}  // namespace imc
