@@ -11,7 +11,7 @@ CUDA in csrc/.  This Python package is only the host-side mirror used where Juli
 
 The directory name contains a dot, so import it through the root-level loader module ``mpimc_b200``.
 """
-from . import lib, deck, driver  # noqa: F401
+from . import lib, deck, decks, driver  # noqa: F401
 from .lib import Config, Engine, ImcLib, ImcError, cuda_lib  # noqa: F401
 from .driver import main, setup, Simulation  # noqa: F401
 

@@ -1,0 +1,182 @@
+// imc_device.cuh — device-side building blocks shared by the engine kernels:
+//   sorter_dev    Utilities.sorter (imc_utilities.jl:23-54) for one cell
+//   jl_sum        Julia Base.sum (pairwise, 1024-element sequential leaves) as a parallel reduction
+//                 with exactly the reference's association order — the source counts depend on the
+//                 last bit of mesh.totalenergy (imc_sourcing.jl:121, :139), so the order matters
+//   exclusive scan of per-entry counts (int32 -> int64)
+//   warp / block reductions for counters
+#pragma once
+#include <cuda_runtime.h>
+#include "imc_num.h"
+#include "imc_math.h"
+#include "imc_rng.h"
+
+namespace imc {
+
+#define IMC_FULL_MASK 0xffffffffu
+
+// ---- Utilities.sorter -------------------------------------------------------------------------
+// vals: Float64 images of the literal array (<= 12 entries); scales: descending.  Pair products are
+// formed in the array's element type and converted to T: for T-valued inputs that is one rounding of
+// the exact product, for Float64 inputs (Q12/Q31) T(Float64 product) — both equal from_d(a*b).
+template <class P, int NMAX>
+__device__ __forceinline__ void sorter_dev(const double (&vals)[NMAX], int n, const double* scales, int n_scales,
+                                           Num<P>* prod_out, int* idx_out) {
+  for (int j = 0; j < n_scales; ++j) {
+    double s[NMAX + 1];
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) s[i] = i < n ? vals[i] : 0.0;
+    s[n] = scales[j];
+    int m = n + 1;
+    for (int i = 1; i < m; ++i) {  // insertion sort, ascending
+      double key = s[i];
+      int k = i - 1;
+      while (k >= 0 && s[k] > key) { s[k + 1] = s[k]; --k; }
+      s[k + 1] = key;
+    }
+    Num<P> product = Num<P>::from_d(1.0);
+    for (int i = 0; i < m / 2; ++i) product *= Num<P>::from_d(s[i] * s[m - 1 - i]);
+    if (m & 1) product *= Num<P>::from_d(s[m / 2]);
+    if (!is_inf(product) && !is_nan(product)) { *prod_out = product; *idx_out = j; return; }
+  }
+  *prod_out = Num<P>();
+  *idx_out = -1;
+}
+
+// ---- reductions ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(IMC_FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(IMC_FULL_MASK, v, o);
+  return v;
+}
+
+// ---- Julia Base.sum ----------------------------------------------------------------------------
+// Recursion: a range with (last - first) < 1024 is summed left to right; otherwise it is split at
+// mid = first + ((last - first) >> 1) and the halves are added (base/reduce.jl mapreduce_impl).
+// Leaves therefore sit on at most two adjacent depths.  Kernel 1: one thread per slot of the deepest
+// level walks down from the root; the thread standing on the leftmost slot of a leaf sums it.
+// Kernel 2 (one block) folds the levels bottom-up, left + right, as the recursion would.
+inline int jl_sum_depth(long long n) {
+  int d = 0;
+  while (n > 1024) { n = (n + 1) / 2; ++d; }
+  return d;
+}
+
+template <class P>
+__global__ void k_jlsum_leaves(const typename P::store_t* __restrict__ q, long long n, int depth,
+                               typename P::comp_t* __restrict__ part, unsigned char* __restrict__ valid) {
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (1ll << depth)) return;
+  if (n <= 0) { if (tid == 0) { part[0] = 0; valid[0] = 1; } return; }
+  long long first = 0, last = n - 1;
+  int d = 0;
+  while (true) {
+    if (last - first < 1024) {
+      int rem = depth - d;
+      if (rem > 0 && (tid & ((1ll << rem) - 1)) != 0) { valid[tid] = 0; return; }
+      Num<P> v = Num<P>::load(q, first);
+      for (long long i = first + 1; i <= last; ++i) v = v + Num<P>::load(q, i);
+      part[tid] = v.v;
+      valid[tid] = 1;
+      return;
+    }
+    long long mid = first + ((last - first) >> 1);
+    int bit = (int)((tid >> (depth - 1 - d)) & 1);
+    if (bit) first = mid + 1; else last = mid;
+    ++d;
+  }
+}
+
+template <class P>
+__global__ void k_jlsum_fold(typename P::comp_t* part, const unsigned char* valid, int depth,
+                             typename P::comp_t* out) {
+  for (int level = depth; level >= 1; --level) {
+    long long nodes = 1ll << (level - 1);
+    int sh = depth - level;  // slot stride of this level's nodes is 1 << sh
+    for (long long i = threadIdx.x; i < nodes; i += blockDim.x) {
+      long long ls = (2 * i) << sh, rs = (2 * i + 1) << sh;
+      if (valid[rs]) part[ls] = (Num<P>(part[ls]) + Num<P>(part[rs])).v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = part[0];
+}
+
+// ---- exclusive scan int32 -> int64 (three-phase) ----------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <class TIn>
+__global__ void k_scan_tiles(const TIn* __restrict__ in, long long* __restrict__ out, long long n,
+                             long long* __restrict__ tile_sums) {
+  __shared__ long long warp_tot[SCAN_THREADS / 32];
+  long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  long long v[SCAN_ITEMS];
+  long long local = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    long long idx = base + k;
+    v[k] = idx < n ? (long long)in[idx] : 0;
+    local += v[k];
+  }
+  // inclusive warp scan of thread totals
+  long long x = local;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long y = __shfl_up_sync(IMC_FULL_MASK, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[wid] = x;
+  __syncthreads();
+  long long woff = 0;
+  for (int w = 0; w < wid; ++w) woff += warp_tot[w];
+  long long excl = woff + x - local;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    long long idx = base + k;
+    if (idx < n) out[idx] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == SCAN_THREADS - 1) tile_sums[blockIdx.x] = woff + x;
+}
+static __global__ void k_scan_add(long long* __restrict__ out, long long n, const long long* __restrict__ tile_off) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] += tile_off[idx / SCAN_TILE];
+}
+// single-block exclusive scan of a (small) long long array, in place; total written to *total
+static __global__ void k_scan_small(long long* a, long long n, long long* total) {
+  __shared__ long long carry;
+  __shared__ long long warp_tot[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n; base += blockDim.x) {
+    long long idx = base + threadIdx.x;
+    long long v = idx < n ? a[idx] : 0;
+    long long x = v;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(IMC_FULL_MASK, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    long long woff = 0;
+    for (int w = 0; w < wid; ++w) woff += warp_tot[w];
+    long long c = carry;
+    if (idx < n) a[idx] = c + woff + x - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = c + woff + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+}  // namespace imc

@@ -1,0 +1,3 @@
+// EngineT<F32> instantiation (one translation unit per precision so the three compile in parallel).
+#include "imc_engine_impl.cuh"
+namespace imc { EngineBase* make_engine_f32(const imc_config& cfg) { return new EngineT<F32>(cfg); } }

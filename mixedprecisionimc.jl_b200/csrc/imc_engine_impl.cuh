@@ -1,0 +1,735 @@
+// imc_engine_impl.cuh — EngineT<P>: host orchestration of the transport-step kernels for one GPU.
+// Owns all device memory (mesh fields, particle SoA double buffer, reduce buffer, scratch).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <vector>
+#include "imc_engine.h"
+#include "imc_kernels.cuh"
+
+namespace imc {
+
+#define IMC_CK(call)                                                                               \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof b_, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      err = b_;                                                                                    \
+      return e_ == cudaErrorMemoryAllocation ? IMC_ERR_NOMEM : IMC_ERR_CUDA;                        \
+    }                                                                                              \
+  } while (0)
+#define IMC_RC(call) do { int rc_ = (call); if (rc_) return rc_; } while (0)
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count, bool zero = true) {
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    n = count;
+    return zero ? cudaMemset(p, 0, count * sizeof(T)) : cudaSuccess;
+  }
+  cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count, false); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DBuf() { release(); }
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+};
+
+inline unsigned grid_for(long long n, int threads) { return (unsigned)std::max<long long>(1, (n + threads - 1) / threads); }
+
+template <class P>
+struct PartBufs {
+  using S = typename P::store_t;
+  DBuf<S> t, x, y, mu, E, E0;
+  DBuf<int> cx, cy, origin;
+  DBuf<unsigned char> ks;
+  DBuf<unsigned long long> id;
+  cudaError_t alloc(size_t cap, int geom) {
+    cudaError_t e;
+#define A_(b) if ((e = b.alloc(cap, false)) != cudaSuccess) return e
+    A_(t); A_(x); A_(mu); A_(E); A_(E0); A_(cx); A_(ks); A_(id);
+    if (geom == 2) { A_(y); A_(cy); } else { A_(origin); }
+#undef A_
+    return cudaSuccess;
+  }
+  Parts<P> view() { Parts<P> v; v.t = t.p; v.x = x.p; v.y = y.p; v.mu = mu.p; v.E = E.p; v.E0 = E0.p; v.cx = cx.p; v.cy = cy.p; v.origin = origin.p; v.ks = ks.p; v.id = id.p; return v; }
+};
+
+template <class P>
+struct EngineT : EngineBase {
+  using S = typename P::store_t;
+  using Cc = typename P::comp_t;
+  using N = Num<P>;
+  imc_config cfg;
+  int geom, nx, ny, ns, sm_count = 148;
+  long long nc;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool have_mesh = false, temp_wide = false, have_rw = false;
+  // mesh
+  DBuf<S> dx, dy, wx, wy, sa, ss, fleck, beta, bee, sa_c, sa_p, ss_c, ss_p, sigma_static, radsource;
+  DBuf<S> matenergydens, radenergydens, nrg_inc, energydep, emittedenergy, tsurf[4];
+  DBuf<double> temp;
+  DBuf<CellProp1<P>> cp1;
+  DBuf<CellProp2<P>> cp2;
+  MeshDev<P> m;
+  // particles (double buffer for the stable compaction)
+  PartBufs<P> pb[2];
+  int cur = 0;
+  long long n_part = 0, cap = 0;
+  // reduce buffer: [energydep Nc*Ns | radenergydens Nc | scalars]
+  DBuf<double> red;
+  long long red_n = 0;
+  bool red_fixed = false;
+  double fx_mul_dep = 1, fx_mul_rad = 1, fx_mul_lost = 1;
+  // sourcing scratch
+  SrcLayout L;
+  DBuf<S> src_e, src_q, src_nrg, src_qem;
+  DBuf<signed char> src_ks;
+  DBuf<int> src_cnt;
+  DBuf<long long> src_offs, scan_tiles, scan_tiles2, scan_total;
+  DBuf<SrcScalars> src_sc;
+  DBuf<Cc> sums;  // device slots for jl_sum results
+  // jl_sum scratch
+  DBuf<Cc> jl_part;
+  DBuf<unsigned char> jl_valid;
+  // tally scratch
+  DBuf<S> q_dep, q_tot, q_rad;
+  DBuf<double> d_max;
+  DBuf<int> d_flag;
+  DBuf<unsigned long long> over_flag;
+  DBuf<long long> blk_cnt;
+  // outcomes
+  DBuf<signed char> out_event;
+  DBuf<int> out_nseg;
+  long long out_n = 0;
+  // tapes
+  DBuf<double> tt_uni, tt_exp, st_uni;
+  int tt_nuni = 0, tt_nexp = 0, st_nuni = 0;
+  long long tt_slots = 0, st_slots = 0;
+  // random-walk tables
+  DBuf<S> rw_a, rw_pt;
+  std::vector<double> h_rw_a, h_rw_pr, h_rw_pt;
+  // host mirrors of the scalar state
+  double totalenergy = 0, totalenergydep = 0, radenergyold = 0;
+  uint64_t iterations = 0;
+
+  explicit EngineT(const imc_config& c) : cfg(c) {
+    geom = c.geometry; nx = c.nx; ny = geom == 2 ? c.ny : 1; ns = c.n_scales; nc = (long long)nx * ny;
+    L.geom = geom; L.nx = nx; L.ny = ny; L.nc = nc;
+  }
+  ~EngineT() override {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int init() override {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+      err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); the transport step has no CPU fallback";
+      return IMC_ERR_CUDA;
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) { err = "bad device ordinal"; return IMC_ERR_ARG; }
+    IMC_CK(cudaSetDevice(cfg.device));
+    cudaDeviceProp prop;
+    IMC_CK(cudaGetDeviceProperties(&prop, cfg.device));
+    sm_count = prop.multiProcessorCount;
+    IMC_CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    IMC_CK(cudaEventCreate(&ev0));
+    IMC_CK(cudaEventCreate(&ev1));
+    return IMC_OK;
+  }
+  int use_device() { IMC_CK(cudaSetDevice(cfg.device)); return IMC_OK; }
+
+  // ---- helpers -----------------------------------------------------------------------------
+  int upload(DBuf<S>& b, const double* src, size_t n) {
+    std::vector<S> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = P::pack(src ? P::from_d(src[i]) : (Cc)0);
+    IMC_CK(b.alloc(n, false));
+    IMC_CK(cudaMemcpyAsync(b.p, h.data(), n * sizeof(S), cudaMemcpyHostToDevice, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    return IMC_OK;
+  }
+  int download(const S* src, size_t n, double* dst) {
+    std::vector<S> h(n);
+    IMC_CK(cudaMemcpyAsync(h.data(), src, n * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < n; ++i) dst[i] = (double)P::unpack(h[i]);
+    return IMC_OK;
+  }
+  // Julia sum of q[0..n) into the device slot `out`
+  int jl_sum(const S* q, long long n, Cc* out) {
+    int depth = jl_sum_depth(n);
+    size_t slots = (size_t)1 << depth;
+    IMC_CK(jl_part.ensure(slots));
+    IMC_CK(jl_valid.ensure(slots));
+    k_jlsum_leaves<P><<<grid_for((long long)slots, 128), 128, 0, stream>>>(q, n, depth, jl_part.p, jl_valid.p);
+    k_jlsum_fold<P><<<1, 1024, 0, stream>>>(jl_part.p, jl_valid.p, depth, out);
+    IMC_CK(cudaGetLastError());
+    return IMC_OK;
+  }
+  // exclusive scan int32 -> int64, total to scan_total.p[0]
+  int scan_counts(const int* in, long long* out, long long n) {
+    long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    IMC_CK(scan_tiles.ensure((size_t)tiles));
+    IMC_CK(scan_total.ensure(1));
+    k_scan_tiles<int><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(in, out, n, scan_tiles.p);
+    k_scan_small<<<1, 1024, 0, stream>>>(scan_tiles.p, tiles, scan_total.p);
+    k_scan_add<<<grid_for(n, 256), 256, 0, stream>>>(out, n, scan_tiles.p);
+    IMC_CK(cudaGetLastError());
+    return IMC_OK;
+  }
+  int ensure_capacity(long long need) {
+    if (need <= cap) return IMC_OK;
+    long long ncap = std::max<long long>(need, cap + cap / 2);
+    ncap = std::max<long long>(ncap, 1024);
+    PartBufs<P> nb[2];
+    IMC_CK(nb[0].alloc((size_t)ncap, geom));
+    IMC_CK(nb[1].alloc((size_t)ncap, geom));
+    if (n_part > 0) {
+      PartBufs<P>& o = pb[cur];
+#define CP_(f, T_) IMC_CK(cudaMemcpyAsync(nb[0].f.p, o.f.p, (size_t)n_part * sizeof(T_), cudaMemcpyDeviceToDevice, stream))
+      CP_(t, S); CP_(x, S); CP_(mu, S); CP_(E, S); CP_(E0, S); CP_(cx, int); CP_(ks, unsigned char); CP_(id, unsigned long long);
+      if (geom == 2) { CP_(y, S); CP_(cy, int); } else { CP_(origin, int); }
+#undef CP_
+      IMC_CK(cudaStreamSynchronize(stream));
+    }
+    for (int b = 0; b < 2; ++b) {
+#define MV_(f) std::swap(pb[b].f.p, nb[b].f.p); std::swap(pb[b].f.n, nb[b].f.n)
+      MV_(t); MV_(x); MV_(y); MV_(mu); MV_(E); MV_(E0); MV_(cx); MV_(cy); MV_(origin); MV_(ks); MV_(id);
+#undef MV_
+    }
+    if (cur == 1) {  // live data was copied into buffer 0
+      cur = 0;
+    }
+    cap = ncap;
+    return IMC_OK;
+  }
+  RngArgs rng_args(int64_t step, bool source) {
+    RngArgs r;
+    r.tape = cfg.rng_mode == IMC_RNG_TAPE;
+    r.seed = (unsigned long long)cfg.seed;
+    r.step = (unsigned int)step;
+    if (source) { r.uni = st_uni.p; r.ex = nullptr; r.n_uni = st_nuni; r.n_exp = 0; r.stride = st_slots; }
+    else { r.uni = tt_uni.p; r.ex = tt_exp.p; r.n_uni = tt_nuni; r.n_exp = tt_nexp; r.stride = tt_slots; }
+    return r;
+  }
+  long long rb_dep0() const { return 0; }
+  long long rb_rad0() const { return nc * ns; }
+  long long rb_sc0() const { return nc * ns + nc; }
+
+  // ---- set_mesh ----------------------------------------------------------------------------
+  int set_mesh(const double* dx_, const double* dy_, const double* sac, const double* sap, const double* ssc,
+               const double* ssp, const double* sstat, const double* bee_, const double* rad, const double* temp_,
+               const double* tsb, const double* tst, const double* tsl, const double* tsr) override {
+    IMC_RC(use_device());
+    if (!dx_ || !sac || !sap || !ssc || !ssp || !bee_ || !rad || !temp_ || !tsl || !tsr || (geom == 2 && (!dy_ || !tsb || !tst))) {
+      err = "set_mesh: null array"; return IMC_ERR_ARG;
+    }
+    IMC_RC(upload(dx, dx_, nx));
+    if (geom == 2) IMC_RC(upload(dy, dy_, ny)); else { double one = 1.0; IMC_RC(upload(dy, &one, 1)); }
+    IMC_CK(wx.alloc(nx)); IMC_CK(wy.alloc(ny));
+    IMC_RC(upload(sa_c, sac, nc)); IMC_RC(upload(sa_p, sap, nc)); IMC_RC(upload(ss_c, ssc, nc)); IMC_RC(upload(ss_p, ssp, nc));
+    IMC_RC(upload(sa, sac, nc)); IMC_RC(upload(ss, ssc, nc));
+    IMC_RC(upload(sigma_static, sstat, nc));
+    IMC_RC(upload(bee, bee_, nc)); IMC_RC(upload(radsource, rad, nc));
+    {
+      std::vector<double> h(nc);
+      for (long long i = 0; i < nc; ++i) h[i] = (double)P::from_d(temp_[i]);
+      IMC_CK(temp.alloc(nc, false));
+      IMC_CK(cudaMemcpy(temp.p, h.data(), nc * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    temp_wide = false;
+    if (geom == 1) { IMC_RC(upload(tsurf[2], tsl, 1)); IMC_RC(upload(tsurf[3], tsr, 1)); IMC_CK(tsurf[0].alloc(1)); IMC_CK(tsurf[1].alloc(1)); }
+    else { IMC_RC(upload(tsurf[0], tsb, nx)); IMC_RC(upload(tsurf[1], tst, nx)); IMC_RC(upload(tsurf[2], tsl, ny)); IMC_RC(upload(tsurf[3], tsr, ny)); }
+    IMC_CK(fleck.alloc(nc)); IMC_CK(beta.alloc(nc));
+    IMC_CK(matenergydens.alloc(nc)); IMC_CK(radenergydens.alloc(nc)); IMC_CK(nrg_inc.alloc(nc));
+    IMC_CK(energydep.alloc(nc * ns)); IMC_CK(emittedenergy.alloc(nc * ns));
+    if (geom == 1) IMC_CK(cp1.alloc(nc)); else IMC_CK(cp2.alloc(nc));
+    red_n = nc * ns + nc + RB_NSCALARS;
+    IMC_CK(red.alloc(red_n));
+    // sourcing / tally scratch
+    long long M = L.total();
+    IMC_CK(src_e.alloc(M)); IMC_CK(src_q.alloc(M)); IMC_CK(src_nrg.alloc(M)); IMC_CK(src_ks.alloc(M)); IMC_CK(src_cnt.alloc(M));
+    IMC_CK(src_offs.alloc(M + 1)); IMC_CK(src_qem.alloc(nc * ns)); IMC_CK(src_sc.alloc(1)); IMC_CK(sums.alloc(16));
+    IMC_CK(q_dep.alloc(nc * ns)); IMC_CK(q_tot.alloc(nc)); IMC_CK(q_rad.alloc(nc));
+    IMC_CK(d_max.alloc(2)); IMC_CK(d_flag.alloc(2)); IMC_CK(over_flag.alloc(1));
+    // device view
+    m.geom = geom; m.nx = nx; m.ny = ny; m.ns = ns; m.nc = nc;
+    m.dx = dx.p; m.dy = dy.p; m.wx = wx.p; m.wy = wy.p;
+    m.sa = sa.p; m.ss = ss.p; m.fleck = fleck.p; m.beta = beta.p; m.bee = bee.p; m.sa_c = sa_c.p; m.sa_p = sa_p.p;
+    m.ss_c = ss_c.p; m.ss_p = ss_p.p; m.sigma_static = sigma_static.p; m.radsource = radsource.p; m.temp = temp.p;
+    m.matenergydens = matenergydens.p; m.radenergydens = radenergydens.p; m.nrg_inc = nrg_inc.p;
+    m.energydep = energydep.p; m.emittedenergy = emittedenergy.p;
+    for (int k = 0; k < 4; ++k) m.tsurf[k] = tsurf[k].p;
+    m.cp1 = cp1.p; m.cp2 = cp2.p;
+    for (int k = 0; k < IMC_MAX_SCALES; ++k) { m.scales[k] = k < ns ? P::from_d(cfg.energyscales[k]) : (Cc)1; m.scales_d[k] = (double)m.scales[k]; }
+    m.ds = P::from_d(cfg.distancescale); m.c = P::from_d(cfg.phys_c); m.a = P::from_d(cfg.phys_a); m.alpha = P::from_d(cfg.alpha);
+    for (int k = 0; k < 4; ++k) m.bc[k] = cfg.bc[k];
+    k_widths<P><<<grid_for(std::max(nx, ny), 256), 256, 0, stream>>>(m);
+    IMC_CK(cudaGetLastError());
+    IMC_CK(cudaStreamSynchronize(stream));
+    totalenergy = totalenergydep = radenergyold = 0;
+    have_mesh = true;
+    return IMC_OK;
+  }
+
+  // ---- random-walk tables (imc_transport.jl:734-754, :786-797) ------------------------------------
+  static double P_r(double a) {
+    if (a == 0) return 1.0;
+    double Pr = 0.0;
+    for (int n = 1; n <= 100; ++n) {
+      double pin = 3.141592653589793 * (double)n;
+      double sgn = ((n - 1) & 1) ? -1.0 : 1.0;
+      Pr += sgn * dm::exp_d(-a * (pin * pin)) * 2.0;
+    }
+    return Pr;
+  }
+  int rw_table(double lo, double hi, int n, double* a_out, double* pr_out, double* pt_out) override {
+    IMC_RC(use_device());
+    if (n < 2) { err = "rw_table: n < 2"; return IMC_ERR_ARG; }
+    h_rw_a.resize(n); h_rw_pr.resize(n); h_rw_pt.resize(n);
+    for (int i = 0; i < n; ++i) {
+      double t = (double)i / (double)(n - 1);
+      N a = N::from_d((1.0 - t) * lo + t * hi);          // T.(LinRange(lo, hi, n))
+      N pr = N::from_d(P_r(a.d()));                       // stored into zeros(T)
+      N pt = N::from_d(1.0) - pr;                         // T(1 - prVals[i])
+      h_rw_a[i] = a.d(); h_rw_pr[i] = pr.d(); h_rw_pt[i] = pt.d();
+      if (a_out) a_out[i] = a.d();
+      if (pr_out) pr_out[i] = pr.d();
+      if (pt_out) pt_out[i] = pt.d();
+    }
+    IMC_RC(upload(rw_a, h_rw_a.data(), n));
+    IMC_RC(upload(rw_pt, h_rw_pt.data(), n));
+    have_rw = true;
+    return IMC_OK;
+  }
+
+  // ---- Update.update -------------------------------------------------------------------------
+  int update(double dt) override {
+    if (!have_mesh) { err = "update before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    k_update<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, P::from_d(dt), cfg.linearized, cfg.marshak_quirk, temp_wide ? 1 : 0);
+    IMC_CK(cudaGetLastError());
+    return IMC_OK;
+  }
+
+  // ---- Sourcing.sourcing ---------------------------------------------------------------------
+  int source(double dt_, int64_t n_input, double cellmin_, int64_t step, int64_t n_census_global, imc_source_stats* out) override {
+    if (!have_mesh) { err = "source before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    Cc dt = P::from_d(dt_), cellmin = P::from_d(cellmin_);
+    SrcArrays<P> s; s.e = src_e.p; s.q = src_q.p; s.ks = src_ks.p; s.cnt = src_cnt.p; s.nrg = src_nrg.p; s.q_em = src_qem.p;
+    k_src_energies<P><<<grid_for(L.n_surf() + nc, 128), 128, 0, stream>>>(m, s, L, dt);
+    IMC_CK(cudaGetLastError());
+    // totalenergy sums in the reference's association order
+    if (geom == 1) {
+      IMC_RC(jl_sum(s.q + L.body0(), nc, sums.p + 0));
+      IMC_RC(jl_sum(s.q + L.rad0(), nc, sums.p + 1));
+    } else {
+      IMC_RC(jl_sum(s.q + 0, nx, sums.p + 0));
+      IMC_RC(jl_sum(s.q + nx, nx, sums.p + 1));
+      IMC_RC(jl_sum(s.q + 2 * nx, ny, sums.p + 2));
+      IMC_RC(jl_sum(s.q + 2 * nx + ny, ny, sums.p + 3));
+      IMC_RC(jl_sum(s.q + L.body0(), nc, sums.p + 4));
+      IMC_RC(jl_sum(s.q + L.rad0(), nc, sums.p + 5));
+    }
+    IMC_RC(jl_sum(s.q_em, nc * ns, sums.p + 6));
+    long long n_census = n_census_global >= 0 ? n_census_global : n_part;
+    int wide_counts = (P::id == 0) && (std::max<int64_t>(n_input, cfg.n_max) > 65504);
+    k_src_total<P><<<1, 1, 0, stream>>>(s, L, sums.p, src_sc.p, n_input, n_census, cfg.n_max, cellmin, wide_counts);
+    k_src_counts<P><<<grid_for(L.total(), 256), 256, 0, stream>>>(m, s, L, src_sc.p, cellmin, wide_counts);
+    IMC_CK(cudaGetLastError());
+    IMC_RC(scan_counts(s.cnt, src_offs.p, L.total()));
+    SrcScalars hsc; long long total = 0; Cc h_emsum = 0;
+    IMC_CK(cudaMemcpyAsync(&hsc, src_sc.p, sizeof hsc, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaMemcpyAsync(&total, scan_total.p, sizeof total, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaMemcpyAsync(&h_emsum, sums.p + 6, sizeof(Cc), cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    totalenergy = hsc.totalenergy;
+    const long long world = cfg.world > 0 ? cfg.world : 1, rank = cfg.rank;
+    long long n_local = total > rank ? (total - rank + world - 1) / world : 0;
+    if (cfg.rng_mode == IMC_RNG_TAPE && n_local > 0 && total > st_slots) { err = "source tape has fewer slots than new particles"; return IMC_ERR_TAPE; }
+    IMC_RC(ensure_capacity(n_part + n_local));
+    if (n_local > 0) {
+      IMC_CK(cudaMemsetAsync(over_flag.p, 0, sizeof(unsigned long long), stream));
+      k_src_emit<P><<<grid_for(n_local, 256), 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, n_part, n_local, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p);
+      IMC_CK(cudaGetLastError());
+      unsigned long long over = 0;
+      IMC_CK(cudaMemcpyAsync(&over, over_flag.p, sizeof over, cudaMemcpyDeviceToHost, stream));
+      IMC_CK(cudaStreamSynchronize(stream));
+      if (over) { err = "source tape exhausted"; return IMC_ERR_TAPE; }
+    }
+    n_part += n_local;
+    if (out) {
+      out->totalenergy = totalenergy; out->emitted_sum = (double)h_emsum; out->n_source = (int64_t)hsc.nsrc;
+      out->n_new_global = total; out->n_new_local = n_local; out->n_particles = n_part;
+    }
+    if (hsc.bad) { err = "non-finite particle count or unrepresentable energy (reference would throw)"; return IMC_ERR_NUMERIC; }
+    return IMC_OK;
+  }
+
+  // ---- Transport -----------------------------------------------------------------------------
+  int resolve_tally_mode() const {
+    int mode = cfg.tally_mode;
+    if (mode == IMC_TALLY_AUTO) mode = cfg.pairwise ? IMC_TALLY_FIXED : IMC_TALLY_ATOMIC;
+    if (mode == IMC_TALLY_EXACT) mode = IMC_TALLY_FIXED;  // record path: see DESIGN.md (round 2)
+    return mode;
+  }
+  // smallest cell volume / scale, for fixed-point scaling
+  double min_vol_h = 0, min_scale_h = 1, min_dx_h = 0;
+  int compute_min_vol() {
+    std::vector<double> hx(nx), hy(ny);
+    IMC_RC(download(dx.p, nx, hx.data()));
+    double mx = *std::min_element(hx.begin(), hx.end()), my = 1.0;
+    if (geom == 2) { IMC_RC(download(dy.p, ny, hy.data())); my = *std::min_element(hy.begin(), hy.end()); }
+    min_dx_h = mx; min_vol_h = mx * my;
+    min_scale_h = 1e300;
+    for (int k = 0; k < ns; ++k) min_scale_h = std::min(min_scale_h, (double)m.scales[k]);
+    return IMC_OK;
+  }
+  static double pow2_floor_mul(double bound) {  // 2^S with bound * 2^S < 2^62
+    if (!(bound > 0) || !std::isfinite(bound)) return 1.0;
+    int e;
+    std::frexp(bound, &e);  // bound < 2^e
+    return std::ldexp(1.0, 62 - e);
+  }
+  // Fixed-point scales.  They must be identical on every rank (the host sums the integer buffers), so the
+  // energy bound comes from replicated quantities: census energy at the end of the last step plus the
+  // energy sourced this step, times the largest scale.  Without those (set_particles test flows) it falls
+  // back to n * max(E), which is rank-local and therefore only valid for world == 1.
+  double rad_total_h = 0;
+  int prepare_fixed(TallyArgs& ta) {
+    if (min_vol_h == 0) IMC_RC(compute_min_vol());
+    double max_scale = 0;
+    for (int k = 0; k < ns; ++k) max_scale = std::max(max_scale, (double)m.scales[k]);
+    double tot = 2.0 * (rad_total_h + totalenergy) * max_scale;
+    if (!(tot > 0)) {
+      IMC_CK(cudaMemsetAsync(d_max.p, 0, sizeof(double), stream));
+      k_max_energy<P><<<sm_count * 4, 256, 0, stream>>>(pb[cur].view(), n_part, d_max.p);
+      double maxE = 0;
+      IMC_CK(cudaMemcpyAsync(&maxE, d_max.p, sizeof maxE, cudaMemcpyDeviceToHost, stream));
+      IMC_CK(cudaStreamSynchronize(stream));
+      tot = maxE * (double)std::max<long long>(n_part, 1) * (cfg.world > 0 ? cfg.world : 1);
+    }
+    fx_mul_dep = pow2_floor_mul(tot / min_vol_h);
+    fx_mul_rad = pow2_floor_mul(tot / (min_vol_h * min_scale_h));
+    fx_mul_lost = pow2_floor_mul(tot / min_scale_h);
+    ta.fx_mul = fx_mul_dep; ta.fx_mul_lost = fx_mul_lost;
+    return IMC_OK;
+  }
+  size_t smem_for(int mode, long long nacc) const {
+    size_t per = mode == IMC_TALLY_FIXED ? 8 : sizeof(typename AccType<P>::type);
+    return (size_t)nacc * per;
+  }
+
+  int transport(double dt_, int64_t step, imc_transport_stats* out) override {
+    if (!have_mesh) { err = "transport before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    if (cfg.randomwalk && !have_rw) { err = "random-walk tables not set (imc_rw_table)"; return IMC_ERR_STATE; }
+    if (cfg.rng_mode == IMC_RNG_TAPE && n_part > tt_slots) { err = "transport tape has fewer slots than particles"; return IMC_ERR_TAPE; }
+    const int mode = resolve_tally_mode();
+    if ((mode == IMC_TALLY_FIXED) != red_fixed) {  // representation change: start from a clean buffer
+      IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream));
+      red_fixed = mode == IMC_TALLY_FIXED;
+    }
+    // mesh.energydep = zeros(...) (:45); per-call counters; lostenergy keeps accumulating
+    IMC_CK(cudaMemsetAsync(red.p + rb_dep0(), 0, nc * ns * sizeof(double), stream));
+    IMC_CK(cudaMemsetAsync(red.p + rb_sc0() + RB_SEG, 0, (RB_NSCALARS - RB_SEG) * sizeof(double), stream));
+    IMC_CK(cudaMemsetAsync(over_flag.p, 0, sizeof(unsigned long long), stream));
+    TrackArgs<P> a;
+    a.m = m; a.p = pb[cur].view(); a.n = n_part; a.dt = P::from_d(dt_);
+    a.rng = rng_args(step, false);
+    a.tally.mode = mode; a.tally.nacc = (int)(nc * ns);
+    a.tally.g_acc = red.p; a.tally.g_fx = reinterpret_cast<long long*>(red.p);
+    a.tally.fx_mul = 1; a.tally.fx_mul_lost = 1; a.tally.sc0 = rb_sc0();
+    if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
+    size_t smem = smem_for(mode, nc * ns);
+    a.tally.use_smem = smem <= 48 * 1024 ? 1 : 0;
+    if (!a.tally.use_smem) smem = 0;
+    // outcome records for replay checks (small populations only)
+    bool record = n_part <= (1ll << 22);
+    if (record) {
+      IMC_CK(out_event.ensure((size_t)std::max<long long>(n_part, 1)));
+      IMC_CK(out_nseg.ensure((size_t)std::max<long long>(n_part, 1)));
+      a.out_event = out_event.p; a.out_nseg = out_nseg.p; out_n = n_part;
+    } else { a.out_event = nullptr; a.out_nseg = nullptr; out_n = 0; }
+    a.over_flag = over_flag.p;
+    a.aVals = rw_a.p; a.ptVals = rw_pt.p; a.n_rw_table = (int)h_rw_a.size();
+    int variant = IMC_TRACK_HISTORY;
+    if (n_part > 0) {
+      int blocks_per_sm = 2048 / TRACK_THREADS;
+      if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / smem));
+      unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
+      IMC_CK(cudaEventRecord(ev0, stream));
+      if (geom == 1 && cfg.randomwalk) { IMC_RC(launch_rw(a, grid, smem)); }
+      else if (geom == 1) k_track1d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      else k_track2d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      IMC_CK(cudaGetLastError());
+      IMC_CK(cudaEventRecord(ev1, stream));
+    }
+    double sc[RB_NSCALARS];
+    unsigned long long over = 0;
+    IMC_CK(cudaMemcpyAsync(sc, red.p + rb_sc0(), sizeof sc, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaMemcpyAsync(&over, over_flag.p, sizeof over, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    if (n_part > 0) IMC_CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    auto cnt = [&](int k) -> uint64_t {
+      if (mode == IMC_TALLY_FIXED) { long long v; memcpy(&v, &sc[k], 8); return (uint64_t)v; }
+      return (uint64_t)sc[k];
+    };
+    double lost;
+    if (mode == IMC_TALLY_FIXED) { long long v; memcpy(&v, &sc[RB_LOST], 8); lost = (double)v / fx_mul_lost; } else lost = sc[RB_LOST];
+    iterations += cnt(RB_SEG);
+    if (out) {
+      out->lostenergy = (double)P::from_d(lost);
+      out->segments = cnt(RB_SEG); out->segments_total = iterations; out->histories = (int64_t)cnt(RB_HIST);
+      out->n_census = (int64_t)cnt(RB_CENSUS); out->n_absorbed = (int64_t)cnt(RB_ABSORBED); out->n_escaped = (int64_t)cnt(RB_ESCAPED);
+      out->n_rw = (int64_t)cnt(RB_RW); out->n_errors = (int64_t)cnt(RB_ERRORS);
+      out->variant = variant; out->tally_mode = mode; out->kernel_ms = ms;
+    }
+    if (over) { err = "transport tape exhausted"; return IMC_ERR_TAPE; }
+    return IMC_OK;
+  }
+  int launch_rw(TrackArgs<P>& a, unsigned grid, size_t smem) {
+    k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    return IMC_OK;
+  }
+
+  // ---- Clean.clean ---------------------------------------------------------------------------
+  int clean(int64_t* n_alive) override {
+    IMC_RC(use_device());
+    if (n_part == 0) { if (n_alive) *n_alive = 0; return IMC_OK; }
+    long long blocks = (n_part + COMPACT_THREADS - 1) / COMPACT_THREADS;
+    IMC_CK(blk_cnt.ensure((size_t)blocks));
+    IMC_CK(scan_total.ensure(1));
+    Parts<P> src = pb[cur].view(), dst = pb[cur ^ 1].view();
+    k_alive_count<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, n_part, geom, blk_cnt.p);
+    k_scan_small<<<1, 1024, 0, stream>>>(blk_cnt.p, blocks, scan_total.p);
+    k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, dst, n_part, geom, blk_cnt.p);
+    IMC_CK(cudaGetLastError());
+    long long total = 0;
+    IMC_CK(cudaMemcpyAsync(&total, scan_total.p, sizeof total, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    n_part = total;
+    cur ^= 1;
+    if (n_alive) *n_alive = n_part;
+    return IMC_OK;
+  }
+
+  // ---- Tally.tally ---------------------------------------------------------------------------
+  int tally_local() override {
+    if (!have_mesh) { err = "tally before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    const int mode = red_fixed ? IMC_TALLY_FIXED : IMC_TALLY_ATOMIC;
+    IMC_CK(cudaMemsetAsync(red.p + rb_rad0(), 0, nc * sizeof(double), stream));
+    if (n_part == 0) return IMC_OK;
+    TallyArgs ta;
+    ta.mode = mode; ta.nacc = (int)nc; ta.g_acc = red.p + rb_rad0(); ta.g_fx = reinterpret_cast<long long*>(red.p) + rb_rad0();
+    if (mode == IMC_TALLY_FIXED && fx_mul_rad == 1) IMC_RC(prepare_fixed(ta));
+    ta.fx_mul = fx_mul_rad; ta.fx_mul_lost = fx_mul_lost; ta.sc0 = 0;
+    size_t smem = smem_for(mode, nc);
+    ta.use_smem = smem <= 48 * 1024 ? 1 : 0;
+    if (!ta.use_smem) smem = 0;
+    int blocks_per_sm = 2048 / TRACK_THREADS;
+    unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
+    k_census_tally<P><<<grid, TRACK_THREADS, smem, stream>>>(m, pb[cur].view(), n_part, ta);
+    IMC_CK(cudaGetLastError());
+    return IMC_OK;
+  }
+  int tally_finish(double t_, double dt_, imc_tally_stats* out) override {
+    if (!have_mesh) { err = "tally before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    const long long* fx = reinterpret_cast<const long long*>(red.p);
+    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>(red.p + rb_dep0(), fx + rb_dep0(), red_fixed, fx_mul_dep, nc * ns, energydep.p);
+    k_acc_to_field<P><<<grid_for(nc, 256), 256, 0, stream>>>(red.p + rb_rad0(), fx + rb_rad0(), red_fixed, fx_mul_rad, nc, radenergydens.p);
+    TallyScratch<P> s; s.q_dep = q_dep.p; s.q_tot = q_tot.p; s.q_rad = q_rad.p;
+    k_tally_finish<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, s, P::from_d(dt_), t_ == 0.0 ? 1 : 0, cfg.linearized, temp_wide ? 1 : 0);
+    IMC_CK(cudaGetLastError());
+    if (cfg.linearized && P::id != 2) temp_wide = true;
+    // per-plane Julia sums of (energydep .* vol) ./ scale, four planes per readback
+    std::vector<Cc> plane(ns);
+    for (int k0 = 0; k0 < ns; k0 += 4) {
+      int kn = std::min(4, ns - k0);
+      for (int k = 0; k < kn; ++k) IMC_RC(jl_sum(q_dep.p + nc * (k0 + k), nc, sums.p + 8 + k));
+      IMC_CK(cudaMemcpyAsync(plane.data() + k0, sums.p + 8, kn * sizeof(Cc), cudaMemcpyDeviceToHost, stream));
+      IMC_CK(cudaStreamSynchronize(stream));
+    }
+    N ted;
+    for (int k = 0; k < ns; ++k) ted = ted + N(plane[k]);                            // :51 / :55
+    totalenergydep = ted.d();
+    IMC_RC(jl_sum(nrg_inc.p, nc, sums.p + 12));
+    IMC_RC(jl_sum(q_tot.p, nc, sums.p + 13));
+    k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p);
+    IMC_RC(jl_sum(q_rad.p, nc, sums.p + 14));
+    double ninf = -INFINITY;
+    IMC_CK(cudaMemcpyAsync(d_max.p, &ninf, sizeof ninf, cudaMemcpyHostToDevice, stream));
+    IMC_CK(cudaMemsetAsync(d_flag.p, 0, sizeof(int), stream));
+    k_max_f64<<<sm_count * 2, 256, 0, stream>>>(temp.p, nc, d_max.p, d_flag.p);
+    IMC_CK(cudaGetLastError());
+    Cc h2[3]; double mx; int has_nan;
+    IMC_CK(cudaMemcpyAsync(h2, sums.p + 12, 3 * sizeof(Cc), cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaMemcpyAsync(&mx, d_max.p, sizeof mx, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaMemcpyAsync(&has_nan, d_flag.p, sizeof has_nan, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    rad_total_h = (double)h2[2];
+    if (out) {
+      out->totalenergydep = totalenergydep; out->energy_increase = (double)h2[0];
+      out->max_temp = has_nan ? NAN : mx; out->total_energy_density = (double)h2[1];
+    }
+    return IMC_OK;
+  }
+
+  // ---- EnergyCheck.energychecker ---------------------------------------------------------------
+  int energycheck(imc_energy_stats* out) override {
+    if (!have_mesh) { err = "energycheck before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p);
+    IMC_CK(cudaGetLastError());
+    IMC_RC(jl_sum(q_rad.p, nc, sums.p + 14));
+    Cc h; double lost_raw;
+    IMC_CK(cudaMemcpyAsync(&h, sums.p + 14, sizeof h, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaMemcpyAsync(&lost_raw, red.p + rb_sc0() + RB_LOST, sizeof lost_raw, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    double lost;
+    if (red_fixed) { long long v; memcpy(&v, &lost_raw, 8); lost = (double)v / fx_mul_lost; } else lost = lost_raw;
+    N radenergy(h), te = N::from_d(totalenergy), ted = N::from_d(totalenergydep), old = N::from_d(radenergyold), lo = N::from_d(lost);
+    N change = radenergy - old;
+    N e = (((te - ted) - change) - lo) / te;                                          // :34
+    if (out) { out->radenergy = radenergy.d(); out->radenergy_change = change.d(); out->lostenergy = lo.d(); out->energy_error = e.d(); }
+    radenergyold = radenergy.d();                                                     // :36
+    IMC_CK(cudaMemsetAsync(red.p + rb_sc0() + RB_LOST, 0, sizeof(double), stream));   // :37
+    return IMC_OK;
+  }
+
+  int reduce_buffer(void** ptr, int64_t* n, int32_t* is_int) override {
+    if (!have_mesh) { err = "reduce_buffer before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    IMC_CK(cudaStreamSynchronize(stream));  // the host's collective runs on another stream
+    *ptr = red.p; *n = red_n; *is_int = red_fixed ? 1 : 0;
+    return IMC_OK;
+  }
+
+  int get_field(int f, double* dst, int64_t n) override {
+    if (!have_mesh) { err = "get_field before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    const S* src = nullptr; long long len = nc;
+    switch (f) {
+      case IMC_FIELD_TEMP:
+        if (n != nc) { err = "get_field: size"; return IMC_ERR_ARG; }
+        IMC_CK(cudaMemcpyAsync(dst, temp.p, nc * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        IMC_CK(cudaStreamSynchronize(stream));
+        return IMC_OK;
+      case IMC_FIELD_FLECK: src = fleck.p; break;
+      case IMC_FIELD_BETA: src = beta.p; break;
+      case IMC_FIELD_BEE: src = bee.p; break;
+      case IMC_FIELD_SIGMA_A: src = sa.p; break;
+      case IMC_FIELD_SIGMA_S: src = ss.p; break;
+      case IMC_FIELD_ENERGYDEP: src = energydep.p; len = nc * ns; break;
+      case IMC_FIELD_EMITTEDENERGY: src = emittedenergy.p; len = nc * ns; break;
+      case IMC_FIELD_MATENERGYDENS: src = matenergydens.p; break;
+      case IMC_FIELD_RADENERGYDENS: src = radenergydens.p; break;
+      case IMC_FIELD_NRG_INC: src = nrg_inc.p; break;
+      default: err = "get_field: unknown field"; return IMC_ERR_ARG;
+    }
+    if (n != len) { err = "get_field: size"; return IMC_ERR_ARG; }
+    return download(src, (size_t)len, dst);
+  }
+  int set_state(const double* temp_, const double* mat, const double* rad) override {
+    if (!have_mesh) { err = "set_state before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    if (temp_) {
+      std::vector<double> h(nc);
+      for (long long i = 0; i < nc; ++i) h[i] = temp_wide ? temp_[i] : (double)P::from_d(temp_[i]);
+      IMC_CK(cudaMemcpy(temp.p, h.data(), nc * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    auto up = [&](DBuf<S>& b, const double* src) -> int {
+      std::vector<S> h(nc);
+      for (long long i = 0; i < nc; ++i) h[i] = P::pack(P::from_d(src[i]));
+      IMC_CK(cudaMemcpy(b.p, h.data(), nc * sizeof(S), cudaMemcpyHostToDevice));
+      return IMC_OK;
+    };
+    if (mat) IMC_RC(up(matenergydens, mat));
+    if (rad) IMC_RC(up(radenergydens, rad));
+    return IMC_OK;
+  }
+
+  int64_t num_particles() override { return n_part; }
+  int get_particles(double* slots, uint64_t* ids, int64_t capacity) override {
+    IMC_RC(use_device());
+    if (capacity < n_part) { err = "get_particles: capacity"; return IMC_ERR_ARG; }
+    if (n_part == 0) return IMC_OK;
+    int nsl = geom == 1 ? 9 : 10;
+    DBuf<double> d_slots; DBuf<unsigned long long> d_ids;
+    IMC_CK(d_slots.alloc((size_t)n_part * nsl, false));
+    IMC_CK(d_ids.alloc((size_t)n_part, false));
+    k_export_particles<P><<<grid_for(n_part, 256), 256, 0, stream>>>(m, pb[cur].view(), n_part, d_slots.p, d_ids.p);
+    IMC_CK(cudaGetLastError());
+    IMC_CK(cudaMemcpyAsync(slots, d_slots.p, (size_t)n_part * nsl * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (ids) IMC_CK(cudaMemcpyAsync(ids, d_ids.p, (size_t)n_part * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    return IMC_OK;
+  }
+  int set_particles(const double* slots, const uint64_t* ids, int64_t n) override {
+    if (!have_mesh) { err = "set_particles before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    if (n < 0) { err = "set_particles: n < 0"; return IMC_ERR_ARG; }
+    n_part = 0;
+    IMC_RC(ensure_capacity(n));
+    if (n == 0) return IMC_OK;
+    int nsl = geom == 1 ? 9 : 10;
+    DBuf<double> d_slots; DBuf<unsigned long long> d_ids;
+    IMC_CK(d_slots.alloc((size_t)n * nsl, false));
+    IMC_CK(cudaMemcpyAsync(d_slots.p, slots, (size_t)n * nsl * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (ids) { IMC_CK(d_ids.alloc((size_t)n, false)); IMC_CK(cudaMemcpyAsync(d_ids.p, ids, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream)); }
+    IMC_CK(cudaMemsetAsync(d_flag.p, 0, sizeof(int), stream));
+    k_import_particles<P><<<grid_for(n, 256), 256, 0, stream>>>(m, pb[cur].view(), n, d_slots.p, ids ? d_ids.p : nullptr, d_flag.p);
+    IMC_CK(cudaGetLastError());
+    int bad = 0;
+    IMC_CK(cudaMemcpyAsync(&bad, d_flag.p, sizeof bad, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    if (bad) { err = bad & 2 ? "set_particles: cell index out of range" : "set_particles: energyscale not in ENERGYSCALES"; return IMC_ERR_ARG; }
+    n_part = n;
+    return IMC_OK;
+  }
+  int set_transport_tape(const double* u, int nu, const double* e, int ne, int64_t slots) override {
+    IMC_RC(use_device());
+    if (nu < 0 || ne < 0 || slots < 0) { err = "tape: negative size"; return IMC_ERR_ARG; }
+    IMC_CK(tt_uni.alloc((size_t)nu * slots, false)); IMC_CK(tt_exp.alloc((size_t)ne * slots, false));
+    if ((size_t)nu * slots) IMC_CK(cudaMemcpy(tt_uni.p, u, (size_t)nu * slots * sizeof(double), cudaMemcpyHostToDevice));
+    if ((size_t)ne * slots) IMC_CK(cudaMemcpy(tt_exp.p, e, (size_t)ne * slots * sizeof(double), cudaMemcpyHostToDevice));
+    tt_nuni = nu; tt_nexp = ne; tt_slots = slots;
+    return IMC_OK;
+  }
+  int set_source_tape(const double* u, int nu, int64_t slots) override {
+    IMC_RC(use_device());
+    if (nu < 0 || slots < 0) { err = "tape: negative size"; return IMC_ERR_ARG; }
+    IMC_CK(st_uni.alloc((size_t)nu * slots, false));
+    if ((size_t)nu * slots) IMC_CK(cudaMemcpy(st_uni.p, u, (size_t)nu * slots * sizeof(double), cudaMemcpyHostToDevice));
+    st_nuni = nu; st_slots = slots;
+    return IMC_OK;
+  }
+  int get_outcomes(int32_t* ev, int32_t* nseg, int64_t capacity) override {
+    IMC_RC(use_device());
+    if (out_n == 0) { err = "no outcome record (population above 2^22 or no transport call yet)"; return IMC_ERR_STATE; }
+    if (capacity < out_n) { err = "get_outcomes: capacity"; return IMC_ERR_ARG; }
+    std::vector<signed char> h(out_n);
+    IMC_CK(cudaMemcpyAsync(h.data(), out_event.p, (size_t)out_n, cudaMemcpyDeviceToHost, stream));
+    if (nseg) IMC_CK(cudaMemcpyAsync(nseg, out_nseg.p, (size_t)out_n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    if (ev) for (long long i = 0; i < out_n; ++i) ev[i] = h[i];
+    return IMC_OK;
+  }
+};
+
+}  // namespace imc

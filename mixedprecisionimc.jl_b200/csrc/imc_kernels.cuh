@@ -1,0 +1,1035 @@
+// imc_kernels.cuh — the transport-step kernels, templated on the deck precision P (F16 / F32 / F64).
+//
+//   k_update          Update.update                 imc_update.jl:23-54          one thread per cell
+//   k_src_energies    Sourcing.sourcing energies    imc_sourcing.jl:56-107       one thread per cell / edge
+//   k_src_counts      particle counts per entry     imc_sourcing.jl:128-157,240-263
+//   k_src_emit        particle creation             imc_sourcing.jl:159-236,264-366  one thread per new particle
+//   k_track1d         Transport.MC                  imc_transport.jl:46-197      history-based, grid-stride
+//   k_track2d         Transport.MC2D                imc_transport.jl:515-720
+//   k_track1d_rw      Transport.MC_RW               imc_transport.jl:247-467
+//   k_alive_count / k_compact   Clean.clean         imc_clean.jl:13-18           stable stream compaction
+//   k_census_tally    Tally.tally census loop       imc_tally.jl:84-113
+//   k_tally_finish    Tally.tally per-cell update   imc_tally.jl:29-32,44-75
+//
+// Arithmetic is Num<P>: one rounding per Julia operation, Float64 where the reference leaks into
+// Float64.  Compiled with -fmad=false.  Particle state is structure-of-arrays.
+#pragma once
+#include "imc_device.cuh"
+
+namespace imc {
+
+constexpr int TRACK_THREADS = 256;
+
+// reduce-buffer scalar slots that follow [energydep Nc*Ns | radenergydens Nc]
+enum { RB_LOST = 0, RB_SEG, RB_HIST, RB_CENSUS, RB_ABSORBED, RB_ESCAPED, RB_RW, RB_ERRORS, RB_NSCALARS };
+
+template <class P> struct CellProp1 { typename P::store_t w, dx, sig_col, neg_saf; };   // w = dx*ds
+template <class P> struct CellProp2 { typename P::store_t sig_col, neg_saf; };
+
+template <class P>
+struct MeshDev {
+  using S = typename P::store_t;
+  using Cc = typename P::comp_t;
+  int geom, nx, ny, ns;
+  long long nc;
+  S *dx, *dy, *wx, *wy;
+  S *sa, *ss, *fleck, *beta, *bee, *sa_c, *sa_p, *ss_c, *ss_p, *sigma_static, *radsource;
+  double* temp;
+  S *matenergydens, *radenergydens, *nrg_inc, *energydep, *emittedenergy;
+  S* tsurf[4];  // bottom, top, left, right (1-D: left = [2][0], right = [3][0])
+  CellProp1<P>* cp1;
+  CellProp2<P>* cp2;
+  Cc scales[IMC_MAX_SCALES];
+  double scales_d[IMC_MAX_SCALES];
+  Cc ds, c, a, alpha;
+  int bc[4];
+};
+
+template <class P>
+struct Parts {
+  using S = typename P::store_t;
+  S *t, *x, *y, *mu, *E, *E0;
+  int *cx, *cy;             // 0-based cell indices (cy unused in 1-D)
+  int* origin;              // slot 1 of the 1-D layout (never read by the physics)
+  unsigned char* ks;        // energy-scale plane
+  unsigned long long* id;   // Philox counter
+};
+
+struct RngArgs {
+  int tape;
+  unsigned long long seed;
+  unsigned int step;
+  const double *uni, *ex;
+  int n_uni, n_exp;
+  long long stride;
+};
+
+// runtime-selected draw source (Philox or replay tape)
+template <class P>
+struct Draw {
+  int tape;
+  PhiloxDraw<P> ph;
+  TapeDraw<P> tp;
+  __device__ __forceinline__ void init(const RngArgs& r, unsigned long long id, unsigned int stream, long long slot) {
+    tape = r.tape;
+    if (tape) tp.init(r.uni, r.n_uni, r.ex, r.n_exp, (size_t)r.stride, (size_t)slot);
+    else ph.init(r.seed, id, r.step, stream);
+  }
+  __device__ __forceinline__ Num<P> uniform() { return tape ? tp.uniform() : ph.uniform(); }
+  __device__ __forceinline__ Num<P> randexp() { return tape ? tp.randexp() : ph.randexp(); }
+  __device__ __forceinline__ double randexp64() { return tape ? tp.randexp64() : ph.randexp64(); }
+  __device__ __forceinline__ bool over() const { return tape && tp.exhausted(); }
+};
+
+// ======================================================================================
+// Update.update
+// ======================================================================================
+template <class P>
+__global__ void k_update(MeshDev<P> m, typename P::comp_t dt_, int linearized, int marshak, int temp_wide) {
+  using N = Num<P>;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.nc) return;
+  N dt(dt_), a(m.a), one = N::from_d(1.0);
+  double t = m.temp[i];
+  N fourA = N::from_i(4) * a;
+  N val; double w = 0;
+  if (temp_wide) { w = fourA.d() * ((t * t) * t); val = N::from_d(w); }
+  else { N tt = N::from_d(t); val = fourA * ((tt * tt) * tt); }
+  N bee = N::load(m.bee, i), beta;
+  if (linearized) { bee = val; bee.store(m.bee, i); beta = one; }                    // :24-25
+  else beta = temp_wide ? N::from_d(w / bee.d()) : val / bee;                       // :27
+  beta.store(m.beta, i);
+  N sa_c = N::load(m.sa_c, i), sa_p = N::load(m.sa_p, i), ss_c = N::load(m.ss_c, i), ss_p = N::load(m.ss_p, i);
+  N sa, ss;
+  if (temp_wide) {
+    sa = N::from_d(sa_c.d() * MathDet::pow64(t, sa_p.d()));
+    if (m.geom == 1 && marshak) sa = N::from_d(((sa_c.d() / t) / t) / t);          // Q18
+    ss = N::from_d(ss_c.d() * MathDet::pow64(t, ss_p.d()));
+  } else {
+    N tt = N::from_d(t);
+    sa = sa_c * MathDet::pow<P>(tt, sa_p);
+    if (m.geom == 1 && marshak) sa = ((sa_c / tt) / tt) / tt;
+    ss = ss_c * MathDet::pow<P>(tt, ss_p);
+  }
+  sa.store(m.sa, i); ss.store(m.ss, i);
+  double vals[6] = {(double)m.ds, (double)m.alpha, beta.d(), (double)m.c, dt.d(), sa.d()};
+  double sc1 = 1.0;
+  N prod; int idx;
+  sorter_dev<P, 6>(vals, 6, &sc1, 1, &prod, &idx);
+  N f = N::from_d(1.0 / (1.0 + prod.d()));                                         // :39 / :52
+  f.store(m.fleck, i);
+  // per-cell quantities the tracking loop recomputes every segment in the reference, formed once
+  // here with the same operations and roundings (imc_transport.jl:87, :95)
+  N sig_col = sa * (one - f) + ss;
+  N neg_saf = (-sa) * f;
+  if (m.geom == 1) {
+    CellProp1<P> c;
+    N dx = N::load(m.dx, i);
+    c.w = P::pack((dx * N(m.ds)).v); c.dx = P::pack(dx.v); c.sig_col = P::pack(sig_col.v); c.neg_saf = P::pack(neg_saf.v);
+    m.cp1[i] = c;
+  } else {
+    CellProp2<P> c;
+    c.sig_col = P::pack(sig_col.v); c.neg_saf = P::pack(neg_saf.v);
+    m.cp2[i] = c;
+  }
+}
+
+// wx = dx*ds, wy = dy*ds (static)
+template <class P>
+__global__ void k_widths(MeshDev<P> m) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m.nx) (Num<P>::load(m.dx, i) * Num<P>(m.ds)).store(m.wx, i);
+  if (m.geom == 2 && i < m.ny) (Num<P>::load(m.dy, i) * Num<P>(m.ds)).store(m.wy, i);
+}
+
+// ======================================================================================
+// Sourcing
+// ======================================================================================
+// Entry layout.  1-D: [left, right, body(Nc), radsource(Nc)];  2-D: [bottom(Nx), top(Nx), left(Ny),
+// right(Ny), body(Nc), radsource(Nc)] — the reference's emission order (imc_sourcing.jl:161-236, :265-366).
+struct SrcLayout {
+  int geom, nx, ny;
+  long long nc;
+  __host__ __device__ long long n_surf() const { return geom == 1 ? 2 : 2ll * nx + 2ll * ny; }
+  __host__ __device__ long long body0() const { return n_surf(); }
+  __host__ __device__ long long rad0() const { return n_surf() + nc; }
+  __host__ __device__ long long total() const { return n_surf() + 2 * nc; }
+};
+
+template <class P>
+struct SrcArrays {
+  using S = typename P::store_t;
+  S* e;               // energy product per entry (already multiplied by its scale)
+  S* q;               // e / escale (for the totalenergy sums)
+  signed char* ks;    // chosen scale plane per entry (-1: sorter failed)
+  int* cnt;           // loop count per entry
+  S* nrg;             // energy per particle of the entry
+  S* q_em;            // emittedenergy ./ escale, [Nc x Ns], for the print at :75
+};
+
+struct SrcScalars {   // written by k_src_total, read by k_src_counts and by the host
+  double totalenergy; // value of T
+  double nsrc;        // n_source as a T value
+  double sums[8];
+  int bad;
+};
+
+template <class P>
+__global__ void k_src_energies(MeshDev<P> m, SrcArrays<P> s, SrcLayout L, typename P::comp_t dt_) {
+  using N = Num<P>;
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= L.n_surf() + L.nc) return;  // one thread per surface entry and per cell (body + radsource + emitted)
+  const double dt = (double)dt_, a = (double)m.a, c = (double)m.c, ds = (double)m.ds;
+  N prod; int idx;
+  if (e < L.n_surf()) {
+    double vals[9]; int n;
+    if (L.geom == 1) {                                                            // :60-61
+      double ts = Num<P>::load(m.tsurf[e == 0 ? 2 : 3], 0).d();
+      double v[9] = {a, c, ts, ts, ts, ts, dt, 0.25, 0.0};
+      for (int k = 0; k < 9; ++k) vals[k] = v[k];
+      n = 8;
+    } else {                                                                      // :86-93
+      int side; long long i = e;
+      if (i < L.nx) side = 0; else if ((i -= L.nx) < L.nx) side = 1; else if ((i -= L.nx) < L.ny) side = 2; else { i -= L.ny; side = 3; }
+      double ts = Num<P>::load(m.tsurf[side], i).d();
+      double width = side < 2 ? Num<P>::load(m.dx, i).d() : Num<P>::load(m.dy, i).d();
+      double v[9] = {a, c, ts, ts, ts, ts, width, dt, 0.25};
+      for (int k = 0; k < 9; ++k) vals[k] = v[k];
+      n = 9;
+    }
+    sorter_dev<P, 9>(vals, n, m.scales_d, m.ns, &prod, &idx);
+    prod.store(s.e, e); s.ks[e] = (signed char)idx;
+    (prod / (idx >= 0 ? N(m.scales[idx]) : N())).store(s.q, e);
+    return;
+  }
+  long long i = e - L.n_surf();
+  int xi = (int)(L.geom == 1 ? i : i % L.nx), yi = (int)(L.geom == 1 ? 0 : i / L.nx);
+  double t = m.temp[i];
+  double f = N::load(m.fleck, i).d(), sa = N::load(m.sa, i).d(), dx = N::load(m.dx, xi).d();
+  double dy = L.geom == 2 ? N::load(m.dy, yi).d() : 0.0;
+  double rs = N::load(m.radsource, i).d();
+  {                                                                               // body :67 / :102
+    double vals[12] = {f, sa, a, c, t, t, t, t, dx, dt, ds, 0.0};
+    int n = 11;
+    if (L.geom == 2) { vals[9] = dy; vals[10] = dt; vals[11] = ds; n = 12; }
+    sorter_dev<P, 12>(vals, n, m.scales_d, m.ns, &prod, &idx);
+    long long eb = L.body0() + i;
+    prod.store(s.e, eb); s.ks[eb] = (signed char)idx;
+    (prod / (idx >= 0 ? N(m.scales[idx]) : N())).store(s.q, eb);
+  }
+  {                                                                               // radiation source :68 / :103
+    double vals[4] = {rs, dx, dt, 0.0};
+    int n = 3;
+    if (L.geom == 2) { vals[2] = dy; vals[3] = dt; n = 4; }
+    sorter_dev<P, 4>(vals, n, m.scales_d, m.ns, &prod, &idx);
+    long long er = L.rad0() + i;
+    prod.store(s.e, er); s.ks[er] = (signed char)idx;
+    (prod / (idx >= 0 ? N(m.scales[idx]) : N())).store(s.q, er);
+  }
+  {                                                                               // emitted energy density :69-70 / :104-105
+    double vals[10] = {f, sa, a, c, t, t, t, t, dt, ds};
+    sorter_dev<P, 10>(vals, 10, m.scales_d, m.ns, &prod, &idx);
+    for (int k = 0; k < m.ns; ++k) {
+      N v = (k == idx) ? prod : N();
+      v.store(m.emittedenergy, i + m.nc * k);
+      (v / (idx >= 0 ? N(m.scales[idx]) : N())).store(s.q_em, i + m.nc * k);
+    }
+  }
+}
+
+// totalenergy and n_source (imc_sourcing.jl:121, :132-136); sums[] hold the jl_sum results:
+// 1-D: [body, rad]; 2-D: [bottom, top, left, right, body, rad]
+template <class P>
+__global__ void k_src_total(SrcArrays<P> s, SrcLayout L, const typename P::comp_t* sums, SrcScalars* out,
+                            long long n_input, long long n_census, long long n_max, typename P::comp_t cellmin, int wide_counts) {
+  using N = Num<P>;
+  N e_surface, body, rad;
+  if (L.geom == 1) {
+    e_surface = N::load(s.q, 0) + N::load(s.q, 1);                                // :64
+    body = N(sums[0]); rad = N(sums[1]);
+  } else {
+    e_surface = ((N(sums[0]) + N(sums[1])) + N(sums[2])) + N(sums[3]);            // :95
+    body = N(sums[4]); rad = N(sums[5]);
+  }
+  N total = (body + rad) + e_surface;                                             // :121
+  out->totalenergy = total.d();
+  auto toT = [&](long long v) { return wide_counts ? (double)(float)v : N::from_i(v).d(); };
+  double nsrc = toT(n_input);
+  if (n_input + n_census > n_max) {                                               // :134-136 (Q9)
+    long long cand = n_max - n_census - (L.geom == 1 ? 1 : 2) - 1;
+    double cand_t = toT(cand);
+    nsrc = (double)cellmin > cand_t ? (double)cellmin : cand_t;
+  }
+  out->nsrc = nsrc;
+  out->bad = 0;
+}
+
+template <class P>
+__device__ __forceinline__ long long count_of(Num<P> e, Num<P> escale, double nsrc, double total, Num<P> cellmin,
+                                               bool floor_cellmin, int wide_counts, int* bad) {
+  double r;
+  if (wide_counts) {  // Float16 decks with counts beyond Float16: Float32 arithmetic (Q10)
+    using W = Num<F32>;
+    W x = ((W((float)e.v) / W((float)escale.v)) * W::from_d(nsrc)) / W((float)total);
+    x = jl_round(x);
+    if (floor_cellmin) x = jl_max(x, W((float)cellmin.v));
+    r = x.d();
+  } else {
+    Num<P> x = ((e / escale) * Num<P>::from_d(nsrc)) / Num<P>::from_d(total);
+    x = jl_round(x);
+    if (floor_cellmin) x = jl_max(x, cellmin);
+    r = x.d();
+  }
+  if (!(r - r == 0.0) || r < 0 || r > 2147483647.0) { *bad = 1; return 0; }
+  return (long long)r;
+}
+template <class P>
+__device__ __forceinline__ Num<P> div_count(Num<P> e, long long n) {
+  if constexpr (P::id == 0) { if (n > 65504) return Num<P>(P::rnd(e.v / (float)n)); }
+  return e / Num<P>::from_i(n);
+}
+
+template <class P>
+__global__ void k_src_counts(MeshDev<P> m, SrcArrays<P> s, SrcLayout L, SrcScalars* sc, typename P::comp_t cellmin_, int wide_counts) {
+  using N = Num<P>;
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= L.total()) return;
+  N cellmin(cellmin_);
+  const double nsrc = sc->nsrc, total = sc->totalenergy;
+  int bad = 0;
+  N en = N::load(s.e, e);
+  int ks = s.ks[e];
+  N escale = ks >= 0 ? N(m.scales[ks]) : N();
+  long long cnt = 0, loops = 0;
+  if (e < L.n_surf()) {                                                            // :150-157 (1-D, no floor) / :240-263 (2-D)
+    if (en > N()) cnt = count_of(en, escale, nsrc, total, cellmin, L.geom == 2, wide_counts, &bad);
+    loops = cnt;
+  } else if (e < L.rad0()) {                                                       // :138-140
+    cnt = count_of(en, escale, nsrc, total, cellmin, true, wide_counts, &bad);
+    loops = cnt;
+  } else {                                                                         // :142-146
+    if (en > N()) cnt = count_of(en, escale, nsrc, total, cellmin, true, wide_counts, &bad);
+    loops = cnt;
+    if (L.geom == 2 && cnt > 0) {                                                  // Q6: the 2-D loop runs 1:n_body
+      long long eb = e - L.nc;
+      N enb = N::load(s.e, eb);
+      int ksb = s.ks[eb];
+      loops = count_of(enb, ksb >= 0 ? N(m.scales[ksb]) : N(), nsrc, total, cellmin, true, wide_counts, &bad);
+    }
+  }
+  if (ks < 0) bad = 1;
+  s.cnt[e] = (int)loops;
+  (cnt > 0 ? div_count(en, cnt) : N()).store(s.nrg, e);
+  if (bad) atomicOr(&sc->bad, 1);
+}
+
+template <class P>
+__global__ void k_src_emit(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
+                           long long base, long long n_local, int rank, int world, typename P::comp_t dt_,
+                           RngArgs rng, unsigned long long* over_flag) {
+  using N = Num<P>;
+  long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_local) return;
+  long long j = rank + l * (long long)world;  // global ordinal in the reference's emission order
+  // entry = last e with offs[e] <= j
+  long long lo = 0, hi = L.total() - 1;
+  while (lo < hi) {
+    long long mid = (lo + hi + 1) >> 1;
+    if (offs[mid] <= j) lo = mid; else hi = mid - 1;
+  }
+  long long e = lo;
+  N dt(dt_), ds(m.ds), one = N::from_d(1.0), two = N::from_i(2);
+  const double PI = 3.141592653589793;
+  unsigned long long id = ((unsigned long long)rng.step << 40) | (unsigned long long)j;
+  Draw<P> d; d.init(rng, id, STREAM_SOURCE, j);
+  N t, x, y, mu, nrg = N::load(s.nrg, e);
+  int cx = 0, cy = 0;
+  if (L.geom == 1) {
+    if (e < 2) {                                                                   // :161-189
+      bool left = e == 0;
+      cx = left ? 0 : (int)L.nc - 1;
+      x = N::from_d(((left ? 0.01 : 0.99) * N::load(m.dx, cx).d()) * ds.d());
+      mu = MathDet::sqrt<P>(d.uniform());
+      if (!left) mu = -mu;
+      while (mu == N()) { mu = MathDet::sqrt<P>(d.uniform()); if (!left) mu = -mu; }
+      t = dt * d.uniform();
+    } else {                                                                       // :193-236
+      cx = (int)((e - 2) % L.nc);
+      x = (N::load(m.dx, cx) * d.uniform()) * ds;
+      mu = one - two * d.uniform();
+      while (mu == N()) mu = one - two * d.uniform();
+      t = dt * d.uniform();
+    }
+  } else {
+    if (e < L.n_surf()) {                                                          // :265-323
+      int side; long long i = e;
+      if (i < L.nx) side = 0; else if ((i -= L.nx) < L.nx) side = 1; else if ((i -= L.nx) < L.ny) side = 2; else { i -= L.ny; side = 3; }
+      t = dt * d.uniform();
+      if (side == 0) {
+        cx = (int)i; cy = 0;
+        x = (N::load(m.dx, i) * d.uniform()) * ds;
+        y = N::from_d((0.001 * N::load(m.dy, 0).d()) * ds.d());
+        mu = N::from_d(PI) * d.uniform();
+      } else if (side == 1) {
+        cx = (int)i; cy = L.ny - 1;
+        x = (N::load(m.dx, i) * d.uniform()) * ds;
+        y = N::from_d((0.999 * N::load(m.dy, L.ny - 1).d()) * ds.d());
+        mu = N::from_d((-PI) * d.uniform().d());
+      } else {
+        cx = side == 2 ? 0 : L.nx - 1; cy = (int)i;
+        x = N::from_d(((side == 2 ? 0.001 : 0.999) * N::load(m.dx, cx).d()) * ds.d());
+        N dq7 = i < L.nx ? N::load(m.dx, i) : N::load(m.dy, i);                    // Q7: mesh.dx[j]
+        y = (dq7 * d.uniform()) * ds;
+        double u = d.uniform().d();
+        mu = N::from_d(PI * (side == 2 ? 0.5 - u : 0.5 + u));
+      }
+    } else {                                                                       // :326-366
+      long long c = (e - L.n_surf()) % L.nc;
+      cx = (int)(c % L.nx); cy = (int)(c / L.nx);
+      x = (N::load(m.dx, cx) * d.uniform()) * ds;
+      y = (N::load(m.dy, cy) * d.uniform()) * ds;
+      mu = N::from_d((2.0 * PI) * d.uniform().d());
+      t = dt * d.uniform();
+    }
+  }
+  long long o = base + l;
+  t.store(p.t, o); x.store(p.x, o); mu.store(p.mu, o); nrg.store(p.E, o); nrg.store(p.E0, o);
+  p.cx[o] = cx; p.ks[o] = (unsigned char)(s.ks[e] < 0 ? 0 : s.ks[e]); p.id[o] = id;
+  if (L.geom == 2) { y.store(p.y, o); p.cy[o] = cy; } else p.origin[o] = cx;
+  if (d.over()) atomicAdd(over_flag, 1ull);
+}
+
+// ======================================================================================
+// Tallies
+// ======================================================================================
+template <class P> struct AccType { using type = float; };
+template <> struct AccType<F64> { using type = double; };
+
+struct TallyArgs {
+  int mode;          // IMC_TALLY_ATOMIC or IMC_TALLY_FIXED (EXACT uses the record path)
+  int use_smem;      // block-private accumulators in shared memory (nacc of them)
+  int nacc;          // Nc * Ns
+  double* g_acc;     // reduce buffer viewed as Float64 (ATOMIC)
+  long long* g_fx;   // reduce buffer viewed as int64 (FIXED)
+  double fx_mul;     // 2^S for densities
+  double fx_mul_lost;
+  long long sc0;     // index of the first scalar slot in the reduce buffer
+};
+
+template <class P>
+struct Tally {
+  using A = typename AccType<P>::type;
+  const TallyArgs& a;
+  A* s_acc; unsigned long long* s_fx;
+  __device__ __forceinline__ Tally(const TallyArgs& a_, unsigned char* smem) : a(a_) {
+    s_acc = reinterpret_cast<A*>(smem); s_fx = reinterpret_cast<unsigned long long*>(smem);
+  }
+  __device__ __forceinline__ void zero() {
+    if (!a.use_smem) return;
+    if (a.mode == IMC_TALLY_FIXED) { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_fx[i] = 0ull; }
+    else { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_acc[i] = (A)0; }
+    __syncthreads();
+  }
+  __device__ __forceinline__ void add(long long idx, Num<P> v) {
+    if (a.mode == IMC_TALLY_FIXED) {
+      long long q = __double2ll_rn(v.d() * a.fx_mul);
+      if (a.use_smem) atomicAdd(&s_fx[idx], (unsigned long long)q);
+      else atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + idx, (unsigned long long)q);
+    } else {
+      if (a.use_smem) atomicAdd(&s_acc[idx], (A)v.v);
+      else atomicAdd(a.g_acc + idx, v.d());
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if (!a.use_smem) return;
+    __syncthreads();
+    if (a.mode == IMC_TALLY_FIXED) {
+      for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) { unsigned long long q = s_fx[i]; if (q) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + i, q); }
+    } else {
+      for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) { A q = s_acc[i]; if (q != (A)0) atomicAdd(a.g_acc + i, (double)q); }
+    }
+  }
+};
+
+// per-thread event counters + lost energy, reduced per warp and added to the reduce buffer
+struct Counters {
+  unsigned long long seg = 0, hist = 0, census = 0, absorbed = 0, escaped = 0, rw = 0, errors = 0;
+  double lost = 0; long long lost_fx = 0;
+  template <class P>
+  __device__ __forceinline__ void lose(const TallyArgs& a, Num<P> e_over_scale) {
+    if (a.mode == IMC_TALLY_FIXED) lost_fx += __double2ll_rn(e_over_scale.d() * a.fx_mul_lost);
+    else lost += e_over_scale.d();
+  }
+  __device__ __forceinline__ void commit(const TallyArgs& a) {
+    unsigned long long v[7] = {seg, hist, census, absorbed, escaped, rw, errors};
+    int lane = threadIdx.x & 31;
+    if (a.mode == IMC_TALLY_FIXED) {
+      unsigned long long* g = reinterpret_cast<unsigned long long*>(a.g_fx) + a.sc0;
+      unsigned long long l = warp_sum_u64((unsigned long long)lost_fx);
+      if (lane == 0 && l) atomicAdd(g + RB_LOST, l);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { unsigned long long s = warp_sum_u64(v[k]); if (lane == 0 && s) atomicAdd(g + RB_SEG + k, s); }
+    } else {
+      double* g = a.g_acc + a.sc0;
+      double l = warp_sum_f64(lost);
+      if (lane == 0 && l != 0.0) atomicAdd(g + RB_LOST, l);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { unsigned long long s = warp_sum_u64(v[k]); if (lane == 0 && s) atomicAdd(g + RB_SEG + k, (double)s); }
+    }
+  }
+};
+
+// ======================================================================================
+// Transport.MC — 1-D history-based tracking
+// ======================================================================================
+template <class P>
+struct TrackArgs {
+  MeshDev<P> m;
+  Parts<P> p;
+  long long n;
+  typename P::comp_t dt;
+  RngArgs rng;
+  TallyArgs tally;
+  signed char* out_event;  // optional per-particle outcome record (replay checks)
+  int* out_nseg;
+  unsigned long long* over_flag;
+  // random-walk tables (MC_RW)
+  const typename P::store_t *aVals, *ptVals;
+  int n_rw_table;
+};
+
+template <class P>
+__global__ void __launch_bounds__(TRACK_THREADS) k_track1d(TrackArgs<P> a) {
+  using N = Num<P>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Tally<P> tal(a.tally, smem);
+  tal.zero();
+  Counters cn;
+  const N one = N::from_d(1.0), two = N::from_i(2), zero;
+  const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
+  const int nc = (int)a.m.nc;
+  const bool reflect_l = a.m.bc[IMC_BC_LEFT] == IMC_REFLECT, reflect_r = a.m.bc[IMC_BC_RIGHT] == IMC_REFLECT;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
+    N E0 = N::load(a.p.E0, pi);
+    if (E0.v == (typename P::comp_t)-1) continue;  // flagged dead and not yet cleaned
+    N t = N::load(a.p.t, pi), x = N::load(a.p.x, pi), mu = N::load(a.p.mu, pi), E = N::load(a.p.E, pi);
+    int cell = a.p.cx[pi];
+    const int k = a.p.ks[pi];
+    const N escale(a.m.scales[k]);
+    const N minE = N::from_d(0.01 * E0.d());                                       // :61
+    const long long kbase = (long long)nc * k;
+    Draw<P> d; d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
+    int nseg = 0, ev = 0;
+    ++cn.hist;
+    while (true) {
+      ++nseg;                                                                       // :73
+      const CellProp1<P> cp = a.m.cp1[cell];
+      const N w(P::unpack(cp.w)), dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
+      N dist_b = mu > zero ? (w - x) / mu : nabs(x / mu);                           // :77-83
+      N dist_col = d.randexp() / sig_col;                                           // :87
+      N dist_cen = (c_light * (dt - t)) * ds;                                       // :89
+      N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                          // :92
+      N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
+      N newE = E * ex;                                                              // :95
+      if (is_nan(newE) || is_nan(dist)) ++cn.errors;
+      if (newE <= minE) {                                                           // :97-106
+        tal.add(kbase + cell, E / dx);
+        E0 = N::from_d(-1.0); ev = 1; ++cn.absorbed;
+        break;
+      }
+      tal.add(kbase + cell, (-(E / dx)) * em1);                                     // :110 / :120
+      x = x + mu * dist;                                                            // :124
+      t = t + (dist / ds) / c_light;                                                // :125
+      E = newE;                                                                     // :126
+      bool dead = false;
+      if (dist == dist_b) {                                                         // :130-170
+        if (mu > zero) {
+          if (cell == nc - 1) {
+            if (reflect_r) mu = -mu; else dead = true;
+          }
+          if (!dead) { cell += 1; x = zero; }
+        }
+        if (!dead && mu < zero) {
+          if (cell == 0) {
+            if (reflect_l) mu = -mu; else dead = true;
+          } else { cell -= 1; x = N::load(a.m.wx, cell); }
+        }
+      }
+      if (dead) { cn.lose<P>(a.tally, E / escale); E0 = N::from_d(-1.0); ev = 2; ++cn.escaped; break; }  // :141 / :160
+      if (dist == dist_col) {                                                       // :174-183
+        mu = zero;
+        while (mu == zero) mu = one - two * d.uniform();
+      }
+      if (dist == dist_cen) { t = zero; ev = 0; ++cn.census; break; }               // :185-193
+    }
+    cn.seg += (unsigned long long)nseg;
+    if (ev == 0) { t.store(a.p.t, pi); x.store(a.p.x, pi); mu.store(a.p.mu, pi); E.store(a.p.E, pi); a.p.cx[pi] = cell; }
+    else E0.store(a.p.E0, pi);  // dead: only the flag is written; the other slots stay stale (Q16)
+    if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = nseg; }
+    if (d.over()) atomicAdd(a.over_flag, 1ull);
+  }
+  tal.flush();
+  cn.commit(a.tally);
+}
+
+// ======================================================================================
+// Transport.MC2D — 2-D history-based tracking
+// ======================================================================================
+template <class P>
+__global__ void __launch_bounds__(TRACK_THREADS) k_track2d(TrackArgs<P> a) {
+  using N = Num<P>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Tally<P> tal(a.tally, smem);
+  tal.zero();
+  Counters cn;
+  const N one = N::from_d(1.0), zero;
+  const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
+  const int nx = a.m.nx, ny = a.m.ny;
+  const double TWO_PI = 2.0 * 3.141592653589793;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
+    N E = N::load(a.p.E, pi);
+    if (E.v == (typename P::comp_t)-1) continue;  // 2-D dead flag lives in the energy slot (Q16)
+    N E0 = N::load(a.p.E0, pi);
+    N t = N::load(a.p.t, pi), x = N::load(a.p.x, pi), y = N::load(a.p.y, pi), mu = N::load(a.p.mu, pi);
+    int xi = a.p.cx[pi], yi = a.p.cy[pi];
+    const int k = a.p.ks[pi];
+    const N escale(a.m.scales[k]);
+    const N minE = N::from_d(0.01 * E0.d());                                       // :531
+    const long long kbase = a.m.nc * k;
+    Draw<P> d; d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
+    int nseg = 0, ev = 0;
+    ++cn.hist;
+    N vx, vy;
+    MathDet::sincos<P>(mu, &vy, &vx);                                              // :534 (recomputed only when mu changes)
+    N dxc = N::load(a.m.dx, xi), dyc = N::load(a.m.dy, yi), wxc = N::load(a.m.wx, xi), wyc = N::load(a.m.wy, yi);
+    while (true) {
+      ++nseg;
+      const long long c = (long long)xi + (long long)nx * yi;
+      const CellProp2<P> cp = a.m.cp2[c];
+      const N sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
+      N dist_bx = vx > zero ? nabs((wxc - x) / vx) : nabs(x / vx);                  // :538-542
+      N dist_by = vy > zero ? nabs((wyc - y) / vy) : nabs(y / vy);                  // :544-548
+      N dist_b = is_nan(dist_bx) ? dist_by : is_nan(dist_by) ? dist_bx : jl_min(dist_bx, dist_by);  // :551-557
+      N dist_col = d.randexp() / sig_col;                                           // :561
+      N dist_cen = (c_light * (dt - t)) * ds;                                       // :569
+      N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                          // :571
+      if (is_nan(dist) || dist_col < zero) ++cn.errors;
+      N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
+      N newE = E * ex;                                                              // :580
+      if (newE <= minE) {                                                           // :586-595
+        tal.add(kbase + c, (E / dxc) / dyc);
+        E = N::from_d(-1.0); ev = 1; ++cn.absorbed;
+        break;
+      }
+      tal.add(kbase + c, ((-(E / dxc)) / dyc) * em1);                               // :599 / :607
+      x = x + dist * vx;                                                            // :615
+      y = y + dist * vy;                                                            // :616
+      t = t + (dist / ds) / c_light;                                                // :617
+      E = newE;                                                                     // :618
+      if (dist == dist_bx || dist == dist_by) {                                     // :621
+        int side = -1;
+        if (dist_bx < dist_by) {                                                    // :622
+          if (vx > zero) { if (xi == nx - 1) side = IMC_BC_RIGHT; else { xi += 1; x = zero; } }
+          else { if (xi == 0) side = IMC_BC_LEFT; else { xi -= 1; x = N::load(a.m.wx, xi); } }
+          if (side < 0) { dxc = N::load(a.m.dx, xi); wxc = N::load(a.m.wx, xi); }
+          else if (a.m.bc[side] == IMC_REFLECT) { mu = MathDet::atan2<P>(vy, -vx); MathDet::sincos<P>(mu, &vy, &vx); }  // :626-628
+        } else {
+          if (vy > zero) { if (yi == ny - 1) side = IMC_BC_TOP; else { yi += 1; y = zero; } }
+          else { if (yi == 0) side = IMC_BC_BOTTOM; else { yi -= 1; y = N::load(a.m.wy, yi); } }
+          if (side < 0) { dyc = N::load(a.m.dy, yi); wyc = N::load(a.m.wy, yi); }
+          else if (a.m.bc[side] == IMC_REFLECT) { mu = MathDet::atan2<P>(-vy, vx); MathDet::sincos<P>(mu, &vy, &vx); }  // :666-668
+        }
+        if (side >= 0 && a.m.bc[side] != IMC_REFLECT) {                             // VACUUM :629-636 ...
+          cn.lose<P>(a.tally, E / escale);
+          E = N::from_d(-1.0); ev = 2; ++cn.escaped;
+          break;
+        }
+        continue;                                                                   // :703 (Q15)
+      }
+      if (dist == dist_col) { mu = N::from_d(TWO_PI * d.uniform().d()); MathDet::sincos<P>(mu, &vy, &vx); }  // :706-710
+      if (dist == dist_cen) { t = zero; ev = 0; ++cn.census; break; }               // :712-717
+    }
+    cn.seg += (unsigned long long)nseg;
+    if (ev == 0) {
+      t.store(a.p.t, pi); x.store(a.p.x, pi); y.store(a.p.y, pi); mu.store(a.p.mu, pi); E.store(a.p.E, pi);
+      a.p.cx[pi] = xi; a.p.cy[pi] = yi;
+    } else E.store(a.p.E, pi);
+    if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = nseg; }
+    if (d.over()) atomicAdd(a.over_flag, 1ull);
+  }
+  tal.flush();
+  cn.commit(a.tally);
+}
+
+// ======================================================================================
+// Transport.MC_RW — 1-D tracking with random-walk acceleration
+// ======================================================================================
+// A value whose Julia type is T or Float64 at run time: MC_RW draws randexp() in Float64 and ignores
+// the distance scale, so position / time / energy are promoted to Float64 inside a history after the
+// first ordinary segment and only rounded to T on write-back (Q3).
+template <class P>
+struct DynD {
+  double v; bool wide;
+  __device__ __forceinline__ DynD() : v(0), wide(false) {}
+  __device__ __forceinline__ DynD(Num<P> x) : v(x.d()), wide(false) {}
+  static __device__ __forceinline__ DynD w(double x) { DynD r; r.v = x; r.wide = true; return r; }
+  __device__ __forceinline__ Num<P> narrow() const { return Num<P>::from_d(v); }
+};
+#define IMC_DYN_OP(name, op)                                                                         \
+  template <class P> __device__ __forceinline__ DynD<P> name(DynD<P> a, DynD<P> b) {                \
+    if (a.wide || b.wide) return DynD<P>::w(a.v op b.v);                                            \
+    return DynD<P>(a.narrow() op b.narrow());                                                        \
+  }
+IMC_DYN_OP(dyn_add, +)
+IMC_DYN_OP(dyn_sub, -)
+IMC_DYN_OP(dyn_mul, *)
+IMC_DYN_OP(dyn_div, /)
+#undef IMC_DYN_OP
+template <class P> __device__ __forceinline__ DynD<P> dyn_abs(DynD<P> a) { a.v = a.v < 0 ? -a.v : (a.v == 0 ? 0.0 : a.v); return a; }
+template <class P> __device__ __forceinline__ DynD<P> dyn_min(DynD<P> a, DynD<P> b) {
+  DynD<P> r; r.wide = a.wide || b.wide; r.v = jl_min(Num<F64>(a.v), Num<F64>(b.v)).v; return r;
+}
+
+// Transport.P_r (imc_transport.jl:734-754): 100-term series accumulated in Float64 (Q31).  Terms are
+// added in order; once exp() has underflowed to exactly 0 the remaining terms cannot change the sum.
+__device__ __forceinline__ double rw_P_r(double a) {
+  if (a == 0) return 1.0;
+  double Pr = 0.0;
+  for (int n = 1; n <= 100; ++n) {
+    double pin = 3.141592653589793 * (double)n;
+    double e = dm::exp_d(-a * (pin * pin));
+    if (e == 0.0) break;
+    Pr += (((n - 1) & 1) ? -1.0 : 1.0) * e * 2.0;
+  }
+  return Pr;
+}
+// Transport.bisection (imc_transport.jl:756-784), 1-based
+template <class P>
+__device__ __forceinline__ int rw_bisection(const typename P::store_t* arr, int n, double value) {
+  if (value < Num<P>::load(arr, 0).d()) return 1;
+  if (value > Num<P>::load(arr, n - 1).d()) return n;
+  int jl = 1, ju = n;
+  while (ju - jl > 1) {
+    int jm = (ju + jl) >> 1;
+    if (value >= Num<P>::load(arr, jm - 1).d()) jl = jm; else ju = jm;
+  }
+  if (value == Num<P>::load(arr, 0).d()) return 1;
+  if (value == Num<P>::load(arr, n - 1).d()) return n;
+  return jl;
+}
+
+template <class P>
+__global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
+  using N = Num<P>;
+  using D = DynD<P>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Tally<P> tal(a.tally, smem);
+  tal.zero();
+  Counters cn;
+  const N one = N::from_d(1.0), two = N::from_i(2), three = N::from_i(3), zero;
+  const N dt(a.dt), c_light(a.m.c);
+  const int nc = (int)a.m.nc;
+  const bool reflect_l = a.m.bc[IMC_BC_LEFT] == IMC_REFLECT, reflect_r = a.m.bc[IMC_BC_RIGHT] == IMC_REFLECT;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
+    N E0 = N::load(a.p.E0, pi);
+    if (E0.v == (typename P::comp_t)-1) continue;
+    D t(N::load(a.p.t, pi)), x(N::load(a.p.x, pi)), E(N::load(a.p.E, pi));
+    N mu = N::load(a.p.mu, pi);
+    int cell = a.p.cx[pi];
+    const int k = a.p.ks[pi];
+    const N escale(a.m.scales[k]);
+    const N minE = N::from_d(0.01 * E0.d());                                       // :262
+    const long long kbase = (long long)nc * k;
+    Draw<P> d; d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
+    int nseg = 0, ev = 0;
+    ++cn.hist;
+    while (true) {
+      ++nseg;                                                                       // :265
+      const CellProp1<P> cp = a.m.cp1[cell];
+      const N dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
+      D dist_b = mu > zero ? dyn_div(dyn_sub(D(dx), x), D(mu)) : dyn_abs(dyn_div(x, D(mu)));   // :269-275 (no distancescale)
+      double rex = d.randexp64();
+      D dist_col = D::w((rex < 0 ? -rex : rex) / sig_col.d());                      // :279 (Float64)
+      D dist_cen = dyn_mul(D(c_light), dyn_sub(D(dt), t));                          // :281
+      D dist = dyn_min(dyn_min(dist_b, dist_col), dist_cen);                        // :284
+      D R0 = dyn_min(dyn_abs(dyn_sub(D(dx), x)), dyn_abs(x));                       // :286
+      N inv_sigma = N::from_i(1) / N::load(a.m.sigma_static, cell);                 // 1/mesh.sigma[cellindex] (Q4)
+      if (R0.v > inv_sigma.d() && dist_col.v < R0.v) {                              // :289
+        ++cn.rw;
+        const N sa = N::load(a.m.sa, cell), f = N::load(a.m.fleck, cell);
+        N u = d.uniform();                                                          // :290
+        N Dc = c_light / ((three * sa) * (one - f));                                // :292
+        D aa = dyn_div(dyn_mul(D(Dc), D(dt)), dyn_mul(R0, R0));                     // :294
+        double Pr = rw_P_r(aa.v);                                                   // :296
+        double Pt = 1.0 - Pr;                                                       // :297
+        N lg = MathDet::log<P>(one - f);
+        N expo;
+        if (u.d() < Pt) {                                                           // :298
+          int ai = rw_bisection<P>(a.ptVals, a.n_rw_table, u.d());                  // :301
+          D tp = dyn_div(dyn_mul(D(N::load(a.aVals, ai - 1)), dyn_mul(R0, R0)), D(Dc));
+          N t_p = N::from_d(tp.v);                                                  // :303
+          expo = (((t_p * c_light) * (one - f)) * sa) / lg;                         // :306
+        } else {
+          (void)d.uniform();                                                        // u_prime :338
+          expo = (((c_light * (one - f)) * sa) * dt) / lg;                          // :346
+        }
+        // newenergy <= startenergy always holds (Q1): the random-walk step deposits and kills
+        N ex, em1; MathDet::exp_expm1<P>(expo, &ex, &em1);
+        D newE = dyn_mul(E, D(ex));
+        D depv = dyn_mul(dyn_mul(D(-one), dyn_div(E, D(dx))), D(em1));              // :317-320 / :352-356
+        tal.add(kbase + cell, N::from_d(depv.v));  // a Float64 deposit is converted on push! / setindex!
+        if (newE.v != newE.v) ++cn.errors;
+        E0 = N::from_d(-1.0); ev = 3; ++cn.absorbed;
+        break;
+      }
+      D newE = dyn_mul(E, D::w(dm::exp_d(neg_saf.d() * dist.v)));                   // :376 (Float64)
+      if (newE.v <= minE.d()) newE = D(zero);                                       // :377-379
+      D depv = dyn_sub(E, newE);                                                    // :383 / :385 (not / dx, Q2)
+      tal.add(kbase + cell, N::from_d(depv.v));
+      if (newE.v == 0.0) { E0 = N::from_d(-1.0); ev = 1; ++cn.absorbed; break; }    // :390-394
+      x = dyn_add(x, dyn_mul(D(mu), dist));                                         // :397
+      t = dyn_add(t, dyn_div(dist, D(c_light)));                                    // :398
+      E = newE;                                                                     // :399
+      bool dead = false;
+      if (dist.v == dist_b.v) {                                                     // :403-443
+        if (mu > zero) {
+          if (cell == nc - 1) { if (reflect_r) mu = -mu; else dead = true; }
+          if (!dead) { cell += 1; x = D(zero); }
+        }
+        if (!dead && mu < zero) {
+          if (cell == 0) { if (reflect_l) mu = -mu; else dead = true; }
+          else { cell -= 1; x = D(N::load(a.m.dx, cell)); }
+        }
+      }
+      if (dead) {                                                                   // :414 / :433
+        if (E.wide) { if (a.tally.mode == IMC_TALLY_FIXED) cn.lost_fx += __double2ll_rn((E.v / escale.d()) * a.tally.fx_mul_lost); else cn.lost += E.v / escale.d(); }
+        else cn.lose<P>(a.tally, E.narrow() / escale);
+        E0 = N::from_d(-1.0); ev = 2; ++cn.escaped;
+        break;
+      }
+      if (dist.v == dist_col.v) {                                                   // :446-453
+        mu = one - two * d.uniform();
+        while (mu == zero) mu = one - two * d.uniform();
+      }
+      if (dist.v == dist_cen.v) { ev = 0; ++cn.census; break; }                     // :455-463
+    }
+    cn.seg += (unsigned long long)nseg;
+    if (ev == 0) {
+      zero.store(a.p.t, pi); N::from_d(x.v).store(a.p.x, pi); mu.store(a.p.mu, pi); N::from_d(E.v).store(a.p.E, pi); a.p.cx[pi] = cell;
+    } else E0.store(a.p.E0, pi);
+    if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = nseg; }
+    if (d.over()) atomicAdd(a.over_flag, 1ull);
+  }
+  tal.flush();
+  cn.commit(a.tally);
+}
+
+// ======================================================================================
+// Clean.clean — stable compaction
+// ======================================================================================
+constexpr int COMPACT_THREADS = 512;
+
+template <class P>
+__device__ __forceinline__ bool particle_alive(const Parts<P>& p, long long i, int geom) {
+  // slot 8 == -1.0: startenergy in 1-D, energy in 2-D (imc_clean.jl:15, Q16)
+  return geom == 1 ? (P::unpack(p.E0[i]) != (typename P::comp_t)-1) : (P::unpack(p.E[i]) != (typename P::comp_t)-1);
+}
+
+template <class P>
+__global__ void k_alive_count(Parts<P> p, long long n, int geom, long long* __restrict__ block_counts) {
+  __shared__ int warp_cnt[COMPACT_THREADS / 32];
+  long long i = (long long)blockIdx.x * COMPACT_THREADS + threadIdx.x;
+  bool alive = i < n && particle_alive(p, i, geom);
+  unsigned b = __ballot_sync(IMC_FULL_MASK, alive);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < COMPACT_THREADS / 32; ++w) s += warp_cnt[w];
+    block_counts[blockIdx.x] = s;
+  }
+}
+
+template <class P>
+__global__ void k_compact(Parts<P> src, Parts<P> dst, long long n, int geom, const long long* __restrict__ block_offs) {
+  __shared__ int warp_cnt[COMPACT_THREADS / 32];
+  long long i = (long long)blockIdx.x * COMPACT_THREADS + threadIdx.x;
+  bool alive = i < n && particle_alive(src, i, geom);
+  unsigned b = __ballot_sync(IMC_FULL_MASK, alive);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[wid] = __popc(b);
+  __syncthreads();
+  if (!alive) return;
+  long long o = block_offs[blockIdx.x] + __popc(b & ((1u << lane) - 1));
+  for (int w = 0; w < wid; ++w) o += warp_cnt[w];
+  dst.t[o] = src.t[i]; dst.x[o] = src.x[i]; dst.mu[o] = src.mu[i]; dst.E[o] = src.E[i]; dst.E0[o] = src.E0[i];
+  dst.cx[o] = src.cx[i]; dst.ks[o] = src.ks[i]; dst.id[o] = src.id[i];
+  if (geom == 2) { dst.y[o] = src.y[i]; dst.cy[o] = src.cy[i]; } else dst.origin[o] = src.origin[i];
+}
+
+// ======================================================================================
+// Tally.tally
+// ======================================================================================
+// census radiation energy density: E / (dx [*dy] * scale) per surviving particle (imc_tally.jl:92, :106)
+template <class P>
+__global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Parts<P> p, long long n, TallyArgs ta) {
+  using N = Num<P>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Tally<P> tal(ta, smem);
+  tal.zero();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (!particle_alive(p, i, m.geom)) continue;
+    N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
+    int cx = p.cx[i];
+    if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale));
+    else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale)); }
+  }
+  tal.flush();
+}
+
+// reduce buffer -> energydep (T)
+template <class P>
+__global__ void k_acc_to_field(const double* g_acc, const long long* g_fx, int fixed, double fx_mul, long long n,
+                               typename P::store_t* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = fixed ? (double)g_fx[i] / fx_mul : g_acc[i];
+  Num<P>::from_d(v).store(out, i);
+}
+
+template <class P>
+struct TallyScratch {
+  typename P::store_t* q_dep;   // [Nc x Ns]  (energydep * vol) / scale
+  typename P::store_t* q_tot;   // [Nc]       matenergydens + radenergydens
+  typename P::store_t* q_rad;   // [Nc]       radenergydens * vol (energycheck)
+};
+
+template <class P>
+__global__ void k_tally_finish(MeshDev<P> m, TallyScratch<P> s, typename P::comp_t dt_, int t_is_zero, int linearized, int temp_wide) {
+  using N = Num<P>;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.nc) return;
+  N dt(dt_);
+  double t = m.temp[i];
+  N mat = N::load(m.matenergydens, i);
+  if (t_is_zero) {                                                                 // :29-32 (Q11)
+    double vals[10] = {N::load(m.fleck, i).d(), N::load(m.sa, i).d(), (double)m.a, (double)m.c, t, t, t, t, dt.d(), (double)m.ds};
+    double sc1 = 1.0; int idx;
+    sorter_dev<P, 10>(vals, 10, &sc1, 1, &mat, &idx);
+  }
+  int xi = (int)(m.geom == 1 ? i : i % m.nx), yi = (int)(m.geom == 1 ? 0 : i / m.nx);
+  N vol = m.geom == 1 ? N::load(m.dx, xi) : N::load(m.dx, xi) * N::load(m.dy, yi);
+  N inc;
+  for (int k = 0; k < m.ns; ++k) {                                                 // :47-57
+    N dep = N::load(m.energydep, i + m.nc * k), em = N::load(m.emittedenergy, i + m.nc * k), sc(m.scales[k]);
+    inc = inc + (dep - em) / sc;
+    ((dep * vol) / sc).store(s.q_dep, i + m.nc * k);
+  }
+  inc.store(m.nrg_inc, i);
+  mat = mat + inc;                                                                 // :68
+  mat.store(m.matenergydens, i);
+  if (linearized) t = MathDet::pow64(mat.d(), 0.25);                               // :72 (Q12)
+  else t = temp_wide ? t + (inc / N::load(m.bee, i)).d() : (N::from_d(t) + inc / N::load(m.bee, i)).d();  // :74
+  m.temp[i] = t;
+  (mat + N::load(m.radenergydens, i)).store(s.q_tot, i);
+}
+
+template <class P>
+__global__ void k_rad_energy(MeshDev<P> m, typename P::store_t* q_rad) {          // imc_energycheck.jl:24-29
+  using N = Num<P>;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.nc) return;
+  N r = N::load(m.radenergydens, i);
+  if (m.geom == 1) (r * N::load(m.dx, i)).store(q_rad, i);
+  else ((r * N::load(m.dx, i % m.nx)) * N::load(m.dy, i / m.nx)).store(q_rad, i);
+}
+
+// maximum(temp): NaN-propagating like Julia's maximum
+static __global__ void k_max_f64(const double* __restrict__ v, long long n, double* out, int* has_nan) {
+  double mx = -INFINITY; int nan = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double x = v[i];
+    if (x != x) nan = 1; else if (x > mx) mx = x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { double y = __shfl_xor_sync(IMC_FULL_MASK, mx, o); if (y > mx) mx = y; nan |= __shfl_xor_sync(IMC_FULL_MASK, nan, o); }
+  if ((threadIdx.x & 31) == 0) {
+    if (nan) atomicOr(has_nan, 1);
+    // atomic max on doubles through the ordered integer image
+    unsigned long long* addr = reinterpret_cast<unsigned long long*>(out);
+    unsigned long long old = *addr, assumed;
+    do {
+      assumed = old;
+      if (__longlong_as_double((long long)assumed) >= mx) break;
+      old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(mx));
+    } while (assumed != old);
+  }
+}
+
+// max particle energy (for the fixed-point scale)
+template <class P>
+__global__ void k_max_energy(Parts<P> p, long long n, double* out) {
+  double mx = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double e = (double)P::unpack(p.E[i]);
+    if (e > mx) mx = e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { double y = __shfl_xor_sync(IMC_FULL_MASK, mx, o); if (y > mx) mx = y; }
+  if ((threadIdx.x & 31) == 0 && mx > 0) {
+    unsigned long long* addr = reinterpret_cast<unsigned long long*>(out);
+    unsigned long long old = *addr, assumed;
+    do {
+      assumed = old;
+      if (__longlong_as_double((long long)assumed) >= mx) break;
+      old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(mx));
+    } while (assumed != old);
+  }
+}
+
+// particle SoA <-> reference slot layout (imc_get_particles / imc_set_particles)
+template <class P>
+__global__ void k_export_particles(MeshDev<P> m, Parts<P> p, long long n, double* slots, unsigned long long* ids) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  using N = Num<P>;
+  double scale = (double)m.scales[p.ks[i]];
+  if (m.geom == 1) {
+    double* s = slots + i * 9;
+    s[0] = (double)(p.origin[i] + 1); s[1] = N::load(p.t, i).d(); s[2] = (double)(p.cx[i] + 1); s[3] = N::load(p.x, i).d();
+    s[4] = N::load(p.mu, i).d(); s[5] = 1.0; s[6] = N::load(p.E, i).d(); s[7] = N::load(p.E0, i).d(); s[8] = scale;
+  } else {
+    double* s = slots + i * 10;
+    s[0] = N::load(p.t, i).d(); s[1] = (double)(p.cx[i] + 1); s[2] = (double)(p.cy[i] + 1); s[3] = N::load(p.x, i).d();
+    s[4] = N::load(p.y, i).d(); s[5] = N::load(p.mu, i).d(); s[6] = 1.0; s[7] = N::load(p.E, i).d(); s[8] = N::load(p.E0, i).d(); s[9] = scale;
+  }
+  if (ids) ids[i] = p.id[i];
+}
+template <class P>
+__global__ void k_import_particles(MeshDev<P> m, Parts<P> p, long long n, const double* slots, const unsigned long long* ids, int* bad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  using N = Num<P>;
+  const double* s = slots + i * (m.geom == 1 ? 9 : 10);
+  double scale = s[m.geom == 1 ? 8 : 9];
+  int ks = -1;
+  for (int k = 0; k < m.ns; ++k) if ((double)m.scales[k] == scale) { ks = k; break; }   // findfirst(isequal(scale), energyscales)
+  if (ks < 0) { atomicOr(bad, 1); ks = 0; }
+  p.ks[i] = (unsigned char)ks;
+  p.id[i] = ids ? ids[i] : (unsigned long long)i;
+  if (m.geom == 1) {
+    p.origin[i] = (int)s[0] - 1; N::from_d(s[1]).store(p.t, i); p.cx[i] = (int)s[2] - 1; N::from_d(s[3]).store(p.x, i);
+    N::from_d(s[4]).store(p.mu, i); N::from_d(s[6]).store(p.E, i); N::from_d(s[7]).store(p.E0, i);
+    if (p.cx[i] < 0 || p.cx[i] >= m.nx) atomicOr(bad, 2);
+  } else {
+    N::from_d(s[0]).store(p.t, i); p.cx[i] = (int)s[1] - 1; p.cy[i] = (int)s[2] - 1; N::from_d(s[3]).store(p.x, i);
+    N::from_d(s[4]).store(p.y, i); N::from_d(s[5]).store(p.mu, i); N::from_d(s[7]).store(p.E, i); N::from_d(s[8]).store(p.E0, i);
+    if (p.cx[i] < 0 || p.cx[i] >= m.nx || p.cy[i] < 0 || p.cy[i] >= m.ny) atomicOr(bad, 2);
+  }
+}
+
+}  // namespace imc

@@ -27,8 +27,9 @@ namespace imc {
 // ---------------------------------------------------------------------------------------
 // binary16 <-> float/double conversions (round-to-nearest-even, subnormals kept)
 // ---------------------------------------------------------------------------------------
+// Under nvcc (host and device passes) the cuda_fp16 conversions are used; under plain g++ (oracle) _Float16.
 IMC_HD float half_bits_to_float(uint16_t h) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
   return __half2float(__ushort_as_half(h));
 #else
   _Float16 x;
@@ -37,7 +38,7 @@ IMC_HD float half_bits_to_float(uint16_t h) {
 #endif
 }
 IMC_HD uint16_t float_to_half_bits(float f) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
   return __half_as_ushort(__float2half_rn(f));
 #else
   _Float16 x = (_Float16)f;
@@ -47,7 +48,7 @@ IMC_HD uint16_t float_to_half_bits(float f) {
 #endif
 }
 IMC_HD uint16_t double_to_half_bits(double d) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
   return __half_as_ushort(__double2half(d));
 #else
   _Float16 x = (_Float16)d;  // direct (single) rounding, like Julia's Float16(::Float64)
@@ -124,9 +125,16 @@ struct Num {
 };
 
 template <class P> IMC_HD bool is_nan(Num<P> a) { return a.v != a.v; }
-template <class P> IMC_HD bool is_inf(Num<P> a) { return a.v - a.v != a.v - a.v && a.v == a.v; }
+template <class P> IMC_HD bool is_inf(Num<P> a) { return a.v == a.v && a.v - a.v != a.v - a.v; }
 template <class P> IMC_HD Num<P> nabs(Num<P> a) { return Num<P>(a.v < 0 ? -a.v : (a.v == 0 ? (typename P::comp_t)0 : a.v)); }
 
+IMC_HD bool sign_bit(double x) {
+#if defined(__CUDA_ARCH__)
+  return (__double_as_longlong(x) < 0);
+#else
+  uint64_t u; memcpy(&u, &x, 8); return (u >> 63) != 0;
+#endif
+}
 // Julia's min(x, y) for floats: NaN-propagating; min(-0.0, 0.0) = -0.0.
 template <class P> IMC_HD Num<P> jl_min(Num<P> a, Num<P> b) {
   if (a.v != a.v) return a;
@@ -134,14 +142,14 @@ template <class P> IMC_HD Num<P> jl_min(Num<P> a, Num<P> b) {
   if (a.v < b.v) return a;
   if (b.v < a.v) return b;
   // equal (or +-0): prefer the one with the sign bit set
-  return Num<P>(signbit((double)a.v) ? a.v : b.v);
+  return Num<P>(sign_bit((double)a.v) ? a.v : b.v);
 }
 template <class P> IMC_HD Num<P> jl_max(Num<P> a, Num<P> b) {
   if (a.v != a.v) return a;
   if (b.v != b.v) return b;
   if (a.v > b.v) return a;
   if (b.v > a.v) return b;
-  return Num<P>(signbit((double)a.v) ? b.v : a.v);
+  return Num<P>(sign_bit((double)a.v) ? b.v : a.v);
 }
 
 // round(x) — Julia's default RoundNearest = ties to even.

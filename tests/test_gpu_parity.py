@@ -1,0 +1,173 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Per-particle state, event outcomes, segment counts and particle counts must be BIT-EXACT (both sides use
+the deterministic math header and the same Philox / tape draws).  Tallied fields are sums whose order
+differs (atomics vs the reference's sequential / pairwise order), so they are compared to a tolerance
+stated per precision: Float64 1e-11, Float32 2e-4, Float16 5e-2 relative to the field's max.
+"""
+import numpy as np
+import pytest
+
+from mpimc_b200 import decks, driver, lib
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"FLOAT64": 1e-11, "FLOAT32": 2e-4, "FLOAT16": 5e-2}
+
+
+def field_close(a, b, tol):
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return np.max(np.abs(a - b)) <= tol * scale
+
+
+def run_pair(inputs, gpu_lib, oracle_lib, steps, **cfg):
+    a = driver.setup(inputs, gpu_lib, **cfg)
+    b = driver.setup(inputs, oracle_lib, **{k: v for k, v in cfg.items() if k not in ("tally_mode", "track_mode")})
+    out = []
+    for _ in range(steps):
+        out.append((a.advance(), b.advance()))
+    return a, b, out
+
+
+def assert_step_parity(a, b, out, precision, check_fields=True):
+    for ra, rb in out:
+        for key in ("n_new_global", "n_new_local", "n_particles", "n_source"):
+            assert ra["source"][key] == rb["source"][key], (key, ra["source"], rb["source"])
+        assert ra["source"]["totalenergy"] == rb["source"]["totalenergy"]
+        for key in ("segments", "histories", "n_census", "n_absorbed", "n_escaped", "n_rw"):
+            assert ra["transport"][key] == rb["transport"][key], (key, ra["transport"], rb["transport"])
+    pa, ia = a.engine.particles()
+    pb, ib = b.engine.particles()
+    assert np.array_equal(ia, ib)
+    assert np.array_equal(pa, pb), f"max |diff| = {np.max(np.abs(pa - pb))}"
+    if check_fields:
+        tol = TOL[precision]
+        for name in ("fleck", "sigma_a", "emittedenergy"):
+            assert np.array_equal(a.engine.field(name), b.engine.field(name)) or field_close(a.engine.field(name), b.engine.field(name), tol), name
+        for name in ("energydep", "radenergydens", "matenergydens", "temp"):
+            fa, fb = a.engine.field(name), b.engine.field(name)
+            assert field_close(fa, fb, tol), (name, np.max(np.abs(fa - fb)), np.max(np.abs(fb)))
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32", "FLOAT16"])
+def test_suolson_steps_bit_exact(gpu_lib, oracle_lib, precision):
+    inputs = decks.suolson(precision=precision, n_input=3000, n_max=30000)
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=6)
+    assert_step_parity(a, b, out, precision)
+    assert out[-1][0]["source"]["n_particles"] > 10000
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32", "FLOAT16"])
+def test_crooked_pipe_steps_bit_exact(gpu_lib, oracle_lib, precision):
+    es = (1.0,) if precision != "FLOAT16" else (1024.0,)
+    inputs = decks.crooked_pipe(precision=precision, n_input=4000, n_max=60000, cellmin=1 if precision == "FLOAT16" else 2, energyscales=es)
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=4)
+    assert_step_parity(a, b, out, precision)
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32"])
+def test_small_2d_all_boundaries(gpu_lib, oracle_lib, precision):
+    for bcs in (("REFLECT", "VACUUM", "REFLECT", "REFLECT"), ("VACUUM", "REFLECT", "VACUUM", "VACUUM"), ("REFLECT",) * 4):
+        inputs = decks.small_2d(precision=precision, n_input=2000, bcs=bcs)
+        a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=3)
+        assert_step_parity(a, b, out, precision)
+        esc = sum(r[0]["transport"]["n_escaped"] for r in out)
+        assert (esc > 0) == ("VACUUM" in bcs)
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32"])
+def test_marshak_and_multiscale(gpu_lib, oracle_lib, precision):
+    a, b, out = run_pair(decks.marshak(precision=precision, n_input=3000, n_max=30000), gpu_lib, oracle_lib, steps=5)
+    assert_step_parity(a, b, out, precision)
+    a, b, out = run_pair(decks.nonuniform_1d(precision=precision, n_input=3000), gpu_lib, oracle_lib, steps=4)
+    assert_step_parity(a, b, out, precision)
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32", "FLOAT16"])
+def test_random_walk_bit_exact(gpu_lib, oracle_lib, precision):
+    inputs = decks.marshak(precision=precision, n_cells=64, nonuniform=True, randomwalk="TRUE", n_input=3000, n_max=30000, dx_min=2e-4)
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=5)
+    assert_step_parity(a, b, out, precision, check_fields=precision != "FLOAT16")
+    assert sum(r[0]["transport"]["n_rw"] for r in out) > 0
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32", "FLOAT16"])
+def test_replay_tape_1d(gpu_lib, oracle_lib, precision):
+    """Replay mode: both sides consume the same pre-drawn numbers for a fixed particle batch."""
+    rng = np.random.default_rng(7)
+    T = {"FLOAT64": np.float64, "FLOAT32": np.float32, "FLOAT16": np.float16}[precision]
+    inputs = decks.suolson(precision=precision, n_input=1000, n_max=50000)
+    n = 5000
+    a = driver.setup(inputs, gpu_lib, rng_mode=lib.RNG_TAPE)
+    b = driver.setup(inputs, oracle_lib, rng_mode=lib.RNG_TAPE)
+    bits = {np.float16: 11, np.float32: 24, np.float64: 53}[T]
+    uni = (rng.integers(0, 2 ** bits, size=(48, n)).astype(np.float64)) * 2.0 ** -bits
+    exps = rng.exponential(size=(48, n))
+    nc = a.mesh.nx
+    dx = float(a.mesh.dx[0])
+    slots = np.zeros((n, 9))
+    slots[:, 0] = slots[:, 2] = rng.integers(1, nc + 1, size=n)
+    slots[:, 1] = (rng.random(n) * 0.002).astype(T)
+    slots[:, 3] = (rng.random(n) * dx).astype(T)
+    mu = (1 - 2 * rng.random(n)).astype(T); mu[mu == 0] = 0.5
+    slots[:, 4] = mu; slots[:, 5] = 1.0
+    scale = float(np.atleast_1d(a.mesh.energyscales)[0])
+    slots[:, 6] = slots[:, 7] = (rng.random(n) * 0.01 * scale + 1e-3 * scale).astype(T); slots[:, 8] = scale
+    slots[:50, 2] = 1; slots[:50, 4] = -np.abs(slots[:50, 4])          # reflect at the left wall
+    slots[50:100, 2] = nc; slots[50:100, 4] = np.abs(slots[50:100, 4])  # escape through the right wall
+    for s in (a, b):
+        s.engine.update(0.002)
+        s.engine.set_particles(slots)
+        s.engine.set_transport_tape(uni, exps)
+    ra, rb = a.engine.transport(0.002, 0), b.engine.transport(0.002, 0)
+    for key in ("segments", "n_census", "n_absorbed", "n_escaped"):
+        assert ra[key] == rb[key]
+    eva, nsa = a.engine.outcomes(n)
+    evb, nsb = b.engine.outcomes(n)
+    assert np.array_equal(eva, evb) and np.array_equal(nsa, nsb)
+    assert ra["n_escaped"] > 0
+    pa, _ = a.engine.particles(); pb, _ = b.engine.particles()
+    alive = pb[:, 7] != -1.0
+    assert np.array_equal(pa[alive], pb[alive])
+    assert np.array_equal(pa[:, 7] == -1.0, ~alive)
+    assert a.engine.clean() == b.engine.clean() == int(alive.sum())
+    pa, _ = a.engine.particles(); pb, _ = b.engine.particles()
+    assert np.array_equal(pa, pb)
+
+
+def test_replay_tape_exhaustion_is_an_error(gpu_lib):
+    inputs = decks.suolson(precision="FLOAT64", n_input=100, n_max=1000)
+    a = driver.setup(inputs, gpu_lib, rng_mode=lib.RNG_TAPE)
+    a.engine.update(0.002)
+    slots = np.zeros((4, 9)); slots[:, 0] = slots[:, 2] = 5; slots[:, 3] = 0.005; slots[:, 4] = 0.3; slots[:, 5] = 1
+    slots[:, 6] = slots[:, 7] = 1.0; slots[:, 8] = 1.0
+    a.engine.set_particles(slots)
+    a.engine.set_transport_tape(np.full((1, 4), 0.25), np.full((1, 4), 1e-4))
+    with pytest.raises(lib.ImcError) as e:
+        a.engine.transport(0.002, 0)
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32"])
+def test_fixed_point_tally_is_order_free(gpu_lib, oracle_lib, precision):
+    """TALLY_FIXED: two runs give bit-identical fields, and they agree with the oracle to the tolerance."""
+    inputs = decks.crooked_pipe(precision=precision, n_input=4000, n_max=60000, cellmin=2)
+    runs = []
+    for _ in range(2):
+        a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=3, tally_mode=lib.TALLY_FIXED)
+        runs.append({k: a.engine.field(k) for k in ("energydep", "radenergydens", "temp")})
+        assert_step_parity(a, b, out, precision)
+    for k in runs[0]:
+        assert np.array_equal(runs[0][k], runs[1][k]), k
+
+
+def test_energy_conservation_and_clean_kat(gpu_lib):
+    sim = driver.setup(decks.suolson(precision="FLOAT64", n_input=5000, n_max=100000), gpu_lib)
+    for _ in range(10):
+        r = sim.advance()
+        assert abs(r["energy"]["energy_error"]) < 1e-9
+    # the reference's clean test (test/runtests.jl:78-87): a particle whose slot 8 is -1.0 is removed
+    slots = np.array([[1.0, 2e-4, 3.0, 4e-3, 0.5, 6.0, 7.0, -1.0, 1.0]])
+    sim.engine.set_particles(slots)
+    assert sim.engine.num_particles() == 1
+    assert sim.engine.clean() == 0
