@@ -61,7 +61,8 @@ def _scales(T, energyscales):
     return _arr(T, energyscales)
 
 
-def infinite_medium(precision="FLOAT32", n_input=10000, n_max=50000, pairwise="TRUE", seed=12345) -> Dict:
+def infinite_medium(precision="FLOAT32", n_input=10000, n_max=50000, pairwise="TRUE", seed=12345, randomwalk="FALSE",
+                    energyscales=(1.0,)) -> Dict:
     """src/inputs/InfiniteMedium.txt: equilibrium cv*T + a*T^4 = cv*T0  ->  T_eq = 0.98698."""
     T = _T(precision)
     d = _common("Infinite Medium", precision, seed, "1D")
@@ -75,8 +76,8 @@ def infinite_medium(precision="FLOAT32", n_input=10000, n_max=50000, pairwise="T
         "NINPUT": str(n_input), "NMAX": str(n_max), "CELLMIN": "1",
         "T_INIT": "1.00", "T_SURFACE_VALS": _arr(T, [0.0, 0.0]), "T_SURFACE_REGS": [""],
         "PHYS_C": "299.70", "PHYS_A": "0.01372016", "ALPHA": "1.0",
-        "LINEARIZED": "FALSE", "PAIRWISE": pairwise, "RANDOMWALK": "FALSE",
-        "ENERGYSCALES": ["1.0"], "DISTANCESCALE": "1",
+        "LINEARIZED": "FALSE", "PAIRWISE": pairwise, "RANDOMWALK": randomwalk,
+        "ENERGYSCALES": _scales(T, list(energyscales)), "DISTANCESCALE": "1",
     })
     return d
 
@@ -102,7 +103,7 @@ def graded_nodes_1d(length: float, n_cells: int, dx_min: float) -> np.ndarray:
 
 
 def marshak(precision="FLOAT64", n_cells=300, nonuniform=False, randomwalk="FALSE", n_input=10000, n_max=60000,
-            cellmin=5, pairwise="TRUE", seed=12345, dx_min=1e-5) -> Dict:
+            cellmin=5, pairwise="TRUE", seed=12345, dx_min=1e-5, energyscales=(1.0,)) -> Dict:
     """Marshak wave (src/inputs/MarshakWave.txt: UNIFORM, 300 cells, FLOAT64, RANDOMWALK FALSE).  BASELINE config 2
     is the derived deck: FLOAT32, 2048 graded cells, RANDOMWALK TRUE, NMAX 1e7."""
     T = _T(precision)
@@ -121,7 +122,7 @@ def marshak(precision="FLOAT64", n_cells=300, nonuniform=False, randomwalk="FALS
         "T_INIT": "0.01", "T_SURFACE_VALS": _arr(T, [1.0, 0.01]), "T_SURFACE_REGS": [""],
         "PHYS_C": "299.70", "PHYS_A": "0.01372016", "ALPHA": "1.0",
         "LINEARIZED": "FALSE", "PAIRWISE": pairwise, "RANDOMWALK": randomwalk,
-        "ENERGYSCALES": ["1.0"], "DISTANCESCALE": "1.0",
+        "ENERGYSCALES": _scales(T, list(energyscales)), "DISTANCESCALE": "1.0",
     })
     return d
 
@@ -152,18 +153,19 @@ def _graded_unit(n: int = 10, first: float = 1e-3, total: float = 0.1) -> np.nda
 def crooked_pipe_nodes(refine: int = 1):
     """(xnodes, ynodes) of the crooked-pipe mesh; refine = 1 reproduces the shipped 107 x 48 nodes (to the deck's
     5-6 printed digits), refine = k splits every shipped cell into k equal parts (interfaces stay on nodes)."""
-    unit = np.round(_graded_unit(), 5)
+    unit = _graded_unit()
 
-    def axis(length, refine_map):
+    def axis(length, refine_map, digits):
         nodes = set(np.round(np.arange(0, int(round(length * 10)) + 1) * 0.1, 10))
         for edge, side in refine_map.items():
+            u = np.round(unit, digits.get(edge, 5))  # the deck prints these offsets with 5 or 6 decimals
             if side == "left":
-                nodes.update(np.round(edge - unit, 10))
+                nodes.update(np.round(edge - u, 10))
             else:
-                nodes.update(np.round(edge + unit, 10))
+                nodes.update(np.round(edge + u, 10))
         return np.array(sorted(nodes))
 
-    xn, yn = axis(7.0, CP_X_REFINE), axis(2.0, CP_Y_REFINE)
+    xn, yn = axis(7.0, CP_X_REFINE, {}), axis(2.0, CP_Y_REFINE, {0.5: 6, 1.0: 6})
     if refine > 1:
         def split(n):
             parts = [np.linspace(n[i], n[i + 1], refine, endpoint=False) for i in range(len(n) - 1)]
