@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the IMC transport step (BASELINE.json metric: tracked particle-segments/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path — update -> source -> track -> clean -> tally -> energycheck — over
+the workload's particle population.  Workloads (synthetic decks from mixedprecisionimc.jl_b200/decks.py):
+
+  crookedpipe_f32   (default) CrookedPipe 2-D Float32 on the 4096 x 4096 graded mesh, 1.25e8 particles per GPU:
+                    BASELINE config 5 in its weak-scaling form, the configuration the north-star target is
+                    quoted on (1e9 particles over 8 GPUs).
+  crookedpipe_f64   BASELINE config 3 (1024 x 1024, Float64, 1e8 particles).
+  marshak_f32_rw    BASELINE config 2 (Marshak 1-D Float32, 2048 graded cells, RANDOMWALK, 1e7 particles).
+  suolson_f32       Su-Olson 1-D Float32 scaled to 1e8 particles (config 4 family).
+
+`value`  = whole-job segments/s with everything resident in HBM (all stages of the step timed).
+`e2e`    = the same through the host-buffer path a stateless drop-in shim uses: every step uploads the
+           material state (temp, matenergydens, radenergydens) from pinned host memory and downloads
+           the three fields the reference's host reads after the tally, inside the timed region.
+`roofline` = tracking kernel only: algorithmic bytes/segment x segments / CUDA-event time of
+           the kernel, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` = the oracle (C++ restatement of the reference, 1 thread like the reference) on a bounded
+           sample of the same workload.
+--impl reference times that oracle as the reference arm (Julia is not installable here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (deck factory kwargs, particles per GPU, bytes/segment params)
+    "crookedpipe_f32": dict(deck="crooked_pipe", precision="FLOAT32", mesh=(4096, 4096), particles=125_000_000, geom=2, s=4),
+    "crookedpipe_f64": dict(deck="crooked_pipe", precision="FLOAT64", mesh=(1024, 1024), particles=100_000_000, geom=2, s=8),
+    "marshak_f32_rw": dict(deck="marshak", precision="FLOAT32", mesh=(2048,), particles=10_000_000, geom=1, s=4),
+    "suolson_f32": dict(deck="suolson", precision="FLOAT32", mesh=(1000,), particles=100_000_000, geom=1, s=4),
+}
+
+
+def make_inputs(w: dict, particles: int, mesh):
+    from mpimc_b200 import decks
+    n_max = int(particles)
+    n_input = max(n_max // 2, 1)
+    if w["deck"] == "crooked_pipe":
+        return decks.crooked_pipe(precision=w["precision"], n_input=n_input, n_max=n_max, cellmin=10 if n_max >= 10 * mesh[0] * mesh[1] else 1,
+                                  mesh_cells=mesh, pairwise="FALSE")
+    if w["deck"] == "marshak":
+        return decks.marshak(precision=w["precision"], n_cells=mesh[0], nonuniform=True, randomwalk="TRUE", n_input=n_input,
+                             n_max=n_max, cellmin=5, pairwise="FALSE")
+    if w["deck"] == "suolson":
+        return decks.suolson(precision=w["precision"], n_input=n_input, n_max=n_max, pairwise="FALSE")
+    raise ValueError(w["deck"])
+
+
+def bytes_per_segment(geom: int, s: int, seg_per_hist: float) -> float:
+    """B = B_seg + B_hist / (segments per history); 64-bit particle id carried (+16)."""
+    if geom == 1:
+        return 6 * s + (2 * (5 * s + 5) + 16) / max(seg_per_hist, 1e-9)
+    return 7 * s + (2 * (6 * s + 9) + 16) / max(seg_per_hist, 1e-9)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 3 + k and s[3 + k] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_run(w, mesh, sample_particles: int, steps: int, warmup: int):
+    """Time the oracle (1 thread, like the reference) on a bounded sample of the workload."""
+    import __graft_entry__ as entry
+    from mpimc_b200 import driver, lib
+    if not os.path.exists(entry.ORACLE_LIB):
+        entry.build_oracle()
+    olib = lib.ImcLib(entry.ORACLE_LIB)
+    inputs = make_inputs(w, sample_particles, mesh)
+    sim = driver.setup(inputs, olib)
+    sim.save_history = False
+    for _ in range(warmup):
+        sim.advance()
+    seg = 0
+    hist = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = sim.advance()
+        seg += r["transport"]["segments"]
+        hist += r["transport"]["histories"]
+    dt = time.perf_counter() - t0
+    return seg / dt, dt, seg, hist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="crookedpipe_f32", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
+    ap.add_argument("--mesh", type=int, nargs="*", default=None, help="cells per axis (default: the workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tally", default="auto", choices=["auto", "atomic", "fixed"])
+    args = ap.parse_args()
+
+    w = WORKLOADS[args.workload]
+    mesh = tuple(args.mesh) if args.mesh else w["mesh"]
+    particles = args.particles or w["particles"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.workload}: {w['deck']} {w['precision']} mesh {'x'.join(map(str, mesh))}, "
+                          f"{particles} particles per GPU (NMAX), NINPUT = NMAX/2, PAIRWISE FALSE",
+              "mesh": list(mesh), "particles_per_gpu": particles, "precision": w["precision"],
+              "l2_policy": "inputs larger than L2 (particle state >> 126 MB); no explicit flush",
+              "tally_mode": args.tally, "tracking": "history-based, grid-stride, 256 threads/block"}
+
+    # ---------------------------------------------------------------- reference arm (CPU oracle)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = args.cpu_sample or 200_000
+        seg_s, dt, seg, hist = cpu_port_run(w, mesh if w["geom"] == 1 else (min(mesh[0], 1024), min(mesh[1], 1024)), sample,
+                                            max(1, min(args.steps, 3)), min(args.warmup, 1))
+        line = {"metric": "tracked particle-segments/sec", "value": seg_s, "unit": "segments/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, min(args.steps, 3)),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["precision"].lower().replace("float", "f"),
+                "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": seg_s, "unit": "segments/s", "cores": 1, "kind": "port",
+                                 "sample": f"oracle (C++ restatement of the Julia reference, single-threaded like it) on {sample} particles, "
+                                           f"mesh capped at 1024^2, {max(1, min(args.steps, 3))} steps, {seg} segments in {dt:.1f} s"},
+                "e2e": {"value": seg_s, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    from mpimc_b200 import driver, lib
+    from mpimc_b200 import dist as imc_dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the transport step has no CPU fallback (use --impl reference for the CPU oracle)")
+    if not os.path.exists(entry.LIB):
+        entry.build_cuda()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    glib = lib.ImcLib(entry.LIB)
+    tally_mode = {"auto": lib.TALLY_AUTO, "atomic": lib.TALLY_ATOMIC, "fixed": lib.TALLY_FIXED}[args.tally]
+    inputs = make_inputs(w, particles * world, mesh)  # NMAX / NINPUT are global; each rank emits its stripe
+    sim = driver.setup(inputs, glib, device=local_rank, rank=rank, world=world, tally_mode=tally_mode)
+    sim.save_history = False
+    eng = sim.engine
+    nc = eng.nc
+    dev = torch.device(f"cuda:{local_rank}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        if world > 1:
+            return imc_dist.advance_sharded(sim)
+        return sim.advance()
+
+    # pinned host buffers for the end-to-end path
+    pin = {k: torch.empty(nc, dtype=torch.float64).pin_memory().numpy() for k in ("temp", "matenergydens", "radenergydens")}
+
+    def step_e2e():
+        eng.set_state(temp=pin["temp"], matenergydens=pin["matenergydens"], radenergydens=pin["radenergydens"])  # H2D
+        r = step_resident()
+        for k in pin:                                                                                            # D2H
+            eng.field(k, out=pin[k])
+        return r
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches()
+    seg = hist = 0
+    kms = 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = step_resident()
+        seg += r["transport"]["segments"]; hist += r["transport"]["histories"]; kms += r["transport"]["kernel_ms"]
+    barrier()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = eng.kernel_launches() - l0
+    n_part = eng.num_particles()
+    # end-to-end: same steps through host buffers
+    for k in pin:
+        eng.field(k, out=pin[k])
+    barrier()
+    t1 = time.perf_counter()
+    seg_e = 0
+    for _ in range(args.steps):
+        r = step_e2e()
+        seg_e += r["transport"]["segments"]
+    barrier()
+    wall_e = time.perf_counter() - t1
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+    tot = torch.tensor([seg, hist, seg_e, n_part], dtype=torch.float64, device=dev)
+    mx = torch.tensor([wall, wall_e, kms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    seg_g, hist_g, seg_e_g, n_part_g = tot.tolist()
+    wall_g, wall_e_g, kms_g = mx.tolist()
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        sph = seg_g / max(hist_g, 1)
+        bps = bytes_per_segment(w["geom"], w["s"], sph)
+        # dominant kernel: tracking.  per launch: this rank's segments x bytes/segment over its event time
+        ach = (seg * bps) / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        line = {
+            "metric": "tracked particle-segments/sec", "value": seg_g / wall_g, "unit": "segments/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall_g / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": w["precision"].lower().replace("float", "f"), "data": "synthetic",
+            "config": config,
+            "histories_per_s": hist_g / wall_g, "segments_per_history": sph, "particles_resident": n_part_g,
+            "tracking_kernel_ms_per_step": kms_g / args.steps, "tracking_kernel_share_of_step": kms_g / (1e3 * wall_g),
+            "cuda_event_ms_per_step": ev0.elapsed_time(ev1) / args.steps,
+            "e2e": {"value": seg_e_g / wall_e_g, "unit": "segments/s", "h2d_bytes_per_step": 3 * nc * 8, "d2h_bytes_per_step": 3 * nc * 8,
+                    "ms_per_step": 1e3 * wall_e_g / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "kernel": "k_track2d" if w["geom"] == 2 else ("k_track1d_rw" if w["deck"] == "marshak" else "k_track1d"),
+                         "bytes_per_segment": bps, "peak_source": peak_src},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            sample = args.cpu_sample or 200_000
+            cmesh = mesh if w["geom"] == 1 else (min(mesh[0], 1024), min(mesh[1], 1024))
+            seg_s, dt, cseg, chist = cpu_port_run(w, cmesh, sample, 2, 1)
+            line["cpu_baseline"] = {"value": seg_s, "unit": "segments/s", "cores": 1, "kind": "port",
+                                    "sample": f"oracle (C++ restatement of the Julia reference, single-threaded like it) on {sample} particles, "
+                                              f"mesh {'x'.join(map(str, cmesh))}, 2 steps after 1 warm-up: {cseg} segments in {dt:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

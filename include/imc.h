@@ -216,6 +216,8 @@ int imc_set_state(imc_handle h, const double* temp, const double* matenergydens,
  * indices are 1-based as in Julia; a dead particle has slot 8 == -1.0.  ids (may be NULL) are the
  * engine's 64-bit particle ids (Philox counter). */
 int64_t imc_num_particles(imc_handle h);
+/* diagnostic: CUDA kernels launched by this engine since creation (0 for the oracle) */
+int64_t imc_kernel_launches(imc_handle h);
 int imc_get_particles(imc_handle h, double* slots, uint64_t* ids, int64_t capacity);
 int imc_set_particles(imc_handle h, const double* slots, const uint64_t* ids, int64_t n);
 

@@ -26,6 +26,7 @@ struct EngineBase {
   virtual int get_field(int, double*, int64_t) = 0;
   virtual int set_state(const double*, const double*, const double*) = 0;
   virtual int64_t num_particles() = 0;
+  virtual int64_t launches() = 0;
   virtual int get_particles(double*, uint64_t*, int64_t) = 0;
   virtual int set_particles(const double*, const uint64_t*, int64_t) = 0;
   virtual int set_transport_tape(const double*, int, const double*, int, int64_t) = 0;

@@ -120,6 +120,7 @@ struct EngineT : EngineBase {
   // host mirrors of the scalar state
   double totalenergy = 0, totalenergydep = 0, radenergyold = 0;
   uint64_t iterations = 0;
+  int64_t n_launch = 0;  // kernels launched by this engine (bench.py reports it as gpu_launches)
 
   explicit EngineT(const imc_config& c) : cfg(c) {
     geom = c.geometry; nx = c.nx; ny = geom == 2 ? c.ny : 1; ns = c.n_scales; nc = (long long)nx * ny;
@@ -159,11 +160,19 @@ struct EngineT : EngineBase {
     IMC_CK(cudaStreamSynchronize(stream));
     return IMC_OK;
   }
+  DBuf<double> stage;  // device staging for Float64 <-> T conversion at the ABI boundary
   int download(const S* src, size_t n, double* dst) {
-    std::vector<S> h(n);
-    IMC_CK(cudaMemcpyAsync(h.data(), src, n * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    IMC_CK(stage.ensure(n));
+    k_to_f64<P><<<grid_for((long long)n, 256), 256, 0, stream>>>(src, (long long)n, stage.p); ++n_launch;
+    IMC_CK(cudaMemcpyAsync(dst, stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
     IMC_CK(cudaStreamSynchronize(stream));
-    for (size_t i = 0; i < n; ++i) dst[i] = (double)P::unpack(h[i]);
+    return IMC_OK;
+  }
+  int upload_into(S* dst, const double* src, size_t n) {
+    IMC_CK(stage.ensure(n));
+    IMC_CK(cudaMemcpyAsync(stage.p, src, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    k_from_f64<P><<<grid_for((long long)n, 256), 256, 0, stream>>>(stage.p, (long long)n, dst); ++n_launch;
+    IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
   // Julia sum of q[0..n) into the device slot `out`
@@ -172,8 +181,8 @@ struct EngineT : EngineBase {
     size_t slots = (size_t)1 << depth;
     IMC_CK(jl_part.ensure(slots));
     IMC_CK(jl_valid.ensure(slots));
-    k_jlsum_leaves<P><<<grid_for((long long)slots, 128), 128, 0, stream>>>(q, n, depth, jl_part.p, jl_valid.p);
-    k_jlsum_fold<P><<<1, 1024, 0, stream>>>(jl_part.p, jl_valid.p, depth, out);
+    k_jlsum_leaves<P><<<grid_for((long long)slots, 128), 128, 0, stream>>>(q, n, depth, jl_part.p, jl_valid.p); ++n_launch;
+    k_jlsum_fold<P><<<1, 1024, 0, stream>>>(jl_part.p, jl_valid.p, depth, out); ++n_launch;
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
@@ -182,9 +191,9 @@ struct EngineT : EngineBase {
     long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     IMC_CK(scan_tiles.ensure((size_t)tiles));
     IMC_CK(scan_total.ensure(1));
-    k_scan_tiles<int><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(in, out, n, scan_tiles.p);
-    k_scan_small<<<1, 1024, 0, stream>>>(scan_tiles.p, tiles, scan_total.p);
-    k_scan_add<<<grid_for(n, 256), 256, 0, stream>>>(out, n, scan_tiles.p);
+    k_scan_tiles<int><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(in, out, n, scan_tiles.p); ++n_launch;
+    k_scan_small<<<1, 1024, 0, stream>>>(scan_tiles.p, tiles, scan_total.p); ++n_launch;
+    k_scan_add<<<grid_for(n, 256), 256, 0, stream>>>(out, n, scan_tiles.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
@@ -275,7 +284,7 @@ struct EngineT : EngineBase {
     for (int k = 0; k < IMC_MAX_SCALES; ++k) { m.scales[k] = k < ns ? P::from_d(cfg.energyscales[k]) : (Cc)1; m.scales_d[k] = (double)m.scales[k]; }
     m.ds = P::from_d(cfg.distancescale); m.c = P::from_d(cfg.phys_c); m.a = P::from_d(cfg.phys_a); m.alpha = P::from_d(cfg.alpha);
     for (int k = 0; k < 4; ++k) m.bc[k] = cfg.bc[k];
-    k_widths<P><<<grid_for(std::max(nx, ny), 256), 256, 0, stream>>>(m);
+    k_widths<P><<<grid_for(std::max(nx, ny), 256), 256, 0, stream>>>(m); ++n_launch;
     IMC_CK(cudaGetLastError());
     IMC_CK(cudaStreamSynchronize(stream));
     totalenergy = totalenergydep = radenergyold = 0;
@@ -318,7 +327,7 @@ struct EngineT : EngineBase {
   int update(double dt) override {
     if (!have_mesh) { err = "update before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
-    k_update<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, P::from_d(dt), cfg.linearized, cfg.marshak_quirk, temp_wide ? 1 : 0);
+    k_update<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, P::from_d(dt), cfg.linearized, cfg.marshak_quirk, temp_wide ? 1 : 0); ++n_launch;
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
@@ -329,7 +338,7 @@ struct EngineT : EngineBase {
     IMC_RC(use_device());
     Cc dt = P::from_d(dt_), cellmin = P::from_d(cellmin_);
     SrcArrays<P> s; s.e = src_e.p; s.q = src_q.p; s.ks = src_ks.p; s.cnt = src_cnt.p; s.nrg = src_nrg.p; s.q_em = src_qem.p;
-    k_src_energies<P><<<grid_for(L.n_surf() + nc, 128), 128, 0, stream>>>(m, s, L, dt);
+    k_src_energies<P><<<grid_for(L.n_surf() + nc, 128), 128, 0, stream>>>(m, s, L, dt); ++n_launch;
     IMC_CK(cudaGetLastError());
     // totalenergy sums in the reference's association order
     if (geom == 1) {
@@ -346,8 +355,8 @@ struct EngineT : EngineBase {
     IMC_RC(jl_sum(s.q_em, nc * ns, sums.p + 6));
     long long n_census = n_census_global >= 0 ? n_census_global : n_part;
     int wide_counts = (P::id == 0) && (std::max<int64_t>(n_input, cfg.n_max) > 65504);
-    k_src_total<P><<<1, 1, 0, stream>>>(s, L, sums.p, src_sc.p, n_input, n_census, cfg.n_max, cellmin, wide_counts);
-    k_src_counts<P><<<grid_for(L.total(), 256), 256, 0, stream>>>(m, s, L, src_sc.p, cellmin, wide_counts);
+    k_src_total<P><<<1, 1, 0, stream>>>(s, L, sums.p, src_sc.p, n_input, n_census, cfg.n_max, cellmin, wide_counts); ++n_launch;
+    k_src_counts<P><<<grid_for(L.total(), 256), 256, 0, stream>>>(m, s, L, src_sc.p, cellmin, wide_counts); ++n_launch;
     IMC_CK(cudaGetLastError());
     IMC_RC(scan_counts(s.cnt, src_offs.p, L.total()));
     SrcScalars hsc; long long total = 0; Cc h_emsum = 0;
@@ -362,7 +371,7 @@ struct EngineT : EngineBase {
     IMC_RC(ensure_capacity(n_part + n_local));
     if (n_local > 0) {
       IMC_CK(cudaMemsetAsync(over_flag.p, 0, sizeof(unsigned long long), stream));
-      k_src_emit<P><<<grid_for(n_local, 256), 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, n_part, n_local, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p);
+      k_src_emit<P><<<grid_for(n_local, 256), 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, n_part, n_local, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p); ++n_launch;
       IMC_CK(cudaGetLastError());
       unsigned long long over = 0;
       IMC_CK(cudaMemcpyAsync(&over, over_flag.p, sizeof over, cudaMemcpyDeviceToHost, stream));
@@ -415,7 +424,7 @@ struct EngineT : EngineBase {
     double tot = 2.0 * (rad_total_h + totalenergy) * max_scale;
     if (!(tot > 0)) {
       IMC_CK(cudaMemsetAsync(d_max.p, 0, sizeof(double), stream));
-      k_max_energy<P><<<sm_count * 4, 256, 0, stream>>>(pb[cur].view(), n_part, d_max.p);
+      k_max_energy<P><<<sm_count * 4, 256, 0, stream>>>(pb[cur].view(), n_part, d_max.p); ++n_launch;
       double maxE = 0;
       IMC_CK(cudaMemcpyAsync(&maxE, d_max.p, sizeof maxE, cudaMemcpyDeviceToHost, stream));
       IMC_CK(cudaStreamSynchronize(stream));
@@ -471,9 +480,10 @@ struct EngineT : EngineBase {
       if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / smem));
       unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
       IMC_CK(cudaEventRecord(ev0, stream));
-      if (geom == 1 && cfg.randomwalk) { IMC_RC(launch_rw(a, grid, smem)); }
+      if (geom == 1 && cfg.randomwalk) k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
       else if (geom == 1) k_track1d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
       else k_track2d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      ++n_launch;
       IMC_CK(cudaGetLastError());
       IMC_CK(cudaEventRecord(ev1, stream));
     }
@@ -501,10 +511,6 @@ struct EngineT : EngineBase {
     if (over) { err = "transport tape exhausted"; return IMC_ERR_TAPE; }
     return IMC_OK;
   }
-  int launch_rw(TrackArgs<P>& a, unsigned grid, size_t smem) {
-    k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
-    return IMC_OK;
-  }
 
   // ---- Clean.clean ---------------------------------------------------------------------------
   int clean(int64_t* n_alive) override {
@@ -514,9 +520,9 @@ struct EngineT : EngineBase {
     IMC_CK(blk_cnt.ensure((size_t)blocks));
     IMC_CK(scan_total.ensure(1));
     Parts<P> src = pb[cur].view(), dst = pb[cur ^ 1].view();
-    k_alive_count<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, n_part, geom, blk_cnt.p);
-    k_scan_small<<<1, 1024, 0, stream>>>(blk_cnt.p, blocks, scan_total.p);
-    k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, dst, n_part, geom, blk_cnt.p);
+    k_alive_count<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, n_part, geom, blk_cnt.p); ++n_launch;
+    k_scan_small<<<1, 1024, 0, stream>>>(blk_cnt.p, blocks, scan_total.p); ++n_launch;
+    k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, dst, n_part, geom, blk_cnt.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     long long total = 0;
     IMC_CK(cudaMemcpyAsync(&total, scan_total.p, sizeof total, cudaMemcpyDeviceToHost, stream));
@@ -543,7 +549,7 @@ struct EngineT : EngineBase {
     if (!ta.use_smem) smem = 0;
     int blocks_per_sm = 2048 / TRACK_THREADS;
     unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
-    k_census_tally<P><<<grid, TRACK_THREADS, smem, stream>>>(m, pb[cur].view(), n_part, ta);
+    k_census_tally<P><<<grid, TRACK_THREADS, smem, stream>>>(m, pb[cur].view(), n_part, ta); ++n_launch;
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
@@ -551,10 +557,10 @@ struct EngineT : EngineBase {
     if (!have_mesh) { err = "tally before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     const long long* fx = reinterpret_cast<const long long*>(red.p);
-    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>(red.p + rb_dep0(), fx + rb_dep0(), red_fixed, fx_mul_dep, nc * ns, energydep.p);
-    k_acc_to_field<P><<<grid_for(nc, 256), 256, 0, stream>>>(red.p + rb_rad0(), fx + rb_rad0(), red_fixed, fx_mul_rad, nc, radenergydens.p);
+    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>(red.p + rb_dep0(), fx + rb_dep0(), red_fixed, fx_mul_dep, nc * ns, energydep.p); ++n_launch;
+    k_acc_to_field<P><<<grid_for(nc, 256), 256, 0, stream>>>(red.p + rb_rad0(), fx + rb_rad0(), red_fixed, fx_mul_rad, nc, radenergydens.p); ++n_launch;
     TallyScratch<P> s; s.q_dep = q_dep.p; s.q_tot = q_tot.p; s.q_rad = q_rad.p;
-    k_tally_finish<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, s, P::from_d(dt_), t_ == 0.0 ? 1 : 0, cfg.linearized, temp_wide ? 1 : 0);
+    k_tally_finish<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, s, P::from_d(dt_), t_ == 0.0 ? 1 : 0, cfg.linearized, temp_wide ? 1 : 0); ++n_launch;
     IMC_CK(cudaGetLastError());
     if (cfg.linearized && P::id != 2) temp_wide = true;
     // per-plane Julia sums of (energydep .* vol) ./ scale, four planes per readback
@@ -570,12 +576,12 @@ struct EngineT : EngineBase {
     totalenergydep = ted.d();
     IMC_RC(jl_sum(nrg_inc.p, nc, sums.p + 12));
     IMC_RC(jl_sum(q_tot.p, nc, sums.p + 13));
-    k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p);
+    k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p); ++n_launch;
     IMC_RC(jl_sum(q_rad.p, nc, sums.p + 14));
     double ninf = -INFINITY;
     IMC_CK(cudaMemcpyAsync(d_max.p, &ninf, sizeof ninf, cudaMemcpyHostToDevice, stream));
     IMC_CK(cudaMemsetAsync(d_flag.p, 0, sizeof(int), stream));
-    k_max_f64<<<sm_count * 2, 256, 0, stream>>>(temp.p, nc, d_max.p, d_flag.p);
+    k_max_f64<<<sm_count * 2, 256, 0, stream>>>(temp.p, nc, d_max.p, d_flag.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     Cc h2[3]; double mx; int has_nan;
     IMC_CK(cudaMemcpyAsync(h2, sums.p + 12, 3 * sizeof(Cc), cudaMemcpyDeviceToHost, stream));
@@ -594,7 +600,7 @@ struct EngineT : EngineBase {
   int energycheck(imc_energy_stats* out) override {
     if (!have_mesh) { err = "energycheck before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
-    k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p);
+    k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     IMC_RC(jl_sum(q_rad.p, nc, sums.p + 14));
     Cc h; double lost_raw;
@@ -649,22 +655,21 @@ struct EngineT : EngineBase {
     if (!have_mesh) { err = "set_state before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     if (temp_) {
-      std::vector<double> h(nc);
-      for (long long i = 0; i < nc; ++i) h[i] = temp_wide ? temp_[i] : (double)P::from_d(temp_[i]);
-      IMC_CK(cudaMemcpy(temp.p, h.data(), nc * sizeof(double), cudaMemcpyHostToDevice));
+      if (temp_wide) IMC_CK(cudaMemcpyAsync(temp.p, temp_, nc * sizeof(double), cudaMemcpyHostToDevice, stream));
+      else {  // round through T, keep the Float64 image
+        IMC_CK(stage.ensure((size_t)nc));
+        IMC_CK(cudaMemcpyAsync(stage.p, temp_, nc * sizeof(double), cudaMemcpyHostToDevice, stream));
+        k_round_f64<P><<<grid_for(nc, 256), 256, 0, stream>>>(stage.p, nc, temp.p); ++n_launch;
+      }
     }
-    auto up = [&](DBuf<S>& b, const double* src) -> int {
-      std::vector<S> h(nc);
-      for (long long i = 0; i < nc; ++i) h[i] = P::pack(P::from_d(src[i]));
-      IMC_CK(cudaMemcpy(b.p, h.data(), nc * sizeof(S), cudaMemcpyHostToDevice));
-      return IMC_OK;
-    };
-    if (mat) IMC_RC(up(matenergydens, mat));
-    if (rad) IMC_RC(up(radenergydens, rad));
+    if (mat) IMC_RC(upload_into(matenergydens.p, mat, (size_t)nc));
+    if (rad) IMC_RC(upload_into(radenergydens.p, rad, (size_t)nc));
+    IMC_CK(cudaStreamSynchronize(stream));
     return IMC_OK;
   }
 
   int64_t num_particles() override { return n_part; }
+  int64_t launches() override { return n_launch; }
   int get_particles(double* slots, uint64_t* ids, int64_t capacity) override {
     IMC_RC(use_device());
     if (capacity < n_part) { err = "get_particles: capacity"; return IMC_ERR_ARG; }
@@ -673,7 +678,7 @@ struct EngineT : EngineBase {
     DBuf<double> d_slots; DBuf<unsigned long long> d_ids;
     IMC_CK(d_slots.alloc((size_t)n_part * nsl, false));
     IMC_CK(d_ids.alloc((size_t)n_part, false));
-    k_export_particles<P><<<grid_for(n_part, 256), 256, 0, stream>>>(m, pb[cur].view(), n_part, d_slots.p, d_ids.p);
+    k_export_particles<P><<<grid_for(n_part, 256), 256, 0, stream>>>(m, pb[cur].view(), n_part, d_slots.p, d_ids.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     IMC_CK(cudaMemcpyAsync(slots, d_slots.p, (size_t)n_part * nsl * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (ids) IMC_CK(cudaMemcpyAsync(ids, d_ids.p, (size_t)n_part * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
@@ -693,7 +698,7 @@ struct EngineT : EngineBase {
     IMC_CK(cudaMemcpyAsync(d_slots.p, slots, (size_t)n * nsl * sizeof(double), cudaMemcpyHostToDevice, stream));
     if (ids) { IMC_CK(d_ids.alloc((size_t)n, false)); IMC_CK(cudaMemcpyAsync(d_ids.p, ids, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream)); }
     IMC_CK(cudaMemsetAsync(d_flag.p, 0, sizeof(int), stream));
-    k_import_particles<P><<<grid_for(n, 256), 256, 0, stream>>>(m, pb[cur].view(), n, d_slots.p, ids ? d_ids.p : nullptr, d_flag.p);
+    k_import_particles<P><<<grid_for(n, 256), 256, 0, stream>>>(m, pb[cur].view(), n, d_slots.p, ids ? d_ids.p : nullptr, d_flag.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     int bad = 0;
     IMC_CK(cudaMemcpyAsync(&bad, d_flag.p, sizeof bad, cudaMemcpyDeviceToHost, stream));

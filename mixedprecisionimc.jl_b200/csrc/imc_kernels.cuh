@@ -991,6 +991,22 @@ __global__ void k_max_energy(Parts<P> p, long long n, double* out) {
   }
 }
 
+template <class P>
+__global__ void k_to_f64(const typename P::store_t* __restrict__ src, long long n, double* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)P::unpack(src[i]);
+}
+template <class P>
+__global__ void k_from_f64(const double* __restrict__ src, long long n, typename P::store_t* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = P::pack(P::from_d(src[i]));
+}
+template <class P>
+__global__ void k_round_f64(const double* __restrict__ src, long long n, double* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)P::from_d(src[i]);
+}
+
 // particle SoA <-> reference slot layout (imc_get_particles / imc_set_particles)
 template <class P>
 __global__ void k_export_particles(MeshDev<P> m, Parts<P> p, long long n, double* slots, unsigned long long* ids) {

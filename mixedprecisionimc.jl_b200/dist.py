@@ -1,0 +1,64 @@
+"""Particle-sharded multi-GPU time step: one process per GPU, torch.distributed for the plumbing.
+
+The transport step shards by particle: every rank holds the whole mesh, emits the
+new-particle ordinals j with j % world == rank, tracks and cleans its own slice, and the per-cell tallies
+are combined by ONE all-reduce per time step over the engine's reduce buffer
+[energydep | radenergydens | lostenergy | counters]; the per-cell update that follows is replicated, so
+every rank ends the step with identical temperature / Fleck fields.  The census count needed by the NMAX
+cap (imc_sourcing.jl:133-136) is a second, scalar all-reduce.
+
+Backends: NCCL over NVLink on the GPU box (the reduce buffer is wrapped zero-copy as a CUDA tensor);
+gloo on CPU for tests with the oracle (the reduce buffer is host memory).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import driver as _driver
+from . import lib as _lib
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device pointer."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def reduce_buffer_tensor(engine: _lib.Engine) -> torch.Tensor:
+    ptr, n, is_int = engine.reduce_buffer()
+    if engine.lib.backend.startswith("cuda"):
+        return torch.as_tensor(_DevArray(ptr, n, "<i8" if is_int else "<f8"), device=f"cuda:{engine.cfg.device}")
+    ctype = C.c_int64 if is_int else C.c_double
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+    return torch.from_numpy(arr)
+
+
+def advance_sharded(sim: _driver.Simulation, group=None) -> dict:
+    """One iteration of the reference's while loop (MixedPrecisionIMC.jl:136-152) on a particle shard."""
+    inputs, mesh, sv, parts = sim.inputs, sim.mesh, sim.simvars, sim.particles
+    eng = mesh.engine
+    on_gpu = eng.lib.backend.startswith("cuda")
+    rec = {"t": float(sv.t), "dt": float(sv.dt), "step": sv.step}
+    _driver.Update.update(inputs, mesh, sv)
+    cnt = torch.tensor([eng.num_particles()], dtype=torch.int64, device=f"cuda:{eng.cfg.device}" if on_gpu else "cpu")
+    dist.all_reduce(cnt, group=group)
+    rec["source"] = _driver.Sourcing.sourcing(mesh, sv, parts, n_census_global=int(cnt.item()))
+    rec["transport"] = eng.transport(float(sv.dt), sv.step)
+    _driver.Clean.clean(parts)
+    eng.tally_local()
+    buf = reduce_buffer_tensor(eng)
+    dist.all_reduce(buf, group=group)
+    if on_gpu:
+        torch.cuda.current_stream().synchronize()
+    rec["tally"] = eng.tally_finish(float(sv.t), float(sv.dt))
+    rec["energy"] = eng.energycheck()
+    _driver.timestep(str(inputs["TIMESTEPPING"]).upper(), sv)
+    sv.step += 1
+    sim.log.append(rec)
+    return rec

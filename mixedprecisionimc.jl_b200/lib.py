@@ -109,6 +109,7 @@ ABI = [
     ("imc_get_field", C.c_int, [C.c_void_p, C.c_int32, _DP, C.c_int64]),
     ("imc_set_state", C.c_int, [C.c_void_p, _DP, _DP, _DP]),
     ("imc_num_particles", C.c_int64, [C.c_void_p]),
+    ("imc_kernel_launches", C.c_int64, [C.c_void_p]),
     ("imc_get_particles", C.c_int, [C.c_void_p, _DP, C.POINTER(C.c_uint64), C.c_int64]),
     ("imc_set_particles", C.c_int, [C.c_void_p, _DP, C.POINTER(C.c_uint64), C.c_int64]),
     ("imc_set_transport_tape", C.c_int, [C.c_void_p, _DP, C.c_int32, _DP, C.c_int32, C.c_int64]),
@@ -312,9 +313,12 @@ class Engine:
         return p.value, n.value, bool(isint.value)
 
     # -- state access ------------------------------------------------------------------------
-    def field(self, name: str) -> np.ndarray:
+    def field(self, name: str, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Download a field as Float64; `out` may be a caller-owned (e.g. pinned) flat buffer."""
         n = self.nc * (self.ns if name in _MULTISCALE else 1)
-        out = np.empty(n, dtype=np.float64)
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        assert out.size == n and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
         self._check(self.lib.dll.imc_get_field(self._h, FIELDS[name], _dp(out), n))
         c = self.cfg
         if c.geometry == 2:
@@ -329,6 +333,9 @@ class Engine:
 
     def num_particles(self) -> int:
         return int(self.lib.dll.imc_num_particles(self._h))
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.dll.imc_kernel_launches(self._h))
 
     def particles(self):
         """(slots [N, 9|10] Float64 in the reference's slot order, ids [N] uint64)."""

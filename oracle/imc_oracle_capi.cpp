@@ -75,6 +75,7 @@ int imc_reduce_buffer(imc_handle h, void** p, int64_t* n, int32_t* is_int) { GUA
 int imc_get_field(imc_handle h, int32_t f, double* dst, int64_t n) { GUARD(h->e->get_field(f, dst, n)); }
 int imc_set_state(imc_handle h, const double* t, const double* m, const double* r) { GUARD(h->e->set_state(t, m, r)); }
 int64_t imc_num_particles(imc_handle h) { return h ? h->e->num_particles() : -1; }
+int64_t imc_kernel_launches(imc_handle h) { return h ? 0 : -1; }
 int imc_get_particles(imc_handle h, double* s, uint64_t* ids, int64_t cap) { GUARD(h->e->get_particles(s, ids, cap)); }
 int imc_set_particles(imc_handle h, const double* s, const uint64_t* ids, int64_t n) { GUARD(h->e->set_particles(s, ids, n)); }
 int imc_set_transport_tape(imc_handle h, const double* u, int32_t nu, const double* e, int32_t ne, int64_t slots) { GUARD(h->e->set_transport_tape(u, nu, e, ne, slots)); }
