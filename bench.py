@@ -163,8 +163,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = args.cpu_sample or 200_000
-        seg_s, dt, seg, hist = cpu_port_run(w, mesh if w["geom"] == 1 else (min(mesh[0], 1024), min(mesh[1], 1024)), sample,
+        sample = args.cpu_sample or 10_000_000
+        seg_s, dt, seg, hist = cpu_port_run(w, mesh if w["geom"] == 1 else (min(mesh[0], 256), min(mesh[1], 256)), sample,
                                             max(1, min(args.steps, 3)), min(args.warmup, 1))
         line = {"metric": "tracked particle-segments/sec", "value": seg_s, "unit": "segments/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, min(args.steps, 3)),
@@ -172,7 +172,8 @@ def main():
                 "data": "synthetic", "config": config, "impl": "reference",
                 "cpu_baseline": {"value": seg_s, "unit": "segments/s", "cores": 1, "kind": "port",
                                  "sample": f"oracle (C++ restatement of the Julia reference, single-threaded like it) on {sample} particles, "
-                                           f"mesh capped at 1024^2, {max(1, min(args.steps, 3))} steps, {seg} segments in {dt:.1f} s"},
+                                           f"mesh capped at 256^2 (every cell emits >= CELLMIN particles, so the mesh bounds the sample), "
+                                           f"{max(1, min(args.steps, 3))} steps, {seg} segments in {dt:.1f} s"},
                 "e2e": {"value": seg_s, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -288,8 +289,8 @@ def main():
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
-            sample = args.cpu_sample or 200_000
-            cmesh = mesh if w["geom"] == 1 else (min(mesh[0], 1024), min(mesh[1], 1024))
+            sample = args.cpu_sample or 10_000_000
+            cmesh = mesh if w["geom"] == 1 else (min(mesh[0], 256), min(mesh[1], 256))
             seg_s, dt, cseg, chist = cpu_port_run(w, cmesh, sample, 2, 1)
             line["cpu_baseline"] = {"value": seg_s, "unit": "segments/s", "cores": 1, "kind": "port",
                                     "sample": f"oracle (C++ restatement of the Julia reference, single-threaded like it) on {sample} particles, "
