@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tally", default="auto", choices=["auto", "atomic", "fixed"])
+    ap.add_argument("--track", default="auto", choices=["auto", "history", "refill"], help="tracking schedule (auto = measured)")
     args = ap.parse_args()
 
     w = WORKLOADS[args.workload]
@@ -157,7 +158,7 @@ def main():
                           f"{particles} particles per GPU (NMAX), NINPUT = NMAX/2, PAIRWISE FALSE",
               "mesh": list(mesh), "particles_per_gpu": particles, "precision": w["precision"],
               "l2_policy": "inputs larger than L2 (particle state >> 126 MB); no explicit flush",
-              "tally_mode": args.tally, "tracking": "history-based, grid-stride, 256 threads/block"}
+              "tally_mode": args.tally, "tracking": f"history-based, schedule {args.track} (static grid-stride | warp refill), 256 threads/block"}
 
     # ---------------------------------------------------------------- reference arm (CPU oracle)
     if args.impl == "reference":
@@ -195,7 +196,8 @@ def main():
     glib = lib.ImcLib(entry.LIB)
     tally_mode = {"auto": lib.TALLY_AUTO, "atomic": lib.TALLY_ATOMIC, "fixed": lib.TALLY_FIXED}[args.tally]
     inputs = make_inputs(w, particles * world, mesh)  # NMAX / NINPUT are global; each rank emits its stripe
-    sim = driver.setup(inputs, glib, device=local_rank, rank=rank, world=world, tally_mode=tally_mode)
+    track_mode = {"auto": lib.TRACK_AUTO, "history": lib.TRACK_HISTORY, "refill": lib.TRACK_REFILL}[args.track]
+    sim = driver.setup(inputs, glib, device=local_rank, rank=rank, world=world, tally_mode=tally_mode, track_mode=track_mode)
     sim.save_history = False
     eng = sim.engine
     nc = eng.nc
@@ -230,6 +232,7 @@ def main():
     l0 = eng.kernel_launches()
     seg = hist = 0
     kms = 0.0
+    variants = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -237,6 +240,7 @@ def main():
     for _ in range(args.steps):
         r = step_resident()
         seg += r["transport"]["segments"]; hist += r["transport"]["histories"]; kms += r["transport"]["kernel_ms"]
+        variants.append({1: "static", 2: "refill"}.get(r["transport"]["variant"], "?"))
     barrier()
     ev1.record()
     torch.cuda.synchronize()
@@ -282,7 +286,7 @@ def main():
             "cuda_event_ms_per_step": ev0.elapsed_time(ev1) / args.steps,
             "e2e": {"value": seg_e_g / wall_e_g, "unit": "segments/s", "h2d_bytes_per_step": 3 * nc * 8, "d2h_bytes_per_step": 3 * nc * 8,
                     "ms_per_step": 1e3 * wall_e_g / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "schedule_per_step": variants,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "kernel": "k_track2d" if w["geom"] == 2 else ("k_track1d_rw" if w["deck"] == "marshak" else "k_track1d"),
                          "bytes_per_segment": bps, "peak_source": peak_src},

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "imc_engine.h"
 #include "imc_kernels.cuh"
@@ -120,6 +121,9 @@ struct EngineT : EngineBase {
   // host mirrors of the scalar state
   double totalenergy = 0, totalenergydep = 0, radenergyold = 0;
   uint64_t iterations = 0;
+  long long n_transport_calls = 0;
+  double rate_static = 0, rate_refill = 0;  // segments per ms of each schedule, last measured
+  static int refill_min_env() { const char* e = getenv("IMC_REFILL_MIN"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 32 ? 32 : v); }
   int64_t n_launch = 0;  // kernels launched by this engine (bench.py reports it as gpu_launches)
 
   explicit EngineT(const imc_config& c) : cfg(c) {
@@ -271,7 +275,7 @@ struct EngineT : EngineBase {
     IMC_CK(src_e.alloc(M)); IMC_CK(src_q.alloc(M)); IMC_CK(src_nrg.alloc(M)); IMC_CK(src_ks.alloc(M)); IMC_CK(src_cnt.alloc(M));
     IMC_CK(src_offs.alloc(M + 1)); IMC_CK(src_qem.alloc(nc * ns)); IMC_CK(src_sc.alloc(1)); IMC_CK(sums.alloc(16));
     IMC_CK(q_dep.alloc(nc * ns)); IMC_CK(q_tot.alloc(nc)); IMC_CK(q_rad.alloc(nc));
-    IMC_CK(d_max.alloc(2)); IMC_CK(d_flag.alloc(2)); IMC_CK(over_flag.alloc(1));
+    IMC_CK(d_max.alloc(2)); IMC_CK(d_flag.alloc(2)); IMC_CK(over_flag.alloc(2));
     // device view
     m.geom = geom; m.nx = nx; m.ny = ny; m.ns = ns; m.nc = nc;
     m.dx = dx.p; m.dy = dy.p; m.wx = wx.p; m.wy = wy.p;
@@ -454,7 +458,7 @@ struct EngineT : EngineBase {
     // mesh.energydep = zeros(...) (:45); per-call counters; lostenergy keeps accumulating
     IMC_CK(cudaMemsetAsync(red.p + rb_dep0(), 0, nc * ns * sizeof(double), stream));
     IMC_CK(cudaMemsetAsync(red.p + rb_sc0() + RB_SEG, 0, (RB_NSCALARS - RB_SEG) * sizeof(double), stream));
-    IMC_CK(cudaMemsetAsync(over_flag.p, 0, sizeof(unsigned long long), stream));
+    IMC_CK(cudaMemsetAsync(over_flag.p, 0, 2 * sizeof(unsigned long long), stream));
     TrackArgs<P> a;
     a.m = m; a.p = pb[cur].view(); a.n = n_part; a.dt = P::from_d(dt_);
     a.rng = rng_args(step, false);
@@ -474,13 +478,28 @@ struct EngineT : EngineBase {
     } else { a.out_event = nullptr; a.out_nseg = nullptr; out_n = 0; }
     a.over_flag = over_flag.p;
     a.aVals = rw_a.p; a.ptVals = rw_pt.p; a.n_rw_table = (int)h_rw_a.size();
-    int variant = IMC_TRACK_HISTORY;
+    // schedule: static grid-stride or dynamic warp refill.  AUTO measures both (alternating on the first
+    // steps, re-probing every 32 calls) and keeps the one with the higher segments/s.
+    int variant = cfg.track_mode;
+    if (variant == IMC_TRACK_EVENT) variant = IMC_TRACK_AUTO;  // event-based variant: DESIGN.md (not built yet)
+    if (geom == 1 && cfg.randomwalk) variant = IMC_TRACK_HISTORY;
+    if (variant == IMC_TRACK_AUTO) {
+      long long phase = n_transport_calls % 32;
+      if (phase == 0) variant = IMC_TRACK_HISTORY;
+      else if (phase == 1) variant = IMC_TRACK_REFILL;
+      else variant = rate_static >= rate_refill ? IMC_TRACK_HISTORY : IMC_TRACK_REFILL;
+    }
+    ++n_transport_calls;
+    a.queue = over_flag.p + 1;
+    a.refill_min = refill_min_env();
     if (n_part > 0) {
       int blocks_per_sm = 2048 / TRACK_THREADS;
       if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / smem));
       unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
       IMC_CK(cudaEventRecord(ev0, stream));
       if (geom == 1 && cfg.randomwalk) k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      else if (variant == IMC_TRACK_REFILL && geom == 1) k_track_refill<P, 1><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      else if (variant == IMC_TRACK_REFILL) k_track_refill<P, 2><<<grid, TRACK_THREADS, smem, stream>>>(a);
       else if (geom == 1) k_track1d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
       else k_track2d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
       ++n_launch;
@@ -501,6 +520,10 @@ struct EngineT : EngineBase {
     double lost;
     if (mode == IMC_TALLY_FIXED) { long long v; memcpy(&v, &sc[RB_LOST], 8); lost = (double)v / fx_mul_lost; } else lost = sc[RB_LOST];
     iterations += cnt(RB_SEG);
+    if (ms > 0) {
+      double rate = (double)cnt(RB_SEG) / ms;
+      if (variant == IMC_TRACK_REFILL) rate_refill = rate; else rate_static = rate;
+    }
     if (out) {
       out->lostenergy = (double)P::from_d(lost);
       out->segments = cnt(RB_SEG); out->segments_total = iterations; out->histories = (int64_t)cnt(RB_HIST);

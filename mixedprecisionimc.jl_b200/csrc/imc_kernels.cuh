@@ -496,78 +496,111 @@ struct TrackArgs {
   // random-walk tables (MC_RW)
   const typename P::store_t *aVals, *ptVals;
   int n_rw_table;
+  // dynamic schedule
+  unsigned long long* queue;  // next unclaimed particle index
+  int refill_min;             // refill when at least this many lanes of a warp are idle
 };
+
+// One particle's registers while it is being tracked, and one loop iteration ("segment") as a device
+// function, shared by the two history-based schedules:
+//   k_track*         static: thread t takes particles t, t + stride, ...; a warp waits for its longest history
+//   k_track_refill   dynamic: lanes whose history ended take the next particles from a global queue
+//                    (warp-aggregated atomic) while the other lanes keep tracking — keeps lanes busy when
+//                    history lengths differ by orders of magnitude (thin pipe vs hot thick wall)
+// seg*() returns -1 to continue, or the outcome 0 census / 1 absorbed / 2 escaped.
+template <class P>
+struct Hist1 {
+  Num<P> t, x, mu, E, E0, minE, escale;
+  int cell, k, nseg;
+  long long kbase, pi;
+};
+template <class P>
+__device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist1<P>& h, Draw<P>& d, Counters& cn) {
+  using N = Num<P>;
+  h.E0 = N::load(a.p.E0, pi);
+  if (h.E0.v == (typename P::comp_t)-1) return false;  // flagged dead and not yet cleaned
+  h.pi = pi;
+  h.t = N::load(a.p.t, pi); h.x = N::load(a.p.x, pi); h.mu = N::load(a.p.mu, pi); h.E = N::load(a.p.E, pi);
+  h.cell = a.p.cx[pi];
+  h.k = a.p.ks[pi];
+  h.escale = N(a.m.scales[h.k]);
+  h.minE = N::from_d(0.01 * h.E0.d());                                              // :61
+  h.kbase = a.m.nc * h.k;
+  h.nseg = 0;
+  d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
+  ++cn.hist;
+  return true;
+}
+template <class P>
+__device__ __forceinline__ void store1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>& d, int ev, Counters& cn) {
+  const long long pi = h.pi;
+  cn.seg += (unsigned long long)h.nseg;
+  if (ev == 0) { h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi); a.p.cx[pi] = h.cell; }
+  else h.E0.store(a.p.E0, pi);  // dead: only the flag is written; the other slots stay stale (Q16)
+  if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
+  if (d.over()) atomicAdd(a.over_flag, 1ull);
+}
+template <class P>
+__device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>& d, Tally<P>& tal, Counters& cn) {
+  using N = Num<P>;
+  const N one = N::from_d(1.0), two = N::from_i(2), zero;
+  const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
+  const int nc = (int)a.m.nc;
+  ++h.nseg;                                                                         // :73
+  const CellProp1<P> cp = a.m.cp1[h.cell];
+  const N w(P::unpack(cp.w)), dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
+  N dist_b = h.mu > zero ? (w - h.x) / h.mu : nabs(h.x / h.mu);                     // :77-83
+  N dist_col = d.randexp() / sig_col;                                               // :87
+  N dist_cen = (c_light * (dt - h.t)) * ds;                                         // :89
+  N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                              // :92
+  N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
+  N newE = h.E * ex;                                                                // :95
+  if (is_nan(newE) || is_nan(dist)) ++cn.errors;
+  if (newE <= h.minE) {                                                             // :97-106
+    tal.add(h.kbase + h.cell, h.E / dx);
+    h.E0 = N::from_d(-1.0); ++cn.absorbed;
+    return 1;
+  }
+  tal.add(h.kbase + h.cell, (-(h.E / dx)) * em1);                                   // :110 / :120
+  h.x = h.x + h.mu * dist;                                                          // :124
+  h.t = h.t + (dist / ds) / c_light;                                                // :125
+  h.E = newE;                                                                       // :126
+  bool dead = false;
+  if (dist == dist_b) {                                                             // :130-170
+    if (h.mu > zero) {
+      if (h.cell == nc - 1) {
+        if (a.m.bc[IMC_BC_RIGHT] == IMC_REFLECT) h.mu = -h.mu; else dead = true;
+      }
+      if (!dead) { h.cell += 1; h.x = zero; }
+    }
+    if (!dead && h.mu < zero) {
+      if (h.cell == 0) {
+        if (a.m.bc[IMC_BC_LEFT] == IMC_REFLECT) h.mu = -h.mu; else dead = true;
+      } else { h.cell -= 1; h.x = N::load(a.m.wx, h.cell); }
+    }
+  }
+  if (dead) { cn.lose<P>(a.tally, h.E / h.escale); h.E0 = N::from_d(-1.0); ++cn.escaped; return 2; }  // :141 / :160
+  if (dist == dist_col) {                                                           // :174-183
+    h.mu = zero;
+    while (h.mu == zero) h.mu = one - two * d.uniform();
+  }
+  if (dist == dist_cen) { h.t = zero; ++cn.census; return 0; }                      // :185-193
+  return -1;
+}
 
 template <class P>
 __global__ void __launch_bounds__(TRACK_THREADS) k_track1d(TrackArgs<P> a) {
-  using N = Num<P>;
   extern __shared__ __align__(16) unsigned char smem[];
   Tally<P> tal(a.tally, smem);
   tal.zero();
   Counters cn;
-  const N one = N::from_d(1.0), two = N::from_i(2), zero;
-  const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
-  const int nc = (int)a.m.nc;
-  const bool reflect_l = a.m.bc[IMC_BC_LEFT] == IMC_REFLECT, reflect_r = a.m.bc[IMC_BC_RIGHT] == IMC_REFLECT;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
-    N E0 = N::load(a.p.E0, pi);
-    if (E0.v == (typename P::comp_t)-1) continue;  // flagged dead and not yet cleaned
-    N t = N::load(a.p.t, pi), x = N::load(a.p.x, pi), mu = N::load(a.p.mu, pi), E = N::load(a.p.E, pi);
-    int cell = a.p.cx[pi];
-    const int k = a.p.ks[pi];
-    const N escale(a.m.scales[k]);
-    const N minE = N::from_d(0.01 * E0.d());                                       // :61
-    const long long kbase = (long long)nc * k;
-    Draw<P> d; d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
-    int nseg = 0, ev = 0;
-    ++cn.hist;
-    while (true) {
-      ++nseg;                                                                       // :73
-      const CellProp1<P> cp = a.m.cp1[cell];
-      const N w(P::unpack(cp.w)), dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
-      N dist_b = mu > zero ? (w - x) / mu : nabs(x / mu);                           // :77-83
-      N dist_col = d.randexp() / sig_col;                                           // :87
-      N dist_cen = (c_light * (dt - t)) * ds;                                       // :89
-      N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                          // :92
-      N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
-      N newE = E * ex;                                                              // :95
-      if (is_nan(newE) || is_nan(dist)) ++cn.errors;
-      if (newE <= minE) {                                                           // :97-106
-        tal.add(kbase + cell, E / dx);
-        E0 = N::from_d(-1.0); ev = 1; ++cn.absorbed;
-        break;
-      }
-      tal.add(kbase + cell, (-(E / dx)) * em1);                                     // :110 / :120
-      x = x + mu * dist;                                                            // :124
-      t = t + (dist / ds) / c_light;                                                // :125
-      E = newE;                                                                     // :126
-      bool dead = false;
-      if (dist == dist_b) {                                                         // :130-170
-        if (mu > zero) {
-          if (cell == nc - 1) {
-            if (reflect_r) mu = -mu; else dead = true;
-          }
-          if (!dead) { cell += 1; x = zero; }
-        }
-        if (!dead && mu < zero) {
-          if (cell == 0) {
-            if (reflect_l) mu = -mu; else dead = true;
-          } else { cell -= 1; x = N::load(a.m.wx, cell); }
-        }
-      }
-      if (dead) { cn.lose<P>(a.tally, E / escale); E0 = N::from_d(-1.0); ev = 2; ++cn.escaped; break; }  // :141 / :160
-      if (dist == dist_col) {                                                       // :174-183
-        mu = zero;
-        while (mu == zero) mu = one - two * d.uniform();
-      }
-      if (dist == dist_cen) { t = zero; ev = 0; ++cn.census; break; }               // :185-193
-    }
-    cn.seg += (unsigned long long)nseg;
-    if (ev == 0) { t.store(a.p.t, pi); x.store(a.p.x, pi); mu.store(a.p.mu, pi); E.store(a.p.E, pi); a.p.cx[pi] = cell; }
-    else E0.store(a.p.E0, pi);  // dead: only the flag is written; the other slots stay stale (Q16)
-    if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = nseg; }
-    if (d.over()) atomicAdd(a.over_flag, 1ull);
+    Hist1<P> h; Draw<P> d;
+    if (!load1d(a, pi, h, d, cn)) continue;
+    int ev;
+    while ((ev = seg1d(a, h, d, tal, cn)) < 0) {}
+    store1d(a, h, d, ev, cn);
   }
   tal.flush();
   cn.commit(a.tally);
@@ -577,87 +610,154 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d(TrackArgs<P> a) {
 // Transport.MC2D — 2-D history-based tracking
 // ======================================================================================
 template <class P>
-__global__ void __launch_bounds__(TRACK_THREADS) k_track2d(TrackArgs<P> a) {
+struct Hist2 {
+  Num<P> t, x, y, mu, E, E0, minE, escale, vx, vy, dxc, dyc, wxc, wyc;
+  int xi, yi, k, nseg;
+  long long kbase, pi;
+};
+template <class P>
+__device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, Draw<P>& d, Counters& cn) {
   using N = Num<P>;
+  h.E = N::load(a.p.E, pi);
+  if (h.E.v == (typename P::comp_t)-1) return false;  // 2-D dead flag lives in the energy slot (Q16)
+  h.pi = pi;
+  h.E0 = N::load(a.p.E0, pi);
+  h.t = N::load(a.p.t, pi); h.x = N::load(a.p.x, pi); h.y = N::load(a.p.y, pi); h.mu = N::load(a.p.mu, pi);
+  h.xi = a.p.cx[pi]; h.yi = a.p.cy[pi];
+  h.k = a.p.ks[pi];
+  h.escale = N(a.m.scales[h.k]);
+  h.minE = N::from_d(0.01 * h.E0.d());                                              // :531
+  h.kbase = a.m.nc * h.k;
+  h.nseg = 0;
+  d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
+  MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
+  h.dxc = N::load(a.m.dx, h.xi); h.dyc = N::load(a.m.dy, h.yi); h.wxc = N::load(a.m.wx, h.xi); h.wyc = N::load(a.m.wy, h.yi);
+  ++cn.hist;
+  return true;
+}
+template <class P>
+__device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>& d, int ev, Counters& cn) {
+  const long long pi = h.pi;
+  cn.seg += (unsigned long long)h.nseg;
+  if (ev == 0) {
+    h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.y.store(a.p.y, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi);
+    a.p.cx[pi] = h.xi; a.p.cy[pi] = h.yi;
+  } else h.E.store(a.p.E, pi);
+  if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
+  if (d.over()) atomicAdd(a.over_flag, 1ull);
+}
+template <class P>
+__device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>& d, Tally<P>& tal, Counters& cn) {
+  using N = Num<P>;
+  const N zero;
+  const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
+  const int nx = a.m.nx, ny = a.m.ny;
+  const double TWO_PI = 2.0 * 3.141592653589793;
+  ++h.nseg;
+  const long long c = (long long)h.xi + (long long)nx * h.yi;
+  const CellProp2<P> cp = a.m.cp2[c];
+  const N sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
+  N dist_bx = h.vx > zero ? nabs((h.wxc - h.x) / h.vx) : nabs(h.x / h.vx);          // :538-542
+  N dist_by = h.vy > zero ? nabs((h.wyc - h.y) / h.vy) : nabs(h.y / h.vy);          // :544-548
+  N dist_b = is_nan(dist_bx) ? dist_by : is_nan(dist_by) ? dist_bx : jl_min(dist_bx, dist_by);  // :551-557
+  N dist_col = d.randexp() / sig_col;                                               // :561
+  N dist_cen = (c_light * (dt - h.t)) * ds;                                         // :569
+  N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                              // :571
+  if (is_nan(dist) || dist_col < zero) ++cn.errors;
+  N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
+  N newE = h.E * ex;                                                                // :580
+  if (newE <= h.minE) {                                                             // :586-595
+    tal.add(h.kbase + c, (h.E / h.dxc) / h.dyc);
+    h.E = N::from_d(-1.0); ++cn.absorbed;
+    return 1;
+  }
+  tal.add(h.kbase + c, ((-(h.E / h.dxc)) / h.dyc) * em1);                           // :599 / :607
+  h.x = h.x + dist * h.vx;                                                          // :615
+  h.y = h.y + dist * h.vy;                                                          // :616
+  h.t = h.t + (dist / ds) / c_light;                                                // :617
+  h.E = newE;                                                                       // :618
+  if (dist == dist_bx || dist == dist_by) {                                         // :621
+    int side = -1;
+    if (dist_bx < dist_by) {                                                        // :622
+      if (h.vx > zero) { if (h.xi == nx - 1) side = IMC_BC_RIGHT; else { h.xi += 1; h.x = zero; } }
+      else { if (h.xi == 0) side = IMC_BC_LEFT; else { h.xi -= 1; h.x = N::load(a.m.wx, h.xi); } }
+      if (side < 0) { h.dxc = N::load(a.m.dx, h.xi); h.wxc = N::load(a.m.wx, h.xi); }
+      else if (a.m.bc[side] == IMC_REFLECT) { h.mu = MathDet::atan2<P>(h.vy, -h.vx); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :626-628
+    } else {
+      if (h.vy > zero) { if (h.yi == ny - 1) side = IMC_BC_TOP; else { h.yi += 1; h.y = zero; } }
+      else { if (h.yi == 0) side = IMC_BC_BOTTOM; else { h.yi -= 1; h.y = N::load(a.m.wy, h.yi); } }
+      if (side < 0) { h.dyc = N::load(a.m.dy, h.yi); h.wyc = N::load(a.m.wy, h.yi); }
+      else if (a.m.bc[side] == IMC_REFLECT) { h.mu = MathDet::atan2<P>(-h.vy, h.vx); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :666-668
+    }
+    if (side >= 0 && a.m.bc[side] != IMC_REFLECT) {                                 // VACUUM :629-636 ...
+      cn.lose<P>(a.tally, h.E / h.escale);
+      h.E = N::from_d(-1.0); ++cn.escaped;
+      return 2;
+    }
+    return -1;                                                                      // `continue` :703 (Q15)
+  }
+  if (dist == dist_col) { h.mu = N::from_d(TWO_PI * d.uniform().d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :706-710
+  if (dist == dist_cen) { h.t = zero; ++cn.census; return 0; }                      // :712-717
+  return -1;
+}
+
+template <class P>
+__global__ void __launch_bounds__(TRACK_THREADS) k_track2d(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   Tally<P> tal(a.tally, smem);
   tal.zero();
   Counters cn;
-  const N one = N::from_d(1.0), zero;
-  const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
-  const int nx = a.m.nx, ny = a.m.ny;
-  const double TWO_PI = 2.0 * 3.141592653589793;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
-    N E = N::load(a.p.E, pi);
-    if (E.v == (typename P::comp_t)-1) continue;  // 2-D dead flag lives in the energy slot (Q16)
-    N E0 = N::load(a.p.E0, pi);
-    N t = N::load(a.p.t, pi), x = N::load(a.p.x, pi), y = N::load(a.p.y, pi), mu = N::load(a.p.mu, pi);
-    int xi = a.p.cx[pi], yi = a.p.cy[pi];
-    const int k = a.p.ks[pi];
-    const N escale(a.m.scales[k]);
-    const N minE = N::from_d(0.01 * E0.d());                                       // :531
-    const long long kbase = a.m.nc * k;
-    Draw<P> d; d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
-    int nseg = 0, ev = 0;
-    ++cn.hist;
-    N vx, vy;
-    MathDet::sincos<P>(mu, &vy, &vx);                                              // :534 (recomputed only when mu changes)
-    N dxc = N::load(a.m.dx, xi), dyc = N::load(a.m.dy, yi), wxc = N::load(a.m.wx, xi), wyc = N::load(a.m.wy, yi);
-    while (true) {
-      ++nseg;
-      const long long c = (long long)xi + (long long)nx * yi;
-      const CellProp2<P> cp = a.m.cp2[c];
-      const N sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
-      N dist_bx = vx > zero ? nabs((wxc - x) / vx) : nabs(x / vx);                  // :538-542
-      N dist_by = vy > zero ? nabs((wyc - y) / vy) : nabs(y / vy);                  // :544-548
-      N dist_b = is_nan(dist_bx) ? dist_by : is_nan(dist_by) ? dist_bx : jl_min(dist_bx, dist_by);  // :551-557
-      N dist_col = d.randexp() / sig_col;                                           // :561
-      N dist_cen = (c_light * (dt - t)) * ds;                                       // :569
-      N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                          // :571
-      if (is_nan(dist) || dist_col < zero) ++cn.errors;
-      N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
-      N newE = E * ex;                                                              // :580
-      if (newE <= minE) {                                                           // :586-595
-        tal.add(kbase + c, (E / dxc) / dyc);
-        E = N::from_d(-1.0); ev = 1; ++cn.absorbed;
-        break;
-      }
-      tal.add(kbase + c, ((-(E / dxc)) / dyc) * em1);                               // :599 / :607
-      x = x + dist * vx;                                                            // :615
-      y = y + dist * vy;                                                            // :616
-      t = t + (dist / ds) / c_light;                                                // :617
-      E = newE;                                                                     // :618
-      if (dist == dist_bx || dist == dist_by) {                                     // :621
-        int side = -1;
-        if (dist_bx < dist_by) {                                                    // :622
-          if (vx > zero) { if (xi == nx - 1) side = IMC_BC_RIGHT; else { xi += 1; x = zero; } }
-          else { if (xi == 0) side = IMC_BC_LEFT; else { xi -= 1; x = N::load(a.m.wx, xi); } }
-          if (side < 0) { dxc = N::load(a.m.dx, xi); wxc = N::load(a.m.wx, xi); }
-          else if (a.m.bc[side] == IMC_REFLECT) { mu = MathDet::atan2<P>(vy, -vx); MathDet::sincos<P>(mu, &vy, &vx); }  // :626-628
-        } else {
-          if (vy > zero) { if (yi == ny - 1) side = IMC_BC_TOP; else { yi += 1; y = zero; } }
-          else { if (yi == 0) side = IMC_BC_BOTTOM; else { yi -= 1; y = N::load(a.m.wy, yi); } }
-          if (side < 0) { dyc = N::load(a.m.dy, yi); wyc = N::load(a.m.wy, yi); }
-          else if (a.m.bc[side] == IMC_REFLECT) { mu = MathDet::atan2<P>(-vy, vx); MathDet::sincos<P>(mu, &vy, &vx); }  // :666-668
+    Hist2<P> h; Draw<P> d;
+    if (!load2d(a, pi, h, d, cn)) continue;
+    int ev;
+    while ((ev = seg2d(a, h, d, tal, cn)) < 0) {}
+    store2d(a, h, d, ev, cn);
+  }
+  tal.flush();
+  cn.commit(a.tally);
+}
+
+// ---- dynamic schedule: warp-level refill from a global particle queue --------------------------------
+// Every loop iteration each active lane tracks one segment.  When at least `refill_min` lanes of the warp
+// are idle (or all are), lane 0 claims that many consecutive particle indices with one atomicAdd and the
+// idle lanes load them.  Per-particle results do not depend on the lane that tracks them (Philox is keyed
+// by particle id, the tape by particle slot), so both schedules give identical particle state.
+template <class P, int GEOM>
+__global__ void __launch_bounds__(TRACK_THREADS) k_track_refill(TrackArgs<P> a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Tally<P> tal(a.tally, smem);
+  tal.zero();
+  Counters cn;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  bool active = false, drained = false;
+  Hist1<P> h1; Hist2<P> h2; Draw<P> d;
+  while (true) {
+    const unsigned idle = __ballot_sync(IMC_FULL_MASK, !active);
+    const int nidle = __popc(idle);
+    if (!drained && (nidle >= a.refill_min || idle == IMC_FULL_MASK)) {
+      long long base = 0;
+      if (lane == 0) base = (long long)atomicAdd(a.queue, (unsigned long long)nidle);
+      base = __shfl_sync(IMC_FULL_MASK, base, 0);
+      if (!active) {
+        long long pi = base + __popc(idle & lt_mask);
+        if (pi < a.n) {
+          if constexpr (GEOM == 1) active = load1d(a, pi, h1, d, cn); else active = load2d(a, pi, h2, d, cn);
         }
-        if (side >= 0 && a.m.bc[side] != IMC_REFLECT) {                             // VACUUM :629-636 ...
-          cn.lose<P>(a.tally, E / escale);
-          E = N::from_d(-1.0); ev = 2; ++cn.escaped;
-          break;
-        }
-        continue;                                                                   // :703 (Q15)
       }
-      if (dist == dist_col) { mu = N::from_d(TWO_PI * d.uniform().d()); MathDet::sincos<P>(mu, &vy, &vx); }  // :706-710
-      if (dist == dist_cen) { t = zero; ev = 0; ++cn.census; break; }               // :712-717
+      if (base + nidle >= a.n) drained = true;
     }
-    cn.seg += (unsigned long long)nseg;
-    if (ev == 0) {
-      t.store(a.p.t, pi); x.store(a.p.x, pi); y.store(a.p.y, pi); mu.store(a.p.mu, pi); E.store(a.p.E, pi);
-      a.p.cx[pi] = xi; a.p.cy[pi] = yi;
-    } else E.store(a.p.E, pi);
-    if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = nseg; }
-    if (d.over()) atomicAdd(a.over_flag, 1ull);
+    if (__ballot_sync(IMC_FULL_MASK, active) == 0u) {
+      if (drained) break;
+      continue;
+    }
+    if (active) {
+      int ev;
+      if constexpr (GEOM == 1) { ev = seg1d(a, h1, d, tal, cn); if (ev >= 0) { store1d(a, h1, d, ev, cn); active = false; } }
+      else { ev = seg2d(a, h2, d, tal, cn); if (ev >= 0) { store2d(a, h2, d, ev, cn); active = false; } }
+    }
   }
   tal.flush();
   cn.commit(a.tally);

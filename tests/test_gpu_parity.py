@@ -40,6 +40,12 @@ def run_pair(inputs, gpu_lib, oracle_lib, steps, sync=True, precision=None, **cf
                 assert np.array_equal(a.engine.field(name), b.engine.field(name)), name
             for name in FIELDS_TALLIED:
                 fa, fb = a.engine.field(name), b.engine.field(name)
+                if precision == "FLOAT16" and name in ("nrg_inc", "matenergydens", "temp"):
+                    # differences of Float16 sums: the reference's own accumulation error dominates; bound it by
+                    # the size of the terms instead of the (cancelling) result
+                    ref = max(np.max(np.abs(b.engine.field("energydep"))), np.max(np.abs(b.engine.field("emittedenergy"))), np.max(np.abs(fb)))
+                    assert np.max(np.abs(fa - fb)) <= 4 * tol * ref, (name, np.max(np.abs(fa - fb)), ref)
+                    continue
                 assert field_close(fa, fb, tol), (name, np.max(np.abs(fa - fb)), np.max(np.abs(fb)))
             a.engine.set_state(temp=b.engine.field("temp"), matenergydens=b.engine.field("matenergydens"),
                                radenergydens=b.engine.field("radenergydens"))
@@ -194,3 +200,22 @@ def test_energy_conservation_and_clean_kat(gpu_lib):
     sim.engine.set_particles(slots)
     assert sim.engine.num_particles() == 1
     assert sim.engine.clean() == 0
+
+
+@pytest.mark.parametrize("deckname", ["suolson", "crooked_pipe"])
+def test_refill_schedule_matches_static(gpu_lib, deckname):
+    """The dynamic warp-refill schedule and the static schedule give bit-identical particles and counters."""
+    if deckname == "suolson":
+        inputs = decks.suolson(precision="FLOAT32", n_input=20000, n_max=200000)
+    else:
+        inputs = decks.crooked_pipe(precision="FLOAT32", n_input=20000, n_max=200000, cellmin=2)
+    sims = [driver.setup(inputs, gpu_lib, track_mode=m, tally_mode=lib.TALLY_FIXED) for m in (lib.TRACK_HISTORY, lib.TRACK_REFILL)]
+    for _ in range(4):
+        ra, rb = [s.advance() for s in sims]
+        assert ra["transport"]["variant"] == lib.TRACK_HISTORY and rb["transport"]["variant"] == lib.TRACK_REFILL
+        for key in ("segments", "histories", "n_census", "n_absorbed", "n_escaped"):
+            assert ra["transport"][key] == rb["transport"][key]
+    (pa, ia), (pb, ib) = sims[0].engine.particles(), sims[1].engine.particles()
+    assert np.array_equal(ia, ib) and np.array_equal(pa, pb)
+    for name in ("energydep", "radenergydens", "temp"):   # fixed-point tallies: order-free, so identical too
+        assert np.array_equal(sims[0].engine.field(name), sims[1].engine.field(name)), name
