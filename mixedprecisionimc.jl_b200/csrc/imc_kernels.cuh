@@ -18,7 +18,13 @@
 
 namespace imc {
 
-constexpr int TRACK_THREADS = 256;
+#ifndef IMC_TRACK_THREADS
+#define IMC_TRACK_THREADS 256
+#endif
+#ifndef IMC_TRACK_MIN_BLOCKS
+#define IMC_TRACK_MIN_BLOCKS 3
+#endif
+constexpr int TRACK_THREADS = IMC_TRACK_THREADS;
 
 // reduce-buffer scalar slots that follow [energydep Nc*Ns | radenergydens Nc]
 enum { RB_LOST = 0, RB_SEG, RB_HIST, RB_CENSUS, RB_ABSORBED, RB_ESCAPED, RB_RW, RB_ERRORS, RB_NSCALARS };
@@ -589,7 +595,7 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>
 }
 
 template <class P>
-__global__ void __launch_bounds__(TRACK_THREADS) k_track1d(TrackArgs<P> a) {
+__global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track1d(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   Tally<P> tal(a.tally, smem);
   tal.zero();
@@ -702,7 +708,7 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>
 }
 
 template <class P>
-__global__ void __launch_bounds__(TRACK_THREADS) k_track2d(TrackArgs<P> a) {
+__global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track2d(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   Tally<P> tal(a.tally, smem);
   tal.zero();
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track2d(TrackArgs<P> a) {
 // idle lanes load them.  Per-particle results do not depend on the lane that tracks them (Philox is keyed
 // by particle id, the tape by particle slot), so both schedules give identical particle state.
 template <class P, int GEOM>
-__global__ void __launch_bounds__(TRACK_THREADS) k_track_refill(TrackArgs<P> a) {
+__global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_refill(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   Tally<P> tal(a.tally, smem);
   tal.zero();

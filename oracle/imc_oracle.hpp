@@ -910,10 +910,21 @@ struct Oracle : EngineBase {
       }
     }
     for (size_t c = 0; c < nc; ++c) radenergydens[c] = jl_sum(vec[c]);
+    if (cfg.world > 1) {  // sharded test runs: publish [energydep | radenergydens | lostenergy] for the host's all-reduce
+      redbuf.assign(nc * ns + nc + 8, 0.0);
+      for (size_t i = 0; i < nc * ns; ++i) redbuf[i] = energydep[i].d();
+      for (size_t i = 0; i < nc; ++i) redbuf[nc * ns + i] = radenergydens[i].d();
+      redbuf[nc * ns + nc] = lostenergy;
+    }
     return IMC_OK;
   }
   int tally_finish(double t_, double dt_, imc_tally_stats* out) override {
     N dt = N::from_d(dt_);
+    if (cfg.world > 1 && redbuf.size() == nc * ns + nc + 8) {  // summed over ranks by the host
+      for (size_t i = 0; i < nc * ns; ++i) energydep[i] = N::from_d(redbuf[i]);
+      for (size_t i = 0; i < nc; ++i) radenergydens[i] = N::from_d(redbuf[nc * ns + i]);
+      lostenergy = N::from_d(redbuf[nc * ns + nc]).d();
+    }
     N one = N::from_d(1.0);
     if (t_ == 0.0) {  // :29-32 (Q11)
       for (size_t i = 0; i < nc; ++i) {
@@ -970,7 +981,7 @@ struct Oracle : EngineBase {
   }
 
   int reduce_buffer(void** ptr, int64_t* n, int32_t* is_int) override {
-    redbuf.resize(nc * ns + nc + 8);
+    if (redbuf.size() != nc * ns + nc + 8) redbuf.assign(nc * ns + nc + 8, 0.0);
     *ptr = redbuf.data(); *n = (int64_t)redbuf.size(); *is_int = 0;
     return IMC_OK;
   }

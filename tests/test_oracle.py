@@ -1,0 +1,186 @@
+"""The CPU oracle (restatement of the reference) against everything that pins it: the reference's own clean
+KAT and update smoke test (test/runtests.jl), the deck-embedded Su-Olson benchmark (SuOlson.txt:71-72), the
+analytic infinite-medium equilibrium, energy conservation (imc_energycheck.jl:34) and the host-side logic
+(deck parser, mesh generator, time stepping) against the reference decks when they are present."""
+import os
+
+import numpy as np
+import pytest
+
+from mpimc_b200 import deck, decks, driver, lib
+
+REF_INPUTS = "/root/reference/src/inputs"
+
+
+def test_clean_kat_from_reference_tests(oracle_lib):
+    """test/runtests.jl:78-87 — a particle whose slot 8 is -1.0 is removed; live particles keep their order."""
+    sim = driver.setup(decks.suolson(precision="FLOAT64"), oracle_lib)
+    slots = np.array([[1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, -1.0, 1.0]])
+    slots[0, 1] = 0.0; slots[0, 3] = 0.004
+    sim.engine.set_particles(slots)
+    assert sim.engine.num_particles() == 1
+    assert sim.engine.clean() == 0
+    many = np.tile(np.array([1.0, 0.0, 3.0, 0.004, 0.5, 1.0, 7.0, 7.0, 1.0]), (10, 1))
+    many[:, 6] = np.arange(10) + 1.0
+    many[[2, 3, 7], 7] = -1.0
+    sim.engine.set_particles(many)
+    assert sim.engine.clean() == 7
+    assert sim.engine.particles()[0][:, 6].tolist() == [1.0, 2.0, 5.0, 6.0, 7.0, 9.0, 10.0]
+
+
+def test_update_like_reference_test(oracle_lib):
+    """test/runtests.jl:59-76 on the same deck (test/test_input.txt): beta and sigma_a non-zero, sigma_s zero;
+    plus the closed form of the Fleck factor."""
+    inputs = decks.small_2d(precision="FLOAT64")
+    sim = driver.setup(inputs, oracle_lib)
+    sim.engine.update(0.01)
+    beta, sa, ss, f = (sim.engine.field(k) for k in ("beta", "sigma_a", "sigma_s", "fleck"))
+    assert np.all(beta != 0) and np.all(sa != 0) and np.all(ss == 0)
+    a, c = 0.01372016, 299.70
+    assert np.allclose(beta, 4 * a * 1.0 ** 3 / 1.0, rtol=1e-15)
+    assert np.allclose(f, 1.0 / (1.0 + 1.0 * beta * c * 0.01 * sa), rtol=1e-14)
+    # Su-Olson: alpha = 4 with beta forced to 1 -> f = 1 / (1 + 4 c dt sigma_a) = 0.99602
+    s2 = driver.setup(decks.suolson(precision="FLOAT64"), oracle_lib)
+    s2.engine.update(0.002)
+    assert np.allclose(s2.engine.field("fleck"), 1.0 / (1.0 + 4 * 0.002 * 0.5), rtol=1e-15)
+
+
+def test_marshak_name_quirk(oracle_lib):
+    """imc_update.jl:32-34: NAME == "MARSHAK WAVE" uses sigma0/T/T/T instead of sigma0*T^p (Q18)."""
+    d = decks.marshak(precision="FLOAT64", n_cells=30)
+    s = driver.setup(d, oracle_lib); s.engine.update(1e-5)
+    assert np.array_equal(s.engine.field("sigma_a"), np.full(30, ((1000.0 / 0.01) / 0.01) / 0.01))
+    d["NAME"] = "Not Marshak"
+    s = driver.setup(d, oracle_lib); s.engine.update(1e-5)
+    assert np.allclose(s.engine.field("sigma_a"), 1000.0 * 0.01 ** -3.0, rtol=1e-14)
+
+
+@pytest.mark.parametrize("deckname", ["suolson", "crooked_pipe", "nonuniform_1d", "infinite_medium"])
+def test_energy_conservation_float64(oracle_lib, deckname):
+    inputs = {"suolson": decks.suolson("FLOAT64", 2000, 40000), "crooked_pipe": decks.crooked_pipe("FLOAT64", 3000, 60000, cellmin=1),
+              "nonuniform_1d": decks.nonuniform_1d("FLOAT64", 2000), "infinite_medium": decks.infinite_medium("FLOAT64", 2000)}[deckname]
+    sim = driver.setup(inputs, oracle_lib)
+    sim.save_history = False
+    for _ in range(6):
+        r = sim.advance()
+        assert abs(r["energy"]["energy_error"]) < 1e-10, r["energy"]
+
+
+def test_suolson_benchmark(oracle_lib):
+    """Radiation energy density at t = 1 against the deck's benchmark table (SuOlson.txt:71-72)."""
+    sim = driver.setup(decks.suolson(precision="FLOAT64", n_input=3000, n_max=100000), oracle_lib)
+    sim.save_history = False
+    while float(sim.simvars.t) < 1.0 - 1e-9:
+        sim.advance()
+    assert sim.simvars.step == 500
+    rad = sim.engine.field("radenergydens")
+    cent = np.asarray(sim.mesh.centers, dtype=float)
+    for x, y in zip(decks.SUOLSON_XBENCH, decks.SUOLSON_YBENCH):
+        i = int(np.argmin(np.abs(cent - x)))
+        got = rad[max(0, i - 3):i + 4].mean()
+        assert abs(got - y) < 0.05 + 0.05 * y, (x, y, got)
+
+
+def test_infinite_medium_equilibrium(oracle_lib):
+    """cv T + a T^4 = cv T0 -> T_eq = 0.98698, E_rad = a T_eq^4 = 0.013019."""
+    sim = driver.setup(decks.infinite_medium(precision="FLOAT64", n_input=4000, n_max=40000), oracle_lib)
+    sim.save_history = False
+    for _ in range(60):
+        sim.advance()
+    T = sim.engine.field("temp"); rad = sim.engine.field("radenergydens")
+    assert abs(T.mean() - 0.98698) < 2e-3
+    assert abs(rad.mean() - 0.013019) < 1e-3
+
+
+def test_pairwise_and_sequential_tallies(oracle_lib):
+    """PAIRWISE only changes the summation order (imc_transport.jl:98-121, :198-205): Julia's sum is sequential
+    below 1024 elements, so the two modes differ only in cells that receive more deposits than that."""
+    res = {}
+    for pw in ("TRUE", "FALSE"):
+        sim = driver.setup(decks.suolson(precision="FLOAT32", n_input=20000, n_max=100000, pairwise=pw, dx="0.5"), oracle_lib)
+        sim.engine.update(0.002)
+        sim.engine.source(0.002, 20000, 1.0, 0)
+        sim.engine.transport(0.002, 0)
+        res[pw] = (sim.engine.field("energydep"), sim.engine.particles()[0])
+    assert np.array_equal(res["TRUE"][1], res["FALSE"][1])          # particles do not depend on the tally mode
+    assert np.allclose(res["TRUE"][0], res["FALSE"][0], rtol=1e-4)
+    assert not np.array_equal(res["TRUE"][0], res["FALSE"][0])
+
+
+def test_nmax_cap_and_cellmin(oracle_lib):
+    """imc_sourcing.jl:132-140 (Q9): n_source = max(cellmin, n_max - n_census - length(Ncells) - 1); every body
+    cell still emits >= cellmin particles, so the population may exceed NMAX."""
+    sim = driver.setup(decks.suolson(precision="FLOAT64", n_input=3000, n_max=5000), oracle_lib)
+    r0 = sim.advance()
+    assert r0["source"]["n_source"] == 3000
+    r1 = sim.advance()
+    assert r1["source"]["n_source"] == max(1, 5000 - r0["transport"]["n_census"] - 1 - 1)
+    for _ in range(4):
+        r = sim.advance()
+    assert r["source"]["n_new_global"] >= 1000   # 1000 cells x cellmin 1
+    assert r["source"]["n_particles"] > 5000
+
+
+def test_timestep_logic():
+    """timestep() (MixedPrecisionIMC.jl:181-222): RAMP growth, clamp to dtmax, clamp of the last step, termination."""
+    sv = driver.SimVars(np.float64(0), np.float64(1e-3), np.float64(1e-3), np.float64(1.1), np.float64(0.1), np.float64(1.0), [], 0, 1, 1,
+                        1.0, "FALSE", ("VACUUM", "VACUUM"), np.float64, "1D")
+    n = 0
+    while sv.t <= sv.t_end:
+        driver.timestep("RAMP", sv); n += 1
+        assert sv.dt <= 0.1 + 1e-15
+    assert sv.timesteps[-1] == 1.0 and sv.t > 1.0 and n < 100
+    sv = driver.SimVars(np.float32(0), np.float32(0.3), 0, 0, 0, np.float32(1.0), [], 0, 1, 1, 1.0, "FALSE", (), np.float32, "1D")
+    ts = []
+    while sv.t <= sv.t_end:
+        ts.append(float(sv.t)); driver.timestep("CONSTANT", sv)
+    assert len(ts) == 5 and ts[-1] == 1.0
+
+
+def test_float16_host_parse_quirks():
+    """NINPUT/NMAX are parsed through the deck precision (MixedPrecisionIMC.jl:107-110, Q10): 50000 -> 49984."""
+    d = decks.suolson(precision="FLOAT16")
+    m = deck.mesh_generation(d)
+    sv = driver.make_simvars(d, m)
+    assert sv.n_max == 49984 and sv.n_input == 1000 and m.nx == 1000
+    assert float(m.energyscales[0]) == 32768.0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INPUTS), reason="reference decks not present (GPU box)")
+@pytest.mark.parametrize("fname,gen", [("SuOlson.txt", lambda: decks.suolson("FLOAT16")), ("MarshakWave.txt", lambda: decks.marshak("FLOAT64")),
+                                       ("CrookedPipe.txt", lambda: decks.crooked_pipe("FLOAT64")), ("InfiniteMedium.txt", lambda: decks.infinite_medium("FLOAT32")),
+                                       ("1DNonUniform.txt", lambda: decks.nonuniform_1d("FLOAT64"))])
+def test_deck_generators_match_reference_decks(fname, gen):
+    """The programmatic decks equal what the parser + mesh generator produce from the shipped deck files."""
+    a = deck.mesh_generation(deck.read_inputs(os.path.join(REF_INPUTS, fname)))
+    b = deck.mesh_generation(gen())
+    assert a.Ncells == b.Ncells and a.precision == b.precision
+    tol = 0 if fname != "CrookedPipe.txt" else 0
+    for name in ("dx", "temp", "bee", "radsource", "sigma_a", "sigma_s", "sigma"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    if a.geometry == "2D":
+        assert np.array_equal(a.dy, b.dy)
+        for k in range(4):
+            assert np.array_equal(a.temp_surf[k], b.temp_surf[k])
+    else:
+        assert tuple(map(float, a.temp_surf)) == tuple(map(float, b.temp_surf))
+    ra, rb = deck.read_inputs(os.path.join(REF_INPUTS, fname)), gen()
+    for key in ("NINPUT", "NMAX", "CELLMIN", "PHYS_C", "PHYS_A", "ALPHA", "LINEARIZED", "PAIRWISE", "SEED", "NAME", "TIMESTEPPING"):
+        assert str(ra[key]).strip() == str(rb[key]).strip(), key
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INPUTS), reason="reference decks not present (GPU box)")
+def test_crooked_pipe_materials_and_lattice_deck():
+    m = deck.mesh_generation(deck.read_inputs(os.path.join(REF_INPUTS, "CrookedPipe.txt")))
+    assert m.Ncells == (106, 47)
+    sa = m.sigma_a[..., 1]
+    assert set(np.unique(sa)) == {0.2, 2000.0}
+    xc, yc = np.asarray(m.centers[0]), np.asarray(m.centers[1])
+    pipe = sa == 0.2
+    assert pipe[np.searchsorted(xc, 1.0), np.searchsorted(yc, 0.25)]       # inlet leg
+    assert pipe[np.searchsorted(xc, 3.5), np.searchsorted(yc, 1.25)]       # upper cross-piece
+    assert not pipe[np.searchsorted(xc, 3.5), np.searchsorted(yc, 0.25)]   # wall under it
+    assert np.all(m.temp_surf[2][yc < 0.5] == 0.5) and np.all(m.temp_surf[2][yc > 0.5] == 0.0)
+    # Lattice.txt is stale (no NINPUT/NMAX/CELLMIN): main would throw KeyError
+    lat = deck.read_inputs(os.path.join(REF_INPUTS, "Lattice.txt"))
+    assert "NINPUT" not in lat
