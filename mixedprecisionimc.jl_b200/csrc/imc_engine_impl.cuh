@@ -123,7 +123,7 @@ struct EngineT : EngineBase {
   uint64_t iterations = 0;
   long long n_transport_calls = 0;
   double rate_static = 0, rate_refill = 0;  // segments per ms of each schedule, last measured
-  static int refill_min_env() { const char* e = getenv("IMC_REFILL_MIN"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 32 ? 32 : v); }
+  static int refill_min_env() { const char* e = getenv("IMC_REFILL_MIN"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 32 ? 32 : v); }
   int64_t n_launch = 0;  // kernels launched by this engine (bench.py reports it as gpu_launches)
 
   explicit EngineT(const imc_config& c) : cfg(c) {

@@ -22,7 +22,7 @@ namespace imc {
 #define IMC_TRACK_THREADS 256
 #endif
 #ifndef IMC_TRACK_MIN_BLOCKS
-#define IMC_TRACK_MIN_BLOCKS 3
+#define IMC_TRACK_MIN_BLOCKS 4
 #endif
 constexpr int TRACK_THREADS = IMC_TRACK_THREADS;
 
