@@ -8,6 +8,7 @@
 #include <vector>
 #include "imc_engine.h"
 #include "imc_kernels.cuh"
+#include "imc_exact.h"
 
 namespace imc {
 
@@ -107,6 +108,13 @@ struct EngineT : EngineBase {
   DBuf<int> d_flag;
   DBuf<unsigned long long> over_flag;
   DBuf<long long> blk_cnt;
+  // EXACT tally mode: deposit records
+  DBuf<int> rec_cnt;
+  DBuf<long long> rec_off, rec_start;
+  DBuf<unsigned> rec_key[2];
+  DBuf<double> rec_val[2], lost_val, lost_scratch;
+  DBuf<unsigned char> sort_temp;
+  int last_mode = IMC_TALLY_ATOMIC;
   // outcomes
   DBuf<signed char> out_event;
   DBuf<int> out_nseg;
@@ -394,8 +402,9 @@ struct EngineT : EngineBase {
   // ---- Transport -----------------------------------------------------------------------------
   int resolve_tally_mode() const {
     int mode = cfg.tally_mode;
-    if (mode == IMC_TALLY_AUTO) mode = cfg.pairwise ? IMC_TALLY_FIXED : IMC_TALLY_ATOMIC;
-    if (mode == IMC_TALLY_EXACT) mode = IMC_TALLY_FIXED;  // record path: see DESIGN.md (round 2)
+    // AUTO: PAIRWISE = TRUE asks for the deterministic tree -> EXACT (Julia's pairwise order) while the deposit
+    // records fit the budget, else the order-free fixed-point accumulation; PAIRWISE = FALSE -> float atomics
+    if (mode == IMC_TALLY_AUTO) mode = cfg.pairwise ? IMC_TALLY_EXACT : IMC_TALLY_ATOMIC;
     return mode;
   }
   // smallest cell volume / scale, for fixed-point scaling
@@ -445,12 +454,40 @@ struct EngineT : EngineBase {
     return (size_t)nacc * per;
   }
 
+
+  // EXACT mode: records (key = tally cell, val) in reference order -> out[c] = reduction of cell c's records
+  int exact_reduce_records(long long R, long long nacc, int pairwise, double* out) {
+    IMC_CK(rec_start.ensure((size_t)nacc + 1));
+    if (R > 0) {
+      int end_bit = 1; while ((1ll << end_bit) < nacc + 1 && end_bit < 31) ++end_bit;
+      size_t tb = 0;
+      IMC_CK(exact_sort_pairs(nullptr, tb, rec_key[0].p, rec_key[1].p, rec_val[0].p, rec_val[1].p, R, end_bit, stream));
+      IMC_CK(sort_temp.ensure(tb));
+      IMC_CK(exact_sort_pairs(sort_temp.p, tb, rec_key[0].p, rec_key[1].p, rec_val[0].p, rec_val[1].p, R, end_bit, stream)); n_launch += 3;
+    }
+    k_exact_bounds<<<grid_for(nacc + 1, 256), 256, 0, stream>>>(rec_key[1].p, R, nacc, rec_start.p); ++n_launch;
+    k_exact_reduce<P><<<grid_for(nacc, 128), 128, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, pairwise, out); ++n_launch;
+    IMC_CK(cudaGetLastError());
+    return IMC_OK;
+  }
+  int launch_track(TrackArgs<P>& a, int variant, unsigned grid, size_t smem) {
+    IMC_CK(cudaMemsetAsync(over_flag.p + 1, 0, sizeof(unsigned long long), stream));
+    if (geom == 1 && cfg.randomwalk) k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    else if (variant == IMC_TRACK_REFILL && geom == 1) k_track_refill<P, 1><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    else if (variant == IMC_TRACK_REFILL) k_track_refill<P, 2><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    else if (geom == 1) k_track1d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    else k_track2d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    ++n_launch;
+    IMC_CK(cudaGetLastError());
+    return IMC_OK;
+  }
+
   int transport(double dt_, int64_t step, imc_transport_stats* out) override {
     if (!have_mesh) { err = "transport before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     if (cfg.randomwalk && !have_rw) { err = "random-walk tables not set (imc_rw_table)"; return IMC_ERR_STATE; }
     if (cfg.rng_mode == IMC_RNG_TAPE && n_part > tt_slots) { err = "transport tape has fewer slots than particles"; return IMC_ERR_TAPE; }
-    const int mode = resolve_tally_mode();
+    int mode = resolve_tally_mode();
     if ((mode == IMC_TALLY_FIXED) != red_fixed) {  // representation change: start from a clean buffer
       IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream));
       red_fixed = mode == IMC_TALLY_FIXED;
@@ -465,9 +502,10 @@ struct EngineT : EngineBase {
     a.tally.mode = mode; a.tally.nacc = (int)(nc * ns);
     a.tally.g_acc = red.p; a.tally.g_fx = reinterpret_cast<long long*>(red.p);
     a.tally.fx_mul = 1; a.tally.fx_mul_lost = 1; a.tally.sc0 = rb_sc0();
+    a.tally.pass = 0; a.tally.rec_cnt = nullptr; a.tally.rec_off = nullptr; a.tally.rec_key = nullptr; a.tally.rec_val = nullptr; a.tally.lost_val = nullptr;
     if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
     size_t smem = smem_for(mode, nc * ns);
-    a.tally.use_smem = smem <= 48 * 1024 ? 1 : 0;
+    a.tally.use_smem = (smem <= 48 * 1024 && mode != IMC_TALLY_EXACT) ? 1 : 0;
     if (!a.tally.use_smem) smem = 0;
     // outcome records for replay checks (small populations only)
     bool record = n_part <= (1ll << 22);
@@ -497,13 +535,37 @@ struct EngineT : EngineBase {
       if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / smem));
       unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
       IMC_CK(cudaEventRecord(ev0, stream));
-      if (geom == 1 && cfg.randomwalk) k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
-      else if (variant == IMC_TRACK_REFILL && geom == 1) k_track_refill<P, 1><<<grid, TRACK_THREADS, smem, stream>>>(a);
-      else if (variant == IMC_TRACK_REFILL) k_track_refill<P, 2><<<grid, TRACK_THREADS, smem, stream>>>(a);
-      else if (geom == 1) k_track1d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
-      else k_track2d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
-      ++n_launch;
-      IMC_CK(cudaGetLastError());
+      if (mode == IMC_TALLY_EXACT) {
+        // pass 1: count the deposits of every particle (no side effects), scan -> record offsets
+        IMC_CK(rec_cnt.ensure((size_t)n_part)); IMC_CK(rec_off.ensure((size_t)n_part + 1)); IMC_CK(lost_val.ensure((size_t)n_part));
+        IMC_CK(lost_scratch.ensure((size_t)n_part));
+        a.tally.pass = 1; a.tally.rec_cnt = rec_cnt.p;
+        IMC_RC(launch_track(a, variant, grid, smem));
+        IMC_RC(scan_counts(rec_cnt.p, rec_off.p, n_part));
+        long long R = 0;
+        IMC_CK(cudaMemcpyAsync(&R, scan_total.p, sizeof R, cudaMemcpyDeviceToHost, stream));
+        IMC_CK(cudaStreamSynchronize(stream));
+        long long budget = cfg.exact_record_budget > 0 ? cfg.exact_record_budget : (1ll << 28);
+        if (R > budget) {
+          if (cfg.tally_mode == IMC_TALLY_EXACT) { err = "EXACT tally mode: deposit records exceed exact_record_budget"; return IMC_ERR_NOMEM; }
+          mode = IMC_TALLY_FIXED;  // AUTO: fall back to the order-free fixed-point accumulation
+          if (!red_fixed) { IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream)); red_fixed = true; }
+          a.tally.mode = mode; a.tally.pass = 0;
+          IMC_RC(prepare_fixed(a.tally));
+          smem = smem_for(mode, nc * ns); a.tally.use_smem = smem <= 48 * 1024 ? 1 : 0; if (!a.tally.use_smem) smem = 0;
+          IMC_RC(launch_track(a, variant, grid, smem));
+        } else {
+          for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)std::max<long long>(R, 1))); IMC_CK(rec_val[b].ensure((size_t)std::max<long long>(R, 1))); }
+          IMC_CK(cudaMemsetAsync(lost_val.p, 0xFF, (size_t)n_part * sizeof(double), stream));  // NaN = no loss
+          a.tally.pass = 2; a.tally.rec_off = rec_off.p; a.tally.rec_key = rec_key[0].p; a.tally.rec_val = rec_val[0].p; a.tally.lost_val = lost_val.p;
+          IMC_RC(launch_track(a, variant, grid, smem));
+          IMC_RC(exact_reduce_records(R, nc * ns, cfg.pairwise, red.p + rb_dep0()));
+          k_exact_lost<P><<<1, 1, 0, stream>>>(lost_val.p, pb[cur].view().ks, n_part, m, cfg.pairwise, lost_scratch.p, red.p + rb_sc0() + RB_LOST); ++n_launch;
+          IMC_CK(cudaGetLastError());
+        }
+      } else {
+        IMC_RC(launch_track(a, variant, grid, smem));
+      }
       IMC_CK(cudaEventRecord(ev1, stream));
     }
     double sc[RB_NSCALARS];
@@ -519,6 +581,7 @@ struct EngineT : EngineBase {
     };
     double lost;
     if (mode == IMC_TALLY_FIXED) { long long v; memcpy(&v, &sc[RB_LOST], 8); lost = (double)v / fx_mul_lost; } else lost = sc[RB_LOST];
+    last_mode = mode;
     iterations += cnt(RB_SEG);
     if (ms > 0) {
       double rate = (double)cnt(RB_SEG) / ms;
@@ -560,10 +623,20 @@ struct EngineT : EngineBase {
   int tally_local() override {
     if (!have_mesh) { err = "tally before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
-    const int mode = red_fixed ? IMC_TALLY_FIXED : IMC_TALLY_ATOMIC;
+    int mode = red_fixed ? IMC_TALLY_FIXED : (last_mode == IMC_TALLY_EXACT || (resolve_tally_mode() == IMC_TALLY_EXACT && n_transport_calls == 0) ? IMC_TALLY_EXACT : IMC_TALLY_ATOMIC);
+    if (mode == IMC_TALLY_EXACT && n_part > (cfg.exact_record_budget > 0 ? cfg.exact_record_budget : (1ll << 28))) mode = IMC_TALLY_ATOMIC;
     IMC_CK(cudaMemsetAsync(red.p + rb_rad0(), 0, nc * sizeof(double), stream));
     if (n_part == 0) return IMC_OK;
     TallyArgs ta;
+    ta.pass = 0; ta.rec_cnt = nullptr; ta.rec_off = nullptr; ta.rec_key = nullptr; ta.rec_val = nullptr; ta.lost_val = nullptr;
+    if (mode == IMC_TALLY_EXACT) {  // per-cell vectors + Julia sum, in particle order (imc_tally.jl:84-113, Q19)
+      for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)n_part)); IMC_CK(rec_val[b].ensure((size_t)n_part)); }
+      ta.mode = mode; ta.nacc = (int)nc; ta.use_smem = 0; ta.g_acc = nullptr; ta.g_fx = nullptr; ta.fx_mul = 1; ta.fx_mul_lost = 1; ta.sc0 = 0;
+      ta.pass = 2; ta.rec_key = rec_key[0].p; ta.rec_val = rec_val[0].p;
+      k_census_tally<P><<<grid_for(n_part, TRACK_THREADS), TRACK_THREADS, 0, stream>>>(m, pb[cur].view(), n_part, ta); ++n_launch;
+      IMC_CK(cudaGetLastError());
+      return exact_reduce_records(n_part, nc, 1, red.p + rb_rad0());
+    }
     ta.mode = mode; ta.nacc = (int)nc; ta.g_acc = red.p + rb_rad0(); ta.g_fx = reinterpret_cast<long long*>(red.p) + rb_rad0();
     if (mode == IMC_TALLY_FIXED && fx_mul_rad == 1) IMC_RC(prepare_fixed(ta));
     ta.fx_mul = fx_mul_rad; ta.fx_mul_lost = fx_mul_lost; ta.sc0 = 0;

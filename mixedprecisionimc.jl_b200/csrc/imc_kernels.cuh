@@ -420,6 +420,14 @@ struct TallyArgs {
   double fx_mul;     // 2^S for densities
   double fx_mul_lost;
   long long sc0;     // index of the first scalar slot in the reduce buffer
+  // EXACT mode (reference summation order): pass 1 counts the deposits of every particle, pass 2 writes one
+  // record per deposit at rec_off[particle] + segment, i.e. in the order the reference's loops produce them
+  int pass;                 // 0 = normal, 1 = count only (no side effects), 2 = write records
+  int* rec_cnt;             // [n] deposits per particle (pass 1)
+  const long long* rec_off; // [n] exclusive scan of rec_cnt
+  unsigned* rec_key;        // [R] cell + Nc*k; bit 31 = the value is a Float64 deposit (MC_RW, Q3)
+  double* rec_val;          // [R]
+  double* lost_val;         // [n] energy lost through a VACUUM boundary (NaN = none)
 };
 
 template <class P>
@@ -431,12 +439,16 @@ struct Tally {
     s_acc = reinterpret_cast<A*>(smem); s_fx = reinterpret_cast<unsigned long long*>(smem);
   }
   __device__ __forceinline__ void zero() {
-    if (!a.use_smem) return;
+    if (!a.use_smem || a.mode == IMC_TALLY_EXACT) return;
     if (a.mode == IMC_TALLY_FIXED) { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_fx[i] = 0ull; }
     else { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_acc[i] = (A)0; }
     __syncthreads();
   }
-  __device__ __forceinline__ void add(long long idx, Num<P> v) {
+  __device__ __forceinline__ void add(long long idx, Num<P> v, long long rec = 0, bool wide = false, double wide_v = 0.0) {
+    if (a.mode == IMC_TALLY_EXACT) {
+      if (a.pass == 2) { a.rec_key[rec] = (unsigned)idx | (wide ? 0x80000000u : 0u); a.rec_val[rec] = wide ? wide_v : v.d(); }
+      return;
+    }
     if (a.mode == IMC_TALLY_FIXED) {
       long long q = __double2ll_rn(v.d() * a.fx_mul);
       if (a.use_smem) atomicAdd(&s_fx[idx], (unsigned long long)q);
@@ -447,7 +459,7 @@ struct Tally {
     }
   }
   __device__ __forceinline__ void flush() {
-    if (!a.use_smem) return;
+    if (!a.use_smem || a.mode == IMC_TALLY_EXACT) return;
     __syncthreads();
     if (a.mode == IMC_TALLY_FIXED) {
       for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) { unsigned long long q = s_fx[i]; if (q) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + i, q); }
@@ -462,11 +474,13 @@ struct Counters {
   unsigned long long seg = 0, hist = 0, census = 0, absorbed = 0, escaped = 0, rw = 0, errors = 0;
   double lost = 0; long long lost_fx = 0;
   template <class P>
-  __device__ __forceinline__ void lose(const TallyArgs& a, Num<P> e_over_scale) {
+  __device__ __forceinline__ void lose(const TallyArgs& a, Num<P> e_over_scale, long long pi = 0, double e_raw = 0.0) {
+    if (a.mode == IMC_TALLY_EXACT) { if (a.pass == 2) a.lost_val[pi] = e_raw; return; }
     if (a.mode == IMC_TALLY_FIXED) lost_fx += __double2ll_rn(e_over_scale.d() * a.fx_mul_lost);
     else lost += e_over_scale.d();
   }
   __device__ __forceinline__ void commit(const TallyArgs& a) {
+    if (a.mode == IMC_TALLY_EXACT && a.pass == 1) return;
     unsigned long long v[7] = {seg, hist, census, absorbed, escaped, rw, errors};
     int lane = threadIdx.x & 31;
     if (a.mode == IMC_TALLY_FIXED) {
@@ -518,7 +532,7 @@ template <class P>
 struct Hist1 {
   Num<P> t, x, mu, E, E0, minE, escale;
   int cell, k, nseg;
-  long long kbase, pi;
+  long long kbase, pi, rec_base;
 };
 template <class P>
 __device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist1<P>& h, Draw<P>& d, Counters& cn) {
@@ -533,6 +547,7 @@ __device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist
   h.minE = N::from_d(0.01 * h.E0.d());                                              // :61
   h.kbase = a.m.nc * h.k;
   h.nseg = 0;
+  h.rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
   ++cn.hist;
   return true;
@@ -540,6 +555,7 @@ __device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist
 template <class P>
 __device__ __forceinline__ void store1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>& d, int ev, Counters& cn) {
   const long long pi = h.pi;
+  if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
   cn.seg += (unsigned long long)h.nseg;
   if (ev == 0) { h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi); a.p.cx[pi] = h.cell; }
   else h.E0.store(a.p.E0, pi);  // dead: only the flag is written; the other slots stay stale (Q16)
@@ -563,11 +579,11 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>
   N newE = h.E * ex;                                                                // :95
   if (is_nan(newE) || is_nan(dist)) ++cn.errors;
   if (newE <= h.minE) {                                                             // :97-106
-    tal.add(h.kbase + h.cell, h.E / dx);
+    tal.add(h.kbase + h.cell, h.E / dx, h.rec_base + h.nseg - 1);
     h.E0 = N::from_d(-1.0); ++cn.absorbed;
     return 1;
   }
-  tal.add(h.kbase + h.cell, (-(h.E / dx)) * em1);                                   // :110 / :120
+  tal.add(h.kbase + h.cell, (-(h.E / dx)) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
   h.x = h.x + h.mu * dist;                                                          // :124
   h.t = h.t + (dist / ds) / c_light;                                                // :125
   h.E = newE;                                                                       // :126
@@ -585,7 +601,7 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>
       } else { h.cell -= 1; h.x = N::load(a.m.wx, h.cell); }
     }
   }
-  if (dead) { cn.lose<P>(a.tally, h.E / h.escale); h.E0 = N::from_d(-1.0); ++cn.escaped; return 2; }  // :141 / :160
+  if (dead) { cn.lose<P>(a.tally, h.E / h.escale, h.pi, h.E.d()); h.E0 = N::from_d(-1.0); ++cn.escaped; return 2; }  // :141 / :160
   if (dist == dist_col) {                                                           // :174-183
     h.mu = zero;
     while (h.mu == zero) h.mu = one - two * d.uniform();
@@ -619,7 +635,7 @@ template <class P>
 struct Hist2 {
   Num<P> t, x, y, mu, E, E0, minE, escale, vx, vy, dxc, dyc, wxc, wyc;
   int xi, yi, k, nseg;
-  long long kbase, pi;
+  long long kbase, pi, rec_base;
 };
 template <class P>
 __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, Draw<P>& d, Counters& cn) {
@@ -635,6 +651,7 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   h.minE = N::from_d(0.01 * h.E0.d());                                              // :531
   h.kbase = a.m.nc * h.k;
   h.nseg = 0;
+  h.rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
   MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
   h.dxc = N::load(a.m.dx, h.xi); h.dyc = N::load(a.m.dy, h.yi); h.wxc = N::load(a.m.wx, h.xi); h.wyc = N::load(a.m.wy, h.yi);
@@ -644,6 +661,7 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
 template <class P>
 __device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>& d, int ev, Counters& cn) {
   const long long pi = h.pi;
+  if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
   cn.seg += (unsigned long long)h.nseg;
   if (ev == 0) {
     h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.y.store(a.p.y, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi);
@@ -673,11 +691,11 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   N newE = h.E * ex;                                                                // :580
   if (newE <= h.minE) {                                                             // :586-595
-    tal.add(h.kbase + c, (h.E / h.dxc) / h.dyc);
+    tal.add(h.kbase + c, (h.E / h.dxc) / h.dyc, h.rec_base + h.nseg - 1);
     h.E = N::from_d(-1.0); ++cn.absorbed;
     return 1;
   }
-  tal.add(h.kbase + c, ((-(h.E / h.dxc)) / h.dyc) * em1);                           // :599 / :607
+  tal.add(h.kbase + c, ((-(h.E / h.dxc)) / h.dyc) * em1, h.rec_base + h.nseg - 1);                           // :599 / :607
   h.x = h.x + dist * h.vx;                                                          // :615
   h.y = h.y + dist * h.vy;                                                          // :616
   h.t = h.t + (dist / ds) / c_light;                                                // :617
@@ -696,7 +714,7 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>
       else if (a.m.bc[side] == IMC_REFLECT) { h.mu = MathDet::atan2<P>(-h.vy, h.vx); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :666-668
     }
     if (side >= 0 && a.m.bc[side] != IMC_REFLECT) {                                 // VACUUM :629-636 ...
-      cn.lose<P>(a.tally, h.E / h.escale);
+      cn.lose<P>(a.tally, h.E / h.escale, h.pi, h.E.d());
       h.E = N::from_d(-1.0); ++cn.escaped;
       return 2;
     }
@@ -851,6 +869,7 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
     const long long kbase = (long long)nc * k;
     Draw<P> d; d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
     int nseg = 0, ev = 0;
+    const long long rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
     ++cn.hist;
     while (true) {
       ++nseg;                                                                       // :265
@@ -886,7 +905,7 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
         N ex, em1; MathDet::exp_expm1<P>(expo, &ex, &em1);
         D newE = dyn_mul(E, D(ex));
         D depv = dyn_mul(dyn_mul(D(-one), dyn_div(E, D(dx))), D(em1));              // :317-320 / :352-356
-        tal.add(kbase + cell, N::from_d(depv.v));  // a Float64 deposit is converted on push! / setindex!
+        tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);  // Float64 deposits: converted on push! / added in Float64 on setindex!
         if (newE.v != newE.v) ++cn.errors;
         E0 = N::from_d(-1.0); ev = 3; ++cn.absorbed;
         break;
@@ -894,7 +913,7 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
       D newE = dyn_mul(E, D::w(dm::exp_d(neg_saf.d() * dist.v)));                   // :376 (Float64)
       if (newE.v <= minE.d()) newE = D(zero);                                       // :377-379
       D depv = dyn_sub(E, newE);                                                    // :383 / :385 (not / dx, Q2)
-      tal.add(kbase + cell, N::from_d(depv.v));
+      tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);
       if (newE.v == 0.0) { E0 = N::from_d(-1.0); ev = 1; ++cn.absorbed; break; }    // :390-394
       x = dyn_add(x, dyn_mul(D(mu), dist));                                         // :397
       t = dyn_add(t, dyn_div(dist, D(c_light)));                                    // :398
@@ -911,7 +930,8 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
         }
       }
       if (dead) {                                                                   // :414 / :433
-        if (E.wide) { if (a.tally.mode == IMC_TALLY_FIXED) cn.lost_fx += __double2ll_rn((E.v / escale.d()) * a.tally.fx_mul_lost); else cn.lost += E.v / escale.d(); }
+        if (a.tally.mode == IMC_TALLY_EXACT) { if (a.tally.pass == 2) a.tally.lost_val[pi] = E.v; }
+        else if (E.wide) { if (a.tally.mode == IMC_TALLY_FIXED) cn.lost_fx += __double2ll_rn((E.v / escale.d()) * a.tally.fx_mul_lost); else cn.lost += E.v / escale.d(); }
         else cn.lose<P>(a.tally, E.narrow() / escale);
         E0 = N::from_d(-1.0); ev = 2; ++cn.escaped;
         break;
@@ -922,6 +942,7 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
       }
       if (dist.v == dist_cen.v) { ev = 0; ++cn.census; break; }                     // :455-463
     }
+    if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = nseg; continue; }
     cn.seg += (unsigned long long)nseg;
     if (ev == 0) {
       zero.store(a.p.t, pi); N::from_d(x.v).store(a.p.x, pi); mu.store(a.p.mu, pi); N::from_d(E.v).store(a.p.E, pi); a.p.cx[pi] = cell;
@@ -988,13 +1009,101 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Pa
   tal.zero();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    if (!particle_alive(p, i, m.geom)) continue;
+    if (!particle_alive(p, i, m.geom)) { if (ta.mode == IMC_TALLY_EXACT) { ta.rec_key[i] = 0x7fffffffu; ta.rec_val[i] = 0.0; } continue; }
     N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
     int cx = p.cx[i];
-    if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale));
-    else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale)); }
+    if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale), i);
+    else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale), i); }
   }
   tal.flush();
+}
+
+// ---- EXACT tally mode: per-cell reduction of the sorted deposit records in the reference's order ----------
+// start[c] = first record of cell key c in the key-sorted record array (keys carry the wide flag in bit 31)
+static __global__ void k_exact_bounds(const unsigned* __restrict__ keys, long long R, long long nacc, long long* __restrict__ start) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nacc) return;
+  long long lo = 0, hi = R;  // lower_bound of c on (key & 0x7fffffff)
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if ((long long)(keys[mid] & 0x7fffffffu) < c) lo = mid + 1; else hi = mid;
+  }
+  start[c] = lo;
+}
+// Julia Base.sum (pairwise, 1024-element sequential leaves) of vals[first..last], evaluated by one thread
+template <class P>
+__device__ Num<P> jl_sum_serial(const double* __restrict__ vals, long long first, long long last) {
+  using N = Num<P>;
+  struct Frame { long long first, last; int state; N v1; };
+  Frame st[48];
+  int sp = 0;
+  st[sp++] = {first, last, 0, N()};
+  N ret;
+  while (sp > 0) {
+    Frame& f = st[sp - 1];
+    if (f.state == 0) {
+      if (f.first == f.last) { ret = N::from_d(vals[f.first]); --sp; }
+      else if (f.last - f.first < 1024) {
+        N v = N::from_d(vals[f.first]) + N::from_d(vals[f.first + 1]);
+        for (long long i = f.first + 2; i <= f.last; ++i) v = v + N::from_d(vals[i]);
+        ret = v; --sp;
+      } else {
+        long long mid = f.first + ((f.last - f.first) >> 1);
+        f.state = 1;
+        st[sp++] = {f.first, mid, 0, N()};
+      }
+    } else if (f.state == 1) {
+      f.v1 = ret; f.state = 2;
+      long long mid = f.first + ((f.last - f.first) >> 1);
+      st[sp++] = {mid + 1, f.last, 0, N()};
+    } else { ret = f.v1 + ret; --sp; }
+  }
+  return ret;
+}
+// one thread per tally cell: PAIRWISE = FALSE -> `+=` in record order (imc_transport.jl:101,120); TRUE -> sum(vector) (:202)
+template <class P>
+__global__ void k_exact_reduce(const unsigned* __restrict__ keys, const double* __restrict__ vals, const long long* __restrict__ start,
+                               long long nacc, int pairwise, double* __restrict__ out) {
+  using N = Num<P>;
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nacc) return;
+  long long b = start[c], e = start[c + 1];
+  N v;
+  if (e > b) {
+    if (pairwise) v = jl_sum_serial<P>(vals, b, e - 1);
+    else for (long long i = b; i < e; ++i) {
+      if (keys[i] & 0x80000000u) v = N::from_d(v.d() + vals[i]);   // Float64 deposit added to a T accumulator (MC_RW)
+      else v = v + N::from_d(vals[i]);
+    }
+  }
+  out[c] = v.d();
+}
+// lost energy in particle order (imc_transport.jl:141 / :200), one thread
+template <class P>
+__global__ void k_exact_lost(const double* __restrict__ lost_val, const unsigned char* __restrict__ ks, long long n, MeshDev<P> m,
+                             int pairwise, double* __restrict__ scratch, double* __restrict__ lost_io) {
+  using N = Num<P>;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double lost = *lost_io; bool wide = false;
+  if (!pairwise) {
+    for (long long i = 0; i < n; ++i) {
+      double e = lost_val[i];
+      if (e != e) continue;
+      N scale(m.scales[ks[i]]);
+      N en = N::from_d(e);
+      if (en.d() != e) { lost = lost + e / scale.d(); wide = true; }                 // Float64 energy (MC_RW): lostenergy turns Float64
+      else if (wide) lost = lost + (en / scale).d();
+      else lost = (N::from_d(lost) + en / scale).d();
+    }
+  } else {
+    for (int k = 0; k < m.ns; ++k) {
+      long long cnt = 0;
+      for (long long i = 0; i < n; ++i) { double e = lost_val[i]; if (e == e && ks[i] == k) scratch[cnt++] = N::from_d(e).d(); }
+      N sum = cnt ? jl_sum_serial<P>(scratch, 0, cnt - 1) : N();
+      lost = (N::from_d(lost) + sum / N(m.scales[k])).d();
+    }
+  }
+  *lost_io = lost;
 }
 
 // reduce buffer -> energydep (T)

@@ -219,3 +219,32 @@ def test_refill_schedule_matches_static(gpu_lib, deckname):
     assert np.array_equal(ia, ib) and np.array_equal(pa, pb)
     for name in ("energydep", "radenergydens", "temp"):   # fixed-point tallies: order-free, so identical too
         assert np.array_equal(sims[0].engine.field(name), sims[1].engine.field(name)), name
+
+
+@pytest.mark.parametrize("pairwise", ["TRUE", "FALSE"])
+@pytest.mark.parametrize("case", ["suolson-f32", "suolson-f16", "crooked-f64", "crooked-f32", "nonuniform-f64", "marshak-rw-f32", "infmed-rw-f16"])
+def test_exact_tally_mode_is_bit_exact_without_sync(gpu_lib, oracle_lib, case, pairwise):
+    """EXACT tally mode: deposits are reduced in the reference's own order (sequential `+=` or Julia's pairwise
+    sum), so EVERYTHING — particles, energydep, radenergydens, temperatures — stays bit-identical to the oracle
+    over several time steps with no field synchronisation, in all three precisions."""
+    deck, prec = case.rsplit("-", 1)
+    precision = {"f64": "FLOAT64", "f32": "FLOAT32", "f16": "FLOAT16"}[prec]
+    if deck == "suolson":
+        inputs = decks.suolson(precision=precision, n_input=3000, n_max=30000, pairwise=pairwise)
+    elif deck == "crooked":
+        inputs = decks.crooked_pipe(precision=precision, n_input=4000, n_max=60000, cellmin=2, pairwise=pairwise)
+    elif deck == "nonuniform":
+        inputs = decks.nonuniform_1d(precision=precision, n_input=3000, pairwise=pairwise)
+    elif deck == "marshak-rw":
+        inputs = decks.marshak(precision=precision, n_cells=64, nonuniform=True, randomwalk="TRUE", n_input=3000, n_max=30000, dx_min=2e-4, pairwise=pairwise)
+    else:
+        inputs = decks.infinite_medium(precision=precision, n_input=3000, n_max=30000, randomwalk="TRUE", energyscales=(1024.0,), pairwise=pairwise)
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=5, sync=False, tally_mode=lib.TALLY_EXACT)
+    assert_step_parity(a, b, out, precision)
+    for ra, rb in out:
+        assert ra["transport"]["tally_mode"] == lib.TALLY_EXACT
+        assert ra["transport"]["lostenergy"] == rb["transport"]["lostenergy"]
+        assert ra["tally"] == rb["tally"], (ra["tally"], rb["tally"])
+        assert ra["energy"] == rb["energy"]
+    for name in FIELDS_EXACT + FIELDS_TALLIED + ("bee",):
+        assert np.array_equal(a.engine.field(name), b.engine.field(name)), name
