@@ -47,12 +47,14 @@ WORKLOADS = {
 }
 
 
-def make_inputs(w: dict, particles: int, mesh):
+def make_inputs(w: dict, particles: int, mesh, world: int = 1):
     from mpimc_b200 import decks
     n_max = int(particles)
     n_input = max(n_max // 2, 1)
     if w["deck"] == "crooked_pipe":
-        return decks.crooked_pipe(precision=w["precision"], n_input=n_input, n_max=n_max, cellmin=10 if n_max >= 10 * mesh[0] * mesh[1] else 1,
+        # CELLMIN (every cell emits at least that many particles per step, Q9) grows with the GPU count so that the
+        # per-GPU work stays fixed under weak scaling
+        return decks.crooked_pipe(precision=w["precision"], n_input=n_input, n_max=n_max, cellmin=max(1, world),
                                   mesh_cells=mesh, pairwise="FALSE")
     if w["deck"] == "marshak":
         return decks.marshak(precision=w["precision"], n_cells=mesh[0], nonuniform=True, randomwalk="TRUE", n_input=n_input,
@@ -195,7 +197,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     glib = lib.ImcLib(entry.LIB)
     tally_mode = {"auto": lib.TALLY_AUTO, "atomic": lib.TALLY_ATOMIC, "fixed": lib.TALLY_FIXED}[args.tally]
-    inputs = make_inputs(w, particles * world, mesh)  # NMAX / NINPUT are global; each rank emits its stripe
+    inputs = make_inputs(w, particles * world, mesh, world)  # NMAX / NINPUT are global; each rank emits its stripe
     track_mode = {"auto": lib.TRACK_AUTO, "history": lib.TRACK_HISTORY, "refill": lib.TRACK_REFILL}[args.track]
     sim = driver.setup(inputs, glib, device=local_rank, rank=rank, world=world, tally_mode=tally_mode, track_mode=track_mode)
     sim.save_history = False
