@@ -81,6 +81,7 @@ struct EngineT : EngineBase {
   DBuf<double> temp;
   DBuf<CellProp1<P>> cp1;
   DBuf<CellProp2<P>> cp2;
+  DBuf<AxisProp<P>> axx, axy;
   MeshDev<P> m;
   // particles (double buffer for the stable compaction)
   PartBufs<P> pb[2];
@@ -258,7 +259,7 @@ struct EngineT : EngineBase {
     }
     IMC_RC(upload(dx, dx_, nx));
     if (geom == 2) IMC_RC(upload(dy, dy_, ny)); else { double one = 1.0; IMC_RC(upload(dy, &one, 1)); }
-    IMC_CK(wx.alloc(nx)); IMC_CK(wy.alloc(ny));
+    IMC_CK(wx.alloc(nx)); IMC_CK(wy.alloc(ny)); IMC_CK(axx.alloc(nx)); IMC_CK(axy.alloc(ny));
     IMC_RC(upload(sa_c, sac, nc)); IMC_RC(upload(sa_p, sap, nc)); IMC_RC(upload(ss_c, ssc, nc)); IMC_RC(upload(ss_p, ssp, nc));
     IMC_RC(upload(sa, sac, nc)); IMC_RC(upload(ss, ssc, nc));
     IMC_RC(upload(sigma_static, sstat, nc));
@@ -292,10 +293,11 @@ struct EngineT : EngineBase {
     m.matenergydens = matenergydens.p; m.radenergydens = radenergydens.p; m.nrg_inc = nrg_inc.p;
     m.energydep = energydep.p; m.emittedenergy = emittedenergy.p;
     for (int k = 0; k < 4; ++k) m.tsurf[k] = tsurf[k].p;
-    m.cp1 = cp1.p; m.cp2 = cp2.p;
+    m.cp1 = cp1.p; m.cp2 = cp2.p; m.axx = axx.p; m.axy = axy.p;
     for (int k = 0; k < IMC_MAX_SCALES; ++k) { m.scales[k] = k < ns ? P::from_d(cfg.energyscales[k]) : (Cc)1; m.scales_d[k] = (double)m.scales[k]; }
     m.ds = P::from_d(cfg.distancescale); m.c = P::from_d(cfg.phys_c); m.a = P::from_d(cfg.phys_a); m.alpha = P::from_d(cfg.alpha);
     for (int k = 0; k < 4; ++k) m.bc[k] = cfg.bc[k];
+    m.ds_is_one = (double)m.ds == 1.0; m.c_is_one = (double)m.c == 1.0;
     k_widths<P><<<grid_for(std::max(nx, ny), 256), 256, 0, stream>>>(m); ++n_launch;
     IMC_CK(cudaGetLastError());
     IMC_CK(cudaStreamSynchronize(stream));

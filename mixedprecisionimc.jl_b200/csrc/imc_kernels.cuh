@@ -31,6 +31,7 @@ enum { RB_LOST = 0, RB_SEG, RB_HIST, RB_CENSUS, RB_ABSORBED, RB_ESCAPED, RB_RW, 
 
 template <class P> struct CellProp1 { typename P::store_t w, dx, sig_col, neg_saf; };   // w = dx*ds
 template <class P> struct CellProp2 { typename P::store_t sig_col, neg_saf; };
+template <class P> struct alignas(4 * sizeof(typename P::store_t)) AxisProp { typename P::store_t d, w, inv, pad; };  // dx, dx*ds, 1/dx
 
 template <class P>
 struct MeshDev {
@@ -45,6 +46,8 @@ struct MeshDev {
   S* tsurf[4];  // bottom, top, left, right (1-D: left = [2][0], right = [3][0])
   CellProp1<P>* cp1;
   CellProp2<P>* cp2;
+  AxisProp<P>*axx, *axy;   // per x / y index
+  int ds_is_one, c_is_one;  // x / 1 == x exactly: the divisions by distancescale / phys_c can be skipped
   Cc scales[IMC_MAX_SCALES];
   double scales_d[IMC_MAX_SCALES];
   Cc ds, c, a, alpha;
@@ -70,7 +73,7 @@ struct RngArgs {
   long long stride;
 };
 
-// runtime-selected draw source (Philox or replay tape)
+// runtime-selected draw source (Philox or replay tape) for sourcing and MC_RW: sequential word consumption
 template <class P>
 struct Draw {
   int tape;
@@ -84,6 +87,22 @@ struct Draw {
   __device__ __forceinline__ Num<P> uniform() { return tape ? tp.uniform() : ph.uniform(); }
   __device__ __forceinline__ Num<P> randexp() { return tape ? tp.randexp() : ph.randexp(); }
   __device__ __forceinline__ double randexp64() { return tape ? tp.randexp64() : ph.randexp64(); }
+  __device__ __forceinline__ bool over() const { return tape && tp.exhausted(); }
+};
+// draw source of the MC / MC2D history loops: Philox words reserved per segment (SegDraw), or the tape
+template <class P>
+struct HistDraw {
+  int tape;
+  SegDraw<P> sg;
+  TapeDraw<P> tp;
+  __device__ __forceinline__ void init(const RngArgs& r, unsigned long long id, unsigned int, long long slot) {
+    tape = r.tape;
+    if (tape) tp.init(r.uni, r.n_uni, r.ex, r.n_exp, (size_t)r.stride, (size_t)slot);
+    else sg.init(r.seed, id, r.step);
+  }
+  __device__ __forceinline__ void next_segment() { if (!tape) sg.next_segment(); }
+  __device__ __forceinline__ Num<P> uniform() { return tape ? tp.uniform() : sg.uniform(); }
+  __device__ __forceinline__ Num<P> randexp() { return tape ? tp.randexp() : sg.randexp(); }
   __device__ __forceinline__ bool over() const { return tape && tp.exhausted(); }
 };
 
@@ -144,8 +163,19 @@ __global__ void k_update(MeshDev<P> m, typename P::comp_t dt_, int linearized, i
 template <class P>
 __global__ void k_widths(MeshDev<P> m) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m.nx) (Num<P>::load(m.dx, i) * Num<P>(m.ds)).store(m.wx, i);
-  if (m.geom == 2 && i < m.ny) (Num<P>::load(m.dy, i) * Num<P>(m.ds)).store(m.wy, i);
+  using N = Num<P>;
+  if (i < m.nx) {
+    N d = N::load(m.dx, i), w = d * N(m.ds);
+    w.store(m.wx, i);
+    AxisProp<P> a; a.d = P::pack(d.v); a.w = P::pack(w.v); a.inv = P::pack((N::from_d(1.0) / d).v); a.pad = a.d;
+    m.axx[i] = a;
+  }
+  if (m.geom == 2 && i < m.ny) {
+    N d = N::load(m.dy, i), w = d * N(m.ds);
+    w.store(m.wy, i);
+    AxisProp<P> a; a.d = P::pack(d.v); a.w = P::pack(w.v); a.inv = P::pack((N::from_d(1.0) / d).v); a.pad = a.d;
+    m.axy[i] = a;
+  }
 }
 
 // ======================================================================================
@@ -535,7 +565,7 @@ struct Hist1 {
   long long kbase, pi, rec_base;
 };
 template <class P>
-__device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist1<P>& h, Draw<P>& d, Counters& cn) {
+__device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist1<P>& h, HistDraw<P>& d, Counters& cn) {
   using N = Num<P>;
   h.E0 = N::load(a.p.E0, pi);
   if (h.E0.v == (typename P::comp_t)-1) return false;  // flagged dead and not yet cleaned
@@ -553,7 +583,7 @@ __device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist
   return true;
 }
 template <class P>
-__device__ __forceinline__ void store1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>& d, int ev, Counters& cn) {
+__device__ __forceinline__ void store1d(const TrackArgs<P>& a, Hist1<P>& h, HistDraw<P>& d, int ev, Counters& cn) {
   const long long pi = h.pi;
   if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
   cn.seg += (unsigned long long)h.nseg;
@@ -563,12 +593,13 @@ __device__ __forceinline__ void store1d(const TrackArgs<P>& a, Hist1<P>& h, Draw
   if (d.over()) atomicAdd(a.over_flag, 1ull);
 }
 template <class P>
-__device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>& d, Tally<P>& tal, Counters& cn) {
+__device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, HistDraw<P>& d, Tally<P>& tal, Counters& cn) {
   using N = Num<P>;
   const N one = N::from_d(1.0), two = N::from_i(2), zero;
   const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
   const int nc = (int)a.m.nc;
   ++h.nseg;                                                                         // :73
+  d.next_segment();
   const CellProp1<P> cp = a.m.cp1[h.cell];
   const N w(P::unpack(cp.w)), dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
   N dist_b = h.mu > zero ? (w - h.x) / h.mu : nabs(h.x / h.mu);                     // :77-83
@@ -578,14 +609,17 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, Draw<P>
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   N newE = h.E * ex;                                                                // :95
   if (is_nan(newE) || is_nan(dist)) ++cn.errors;
+  const bool exact = a.tally.mode == IMC_TALLY_EXACT;
+  const N idx = exact ? N() : N(P::unpack(a.m.axx[h.cell].inv));
   if (newE <= h.minE) {                                                             // :97-106
-    tal.add(h.kbase + h.cell, h.E / dx, h.rec_base + h.nseg - 1);
+    tal.add(h.kbase + h.cell, exact ? h.E / dx : h.E * idx, h.rec_base + h.nseg - 1);
     h.E0 = N::from_d(-1.0); ++cn.absorbed;
     return 1;
   }
-  tal.add(h.kbase + h.cell, (-(h.E / dx)) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
+  tal.add(h.kbase + h.cell, exact ? (-(h.E / dx)) * em1 : ((-h.E) * idx) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
   h.x = h.x + h.mu * dist;                                                          // :124
-  h.t = h.t + (dist / ds) / c_light;                                                // :125
+  { N dd = a.m.ds_is_one ? dist : dist / ds;                                          // :125 (x / 1 == x exactly)
+    h.t = h.t + (a.m.c_is_one ? dd : dd / c_light); }
   h.E = newE;                                                                       // :126
   bool dead = false;
   if (dist == dist_b) {                                                             // :130-170
@@ -618,7 +652,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track1d
   Counters cn;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
-    Hist1<P> h; Draw<P> d;
+    Hist1<P> h; HistDraw<P> d;
     if (!load1d(a, pi, h, d, cn)) continue;
     int ev;
     while ((ev = seg1d(a, h, d, tal, cn)) < 0) {}
@@ -633,12 +667,12 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track1d
 // ======================================================================================
 template <class P>
 struct Hist2 {
-  Num<P> t, x, y, mu, E, E0, minE, escale, vx, vy, dxc, dyc, wxc, wyc;
+  Num<P> t, x, y, mu, E, E0, minE, escale, vx, vy, dxc, dyc, wxc, wyc, ivol;  // ivol = (1/dx)*(1/dy), fast deposits only
   int xi, yi, k, nseg;
   long long kbase, pi, rec_base;
 };
 template <class P>
-__device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, Draw<P>& d, Counters& cn) {
+__device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, HistDraw<P>& d, Counters& cn) {
   using N = Num<P>;
   h.E = N::load(a.p.E, pi);
   if (h.E.v == (typename P::comp_t)-1) return false;  // 2-D dead flag lives in the energy slot (Q16)
@@ -654,12 +688,14 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   h.rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
   MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
-  h.dxc = N::load(a.m.dx, h.xi); h.dyc = N::load(a.m.dy, h.yi); h.wxc = N::load(a.m.wx, h.xi); h.wyc = N::load(a.m.wy, h.yi);
+  { const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axy[h.yi];
+    h.dxc = N(P::unpack(ax.d)); h.wxc = N(P::unpack(ax.w)); h.dyc = N(P::unpack(ay.d)); h.wyc = N(P::unpack(ay.w));
+    h.ivol = N(P::unpack(ax.inv)) * N(P::unpack(ay.inv)); }
   ++cn.hist;
   return true;
 }
 template <class P>
-__device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>& d, int ev, Counters& cn) {
+__device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, HistDraw<P>& d, int ev, Counters& cn) {
   const long long pi = h.pi;
   if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
   cn.seg += (unsigned long long)h.nseg;
@@ -671,13 +707,15 @@ __device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, Draw
   if (d.over()) atomicAdd(a.over_flag, 1ull);
 }
 template <class P>
-__device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>& d, Tally<P>& tal, Counters& cn) {
+__device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, HistDraw<P>& d, Tally<P>& tal, Counters& cn) {
   using N = Num<P>;
   const N zero;
   const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
   const int nx = a.m.nx, ny = a.m.ny;
   const double TWO_PI = 2.0 * 3.141592653589793;
+  const bool exact = a.tally.mode == IMC_TALLY_EXACT;
   ++h.nseg;
+  d.next_segment();
   const long long c = (long long)h.xi + (long long)nx * h.yi;
   const CellProp2<P> cp = a.m.cp2[c];
   const N sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
@@ -691,26 +729,37 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, Draw<P>
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   N newE = h.E * ex;                                                                // :580
   if (newE <= h.minE) {                                                             // :586-595
-    tal.add(h.kbase + c, (h.E / h.dxc) / h.dyc, h.rec_base + h.nseg - 1);
+    // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
+    // (EXACT), else E * (1/dx) * (1/dy) (<= 3 ulp from it; sums in these modes are order-dependent anyway)
+    tal.add(h.kbase + c, exact ? (h.E / h.dxc) / h.dyc : h.E * h.ivol, h.rec_base + h.nseg - 1);
     h.E = N::from_d(-1.0); ++cn.absorbed;
     return 1;
   }
-  tal.add(h.kbase + c, ((-(h.E / h.dxc)) / h.dyc) * em1, h.rec_base + h.nseg - 1);                           // :599 / :607
+  tal.add(h.kbase + c, exact ? ((-(h.E / h.dxc)) / h.dyc) * em1 : ((-h.E) * h.ivol) * em1, h.rec_base + h.nseg - 1);  // :599 / :607
   h.x = h.x + dist * h.vx;                                                          // :615
   h.y = h.y + dist * h.vy;                                                          // :616
-  h.t = h.t + (dist / ds) / c_light;                                                // :617
+  { N dd = a.m.ds_is_one ? dist : dist / ds;                                          // :617 (x / 1 == x exactly)
+    h.t = h.t + (a.m.c_is_one ? dd : dd / c_light); }
   h.E = newE;                                                                       // :618
   if (dist == dist_bx || dist == dist_by) {                                         // :621
     int side = -1;
     if (dist_bx < dist_by) {                                                        // :622
       if (h.vx > zero) { if (h.xi == nx - 1) side = IMC_BC_RIGHT; else { h.xi += 1; h.x = zero; } }
-      else { if (h.xi == 0) side = IMC_BC_LEFT; else { h.xi -= 1; h.x = N::load(a.m.wx, h.xi); } }
-      if (side < 0) { h.dxc = N::load(a.m.dx, h.xi); h.wxc = N::load(a.m.wx, h.xi); }
+      else { if (h.xi == 0) side = IMC_BC_LEFT; else { h.xi -= 1; } }
+      if (side < 0) {
+        const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axy[h.yi];
+        h.dxc = N(P::unpack(ax.d)); h.wxc = N(P::unpack(ax.w)); h.ivol = N(P::unpack(ax.inv)) * N(P::unpack(ay.inv));
+        if (!(h.vx > zero)) h.x = h.wxc;
+      }
       else if (a.m.bc[side] == IMC_REFLECT) { h.mu = MathDet::atan2<P>(h.vy, -h.vx); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :626-628
     } else {
       if (h.vy > zero) { if (h.yi == ny - 1) side = IMC_BC_TOP; else { h.yi += 1; h.y = zero; } }
-      else { if (h.yi == 0) side = IMC_BC_BOTTOM; else { h.yi -= 1; h.y = N::load(a.m.wy, h.yi); } }
-      if (side < 0) { h.dyc = N::load(a.m.dy, h.yi); h.wyc = N::load(a.m.wy, h.yi); }
+      else { if (h.yi == 0) side = IMC_BC_BOTTOM; else { h.yi -= 1; } }
+      if (side < 0) {
+        const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axy[h.yi];
+        h.dyc = N(P::unpack(ay.d)); h.wyc = N(P::unpack(ay.w)); h.ivol = N(P::unpack(ax.inv)) * N(P::unpack(ay.inv));
+        if (!(h.vy > zero)) h.y = h.wyc;
+      }
       else if (a.m.bc[side] == IMC_REFLECT) { h.mu = MathDet::atan2<P>(-h.vy, h.vx); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :666-668
     }
     if (side >= 0 && a.m.bc[side] != IMC_REFLECT) {                                 // VACUUM :629-636 ...
@@ -733,7 +782,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track2d
   Counters cn;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
-    Hist2<P> h; Draw<P> d;
+    Hist2<P> h; HistDraw<P> d;
     if (!load2d(a, pi, h, d, cn)) continue;
     int ev;
     while ((ev = seg2d(a, h, d, tal, cn)) < 0) {}
@@ -757,11 +806,14 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   bool active = false, drained = false;
-  Hist1<P> h1; Hist2<P> h2; Draw<P> d;
+  unsigned iter = 0;
+  Hist1<P> h1; Hist2<P> h2; HistDraw<P> d;
   while (true) {
     const unsigned idle = __ballot_sync(IMC_FULL_MASK, !active);
     const int nidle = __popc(idle);
-    if (!drained && (nidle >= a.refill_min || idle == IMC_FULL_MASK)) {
+    // new histories start on even iterations only: SegDraw makes one Philox block per two segments (Float16/32),
+    // so all lanes of the warp then generate their blocks in the same iterations
+    if (!drained && (iter & 1u) == 0u && (nidle >= a.refill_min || idle == IMC_FULL_MASK)) {
       long long base = 0;
       if (lane == 0) base = (long long)atomicAdd(a.queue, (unsigned long long)nidle);
       base = __shfl_sync(IMC_FULL_MASK, base, 0);
@@ -773,8 +825,10 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
       }
       if (base + nidle >= a.n) drained = true;
     }
+    ++iter;
     if (__ballot_sync(IMC_FULL_MASK, active) == 0u) {
       if (drained) break;
+      iter = 0;
       continue;
     }
     if (active) {

@@ -46,7 +46,7 @@ struct Philox {
   }
 };
 
-enum : uint32_t { STREAM_SOURCE = 0u, STREAM_TRACK = 1u };
+enum : uint32_t { STREAM_SOURCE = 0u, STREAM_TRACK = 1u, STREAM_TRACK_EXTRA = 2u };
 
 // One particle's draw stream for one time step.  Words are consumed in order; a new Philox
 // block is generated every 4 words.  counter = (id_lo, id_hi, step, stream<<28 | block).
@@ -115,6 +115,51 @@ struct PhiloxDraw {
   }
   IMC_HD double randexp64() { return randexp64_from_word(s.next_u64()); }
   IMC_HD bool exhausted() const { return false; }
+};
+
+// RNG back-end 1b: Philox with draws RESERVED PER SEGMENT, for the history loops of MC / MC2D.
+// Every loop iteration draws exactly one exponential (imc_transport.jl:87, :561) and at most one uniform (the
+// new direction after a collision, :180, :708), so segment n owns fixed words of the particle's stream:
+//   Float16/Float32: block n>>1 = [exp(n), uni(n), exp(n+1), uni(n+1)]      (one Philox block per two segments)
+//   Float64        : block n    = [exp lo, exp hi, uni lo, uni hi]           (one block per segment)
+// All lanes of a warp therefore generate their blocks in the same iterations (no divergent refresh) and a
+// particle's draws still depend only on (seed, particle id, step, segment).  The rare extra draws of the 1-D
+// `while mu == 0` resampling come from a separate sequential stream.
+template <class P>
+struct SegDraw {
+  uint32_t key[2], ctr[4], buf[4];
+  uint32_t n;       // current segment (0-based); 0xffffffff before the first
+  bool extra_used;
+  PhiloxStream extra;
+  IMC_HD void init(uint64_t seed, uint64_t id, uint32_t step) {
+    key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+    ctr[0] = (uint32_t)id; ctr[1] = (uint32_t)(id >> 32); ctr[2] = step; ctr[3] = STREAM_TRACK << 28;
+    buf[0] = buf[1] = buf[2] = buf[3] = 0u;
+    n = 0xffffffffu;
+    extra_used = false;
+    extra.init(seed, id, step, STREAM_TRACK_EXTRA);
+  }
+  IMC_HD void next_segment() {
+    n += 1u;
+    if (P::id == 2 || (n & 1u) == 0u) {
+      uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3] | (P::id == 2 ? n : (n >> 1))};
+      Philox::block(c, key, buf);
+    }
+    extra_used = false;
+  }
+  IMC_HD Num<P> randexp() {
+    if constexpr (P::id == 2) return Num<P>(randexp64_from_word(((uint64_t)buf[1] << 32) | buf[0]));
+    else return Num<P>(P::rnd(randexp32_from_word((n & 1u) ? buf[2] : buf[0])));
+  }
+  IMC_HD Num<P> uniform() {
+    if (extra_used) {  // second and later uniforms of one segment (1-D `while mu == 0`)
+      if constexpr (P::id == 2) return uniform_from_word<P>(extra.next_u64());
+      else return uniform_from_word<P>((uint64_t)extra.next_u32());
+    }
+    extra_used = true;
+    if constexpr (P::id == 2) return uniform_from_word<P>(((uint64_t)buf[3] << 32) | buf[2]);
+    else return uniform_from_word<P>((uint64_t)((n & 1u) ? buf[3] : buf[1]));
+  }
 };
 
 // RNG back-end 2: tape (replay mode).  Pre-drawn Float64 numbers, draw-major layout

@@ -607,16 +607,19 @@ struct Oracle : EngineBase {
     return -1;
   }
 
+  // MC / MC2D: per-segment reserved Philox words (SegDraw); MC_RW: sequential Philox stream; replay: tape
   struct TDraws {
-    bool tape; PhiloxDraw<P> ph; TapeDraw<P> tp;
-    N uniform() { return tape ? tp.uniform() : ph.uniform(); }
-    N randexp() { return tape ? tp.randexp() : ph.randexp(); }
+    bool tape, seg; PhiloxDraw<P> ph; SegDraw<P> sg; TapeDraw<P> tp;
+    void next_segment() { if (!tape && seg) sg.next_segment(); }
+    N uniform() { return tape ? tp.uniform() : seg ? sg.uniform() : ph.uniform(); }
+    N randexp() { return tape ? tp.randexp() : seg ? sg.randexp() : ph.randexp(); }
     double randexp64() { return tape ? tp.randexp64() : ph.randexp64(); }
     bool over() const { return tape && tp.exhausted(); }
   };
-  TDraws track_draws(size_t slot, int64_t step) {
-    TDraws d; d.tape = cfg.rng_mode == IMC_RNG_TAPE;
+  TDraws track_draws(size_t slot, int64_t step, bool per_segment = true) {
+    TDraws d; d.tape = cfg.rng_mode == IMC_RNG_TAPE; d.seg = per_segment;
     if (d.tape) d.tp.init(tt_uni.data(), tt_nuni, tt_exp.data(), tt_nexp, (size_t)tt_slots, slot);
+    else if (per_segment) d.sg.init((uint64_t)cfg.seed, ids[slot], (uint32_t)step);
     else d.ph.init((uint64_t)cfg.seed, ids[slot], (uint32_t)step, STREAM_TRACK);
     return d;
   }
@@ -651,6 +654,7 @@ struct Oracle : EngineBase {
       int nseg = 0, ev = 0;
       while (true) {
         ++iterations; ++nseg;  // :73
+        d.next_segment();
         size_t c = (size_t)cell - 1;
         N dist_b = mu > N() ? (dx[c] * ds - x) / mu : nabs(x / mu);               // :77-83
         N dist_col = d.randexp() / (sa[c] * (one - fleck[c]) + ss[c]);             // :87
@@ -718,7 +722,7 @@ struct Oracle : EngineBase {
       int k = scale_index(escale);
       if (k < 0 || cell < 1 || cell > (long long)nc) { ++st.n_errors; s[7] = N::from_d(-1.0); out_event[p] = 1; continue; }
       N minenergy = N::from_d(0.01 * E0.d());
-      TDraws d = track_draws(p, step);
+      TDraws d = track_draws(p, step, false);
       int nseg = 0, ev = 0;
       while (true) {
         ++iterations; ++nseg;                                                      // :265
@@ -815,6 +819,7 @@ struct Oracle : EngineBase {
       int nseg = 0, ev = 0;
       while (true) {
         ++iterations; ++nseg;  // counted as in MC (the reference's MC2D has no counter, Q13)
+        d.next_segment();
         N vx, vy; M::template sincos<P>(mu, &vy, &vx);                             // :534
         size_t c = cidx((int)xi, (int)yi);
         N dxc = dx[xi - 1], dyc = dy[yi - 1];
