@@ -474,11 +474,13 @@ struct EngineT : EngineBase {
   }
   int launch_track(TrackArgs<P>& a, int variant, unsigned grid, size_t smem) {
     IMC_CK(cudaMemsetAsync(over_flag.p + 1, 0, sizeof(unsigned long long), stream));
+    smem += COUNTER_SMEM_BYTES;
+    const bool tape = a.rng.tape != 0;
     if (geom == 1 && cfg.randomwalk) k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
-    else if (variant == IMC_TRACK_REFILL && geom == 1) k_track_refill<P, 1><<<grid, TRACK_THREADS, smem, stream>>>(a);
-    else if (variant == IMC_TRACK_REFILL) k_track_refill<P, 2><<<grid, TRACK_THREADS, smem, stream>>>(a);
-    else if (geom == 1) k_track1d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
-    else k_track2d<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    else if (variant == IMC_TRACK_REFILL && geom == 1) { if (tape) k_track_refill<P, 1, true><<<grid, TRACK_THREADS, smem, stream>>>(a); else k_track_refill<P, 1, false><<<grid, TRACK_THREADS, smem, stream>>>(a); }
+    else if (variant == IMC_TRACK_REFILL) { if (tape) k_track_refill<P, 2, true><<<grid, TRACK_THREADS, smem, stream>>>(a); else k_track_refill<P, 2, false><<<grid, TRACK_THREADS, smem, stream>>>(a); }
+    else if (geom == 1) { if (tape) k_track1d<P, true><<<grid, TRACK_THREADS, smem, stream>>>(a); else k_track1d<P, false><<<grid, TRACK_THREADS, smem, stream>>>(a); }
+    else { if (tape) k_track2d<P, true><<<grid, TRACK_THREADS, smem, stream>>>(a); else k_track2d<P, false><<<grid, TRACK_THREADS, smem, stream>>>(a); }
     ++n_launch;
     IMC_CK(cudaGetLastError());
     return IMC_OK;

@@ -89,21 +89,26 @@ struct Draw {
   __device__ __forceinline__ double randexp64() { return tape ? tp.randexp64() : ph.randexp64(); }
   __device__ __forceinline__ bool over() const { return tape && tp.exhausted(); }
 };
-// draw source of the MC / MC2D history loops: Philox words reserved per segment (SegDraw), or the tape
+// draw source of the MC / MC2D history loops, chosen at compile time: Philox words reserved per segment
+// (SegDraw) or the replay tape.  Only the needed state lives in registers.
+template <class P, bool TAPE> struct HistDraw;
 template <class P>
-struct HistDraw {
-  int tape;
+struct HistDraw<P, false> {
   SegDraw<P> sg;
+  __device__ __forceinline__ void init(const RngArgs&, unsigned long long id, long long) { sg.init(id); }
+  __device__ __forceinline__ void next_segment(const RngArgs& r) { sg.next_segment(r.seed, r.step); }
+  __device__ __forceinline__ Num<P> uniform(const RngArgs& r) { return sg.uniform(r.seed, r.step); }
+  __device__ __forceinline__ Num<P> randexp() { return sg.randexp(); }
+  __device__ __forceinline__ bool over() const { return false; }
+};
+template <class P>
+struct HistDraw<P, true> {
   TapeDraw<P> tp;
-  __device__ __forceinline__ void init(const RngArgs& r, unsigned long long id, unsigned int, long long slot) {
-    tape = r.tape;
-    if (tape) tp.init(r.uni, r.n_uni, r.ex, r.n_exp, (size_t)r.stride, (size_t)slot);
-    else sg.init(r.seed, id, r.step);
-  }
-  __device__ __forceinline__ void next_segment() { if (!tape) sg.next_segment(); }
-  __device__ __forceinline__ Num<P> uniform() { return tape ? tp.uniform() : sg.uniform(); }
-  __device__ __forceinline__ Num<P> randexp() { return tape ? tp.randexp() : sg.randexp(); }
-  __device__ __forceinline__ bool over() const { return tape && tp.exhausted(); }
+  __device__ __forceinline__ void init(const RngArgs& r, unsigned long long, long long slot) { tp.init(r.uni, r.n_uni, r.ex, r.n_exp, (size_t)r.stride, (size_t)slot); }
+  __device__ __forceinline__ void next_segment(const RngArgs&) {}
+  __device__ __forceinline__ Num<P> uniform(const RngArgs&) { return tp.uniform(); }
+  __device__ __forceinline__ Num<P> randexp() { return tp.randexp(); }
+  __device__ __forceinline__ bool over() const { return tp.exhausted(); }
 };
 
 // ======================================================================================
@@ -499,35 +504,53 @@ struct Tally {
   }
 };
 
-// per-thread event counters + lost energy, reduced per warp and added to the reduce buffer
+// Event counters and lost energy live in shared memory (one set per block), not in registers: they are
+// touched once per history (warp-aggregated), and 18 fewer live registers in the tracking loop buy a fourth
+// resident block per SM.  Slot RB_LOST holds a Float64 (ATOMIC) or a fixed-point integer (FIXED).
 struct Counters {
-  unsigned long long seg = 0, hist = 0, census = 0, absorbed = 0, escaped = 0, rw = 0, errors = 0;
-  double lost = 0; long long lost_fx = 0;
+  unsigned long long* s;
+  __device__ __forceinline__ void init(unsigned long long* slots) {
+    s = slots;
+    if (threadIdx.x < RB_NSCALARS) s[threadIdx.x] = 0ull;
+    __syncthreads();
+  }
+  // end of one history: outcome ev (0 census, 1 absorbed, 2 escaped, 3 random-walk kill) after nseg segments
+  __device__ __forceinline__ void finish(int ev, int nseg) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    const unsigned segs = __reduce_add_sync(m, (unsigned)nseg);
+    const unsigned c0 = __ballot_sync(m, ev == 0), c2 = __ballot_sync(m, ev == 2);
+    if (lane == leader) {
+      atomicAdd(&s[RB_SEG], (unsigned long long)segs);
+      atomicAdd(&s[RB_HIST], (unsigned long long)__popc(m));
+      if (c0) atomicAdd(&s[RB_CENSUS], (unsigned long long)__popc(c0));
+      if (c2) atomicAdd(&s[RB_ESCAPED], (unsigned long long)__popc(c2));
+      const int nabs = __popc(m) - __popc(c0) - __popc(c2);
+      if (nabs) atomicAdd(&s[RB_ABSORBED], (unsigned long long)nabs);
+    }
+  }
+  __device__ __forceinline__ void error() { atomicAdd(&s[RB_ERRORS], 1ull); }
+  __device__ __forceinline__ void rw() { atomicAdd(&s[RB_RW], 1ull); }
+  __device__ __forceinline__ void lose_value(const TallyArgs& a, double e_over_scale) {
+    if (a.mode == IMC_TALLY_FIXED) atomicAdd(&s[RB_LOST], (unsigned long long)__double2ll_rn(e_over_scale * a.fx_mul_lost));
+    else atomicAdd(reinterpret_cast<double*>(&s[RB_LOST]), e_over_scale);
+  }
   template <class P>
   __device__ __forceinline__ void lose(const TallyArgs& a, Num<P> e_over_scale, long long pi = 0, double e_raw = 0.0) {
     if (a.mode == IMC_TALLY_EXACT) { if (a.pass == 2) a.lost_val[pi] = e_raw; return; }
-    if (a.mode == IMC_TALLY_FIXED) lost_fx += __double2ll_rn(e_over_scale.d() * a.fx_mul_lost);
-    else lost += e_over_scale.d();
+    lose_value(a, e_over_scale.d());
   }
   __device__ __forceinline__ void commit(const TallyArgs& a) {
+    __syncthreads();
     if (a.mode == IMC_TALLY_EXACT && a.pass == 1) return;
-    unsigned long long v[7] = {seg, hist, census, absorbed, escaped, rw, errors};
-    int lane = threadIdx.x & 31;
-    if (a.mode == IMC_TALLY_FIXED) {
-      unsigned long long* g = reinterpret_cast<unsigned long long*>(a.g_fx) + a.sc0;
-      unsigned long long l = warp_sum_u64((unsigned long long)lost_fx);
-      if (lane == 0 && l) atomicAdd(g + RB_LOST, l);
-#pragma unroll
-      for (int k = 0; k < 7; ++k) { unsigned long long s = warp_sum_u64(v[k]); if (lane == 0 && s) atomicAdd(g + RB_SEG + k, s); }
-    } else {
-      double* g = a.g_acc + a.sc0;
-      double l = warp_sum_f64(lost);
-      if (lane == 0 && l != 0.0) atomicAdd(g + RB_LOST, l);
-#pragma unroll
-      for (int k = 0; k < 7; ++k) { unsigned long long s = warp_sum_u64(v[k]); if (lane == 0 && s) atomicAdd(g + RB_SEG + k, (double)s); }
-    }
+    const int k = threadIdx.x;
+    if (k >= RB_NSCALARS || s[k] == 0ull) return;
+    if (a.mode == IMC_TALLY_FIXED) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + a.sc0 + k, s[k]);
+    else if (k == RB_LOST) atomicAdd(a.g_acc + a.sc0 + k, *reinterpret_cast<double*>(&s[k]));
+    else atomicAdd(a.g_acc + a.sc0 + k, (double)s[k]);
   }
 };
+constexpr int COUNTER_SMEM_BYTES = RB_NSCALARS * 8;
 
 // ======================================================================================
 // Transport.MC — 1-D history-based tracking
@@ -564,8 +587,8 @@ struct Hist1 {
   int cell, k, nseg;
   long long kbase, pi, rec_base;
 };
-template <class P>
-__device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist1<P>& h, HistDraw<P>& d, Counters& cn) {
+template <class P, class D>
+__device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist1<P>& h, D& d, Counters& cn) {
   using N = Num<P>;
   h.E0 = N::load(a.p.E0, pi);
   if (h.E0.v == (typename P::comp_t)-1) return false;  // flagged dead and not yet cleaned
@@ -578,28 +601,27 @@ __device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist
   h.kbase = a.m.nc * h.k;
   h.nseg = 0;
   h.rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
-  d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
-  ++cn.hist;
+  d.init(a.rng, a.p.id[pi], pi);
   return true;
 }
-template <class P>
-__device__ __forceinline__ void store1d(const TrackArgs<P>& a, Hist1<P>& h, HistDraw<P>& d, int ev, Counters& cn) {
+template <class P, class D>
+__device__ __forceinline__ void store1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, int ev, Counters& cn) {
   const long long pi = h.pi;
   if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
-  cn.seg += (unsigned long long)h.nseg;
+  cn.finish(ev, h.nseg);
   if (ev == 0) { h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi); a.p.cx[pi] = h.cell; }
   else h.E0.store(a.p.E0, pi);  // dead: only the flag is written; the other slots stay stale (Q16)
   if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
   if (d.over()) atomicAdd(a.over_flag, 1ull);
 }
-template <class P>
-__device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, HistDraw<P>& d, Tally<P>& tal, Counters& cn) {
+template <class P, class D>
+__device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, Tally<P>& tal, Counters& cn) {
   using N = Num<P>;
   const N one = N::from_d(1.0), two = N::from_i(2), zero;
   const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
   const int nc = (int)a.m.nc;
   ++h.nseg;                                                                         // :73
-  d.next_segment();
+  d.next_segment(a.rng);
   const CellProp1<P> cp = a.m.cp1[h.cell];
   const N w(P::unpack(cp.w)), dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
   N dist_b = h.mu > zero ? (w - h.x) / h.mu : nabs(h.x / h.mu);                     // :77-83
@@ -608,12 +630,12 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, HistDra
   N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                              // :92
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   N newE = h.E * ex;                                                                // :95
-  if (is_nan(newE) || is_nan(dist)) ++cn.errors;
+  if (is_nan(newE) || is_nan(dist)) cn.error();
   const bool exact = a.tally.mode == IMC_TALLY_EXACT;
   const N idx = exact ? N() : N(P::unpack(a.m.axx[h.cell].inv));
   if (newE <= h.minE) {                                                             // :97-106
     tal.add(h.kbase + h.cell, exact ? h.E / dx : h.E * idx, h.rec_base + h.nseg - 1);
-    h.E0 = N::from_d(-1.0); ++cn.absorbed;
+    h.E0 = N::from_d(-1.0);
     return 1;
   }
   tal.add(h.kbase + h.cell, exact ? (-(h.E / dx)) * em1 : ((-h.E) * idx) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
@@ -635,24 +657,24 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, HistDra
       } else { h.cell -= 1; h.x = N::load(a.m.wx, h.cell); }
     }
   }
-  if (dead) { cn.lose<P>(a.tally, h.E / h.escale, h.pi, h.E.d()); h.E0 = N::from_d(-1.0); ++cn.escaped; return 2; }  // :141 / :160
+  if (dead) { cn.lose<P>(a.tally, h.E / h.escale, h.pi, h.E.d()); h.E0 = N::from_d(-1.0); return 2; }  // :141 / :160
   if (dist == dist_col) {                                                           // :174-183
     h.mu = zero;
-    while (h.mu == zero) h.mu = one - two * d.uniform();
+    while (h.mu == zero) h.mu = one - two * d.uniform(a.rng);
   }
-  if (dist == dist_cen) { h.t = zero; ++cn.census; return 0; }                      // :185-193
+  if (dist == dist_cen) { h.t = zero; return 0; }                      // :185-193
   return -1;
 }
 
-template <class P>
+template <class P, bool TAPE>
 __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track1d(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  Tally<P> tal(a.tally, smem);
+  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
+  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
-  Counters cn;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
-    Hist1<P> h; HistDraw<P> d;
+    Hist1<P> h; HistDraw<P, TAPE> d;
     if (!load1d(a, pi, h, d, cn)) continue;
     int ev;
     while ((ev = seg1d(a, h, d, tal, cn)) < 0) {}
@@ -671,8 +693,8 @@ struct Hist2 {
   int xi, yi, k, nseg;
   long long kbase, pi, rec_base;
 };
-template <class P>
-__device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, HistDraw<P>& d, Counters& cn) {
+template <class P, class D>
+__device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, D& d, Counters& cn) {
   using N = Num<P>;
   h.E = N::load(a.p.E, pi);
   if (h.E.v == (typename P::comp_t)-1) return false;  // 2-D dead flag lives in the energy slot (Q16)
@@ -686,19 +708,18 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   h.kbase = a.m.nc * h.k;
   h.nseg = 0;
   h.rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
-  d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
+  d.init(a.rng, a.p.id[pi], pi);
   MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
   { const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axy[h.yi];
     h.dxc = N(P::unpack(ax.d)); h.wxc = N(P::unpack(ax.w)); h.dyc = N(P::unpack(ay.d)); h.wyc = N(P::unpack(ay.w));
     h.ivol = N(P::unpack(ax.inv)) * N(P::unpack(ay.inv)); }
-  ++cn.hist;
   return true;
 }
-template <class P>
-__device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, HistDraw<P>& d, int ev, Counters& cn) {
+template <class P, class D>
+__device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, int ev, Counters& cn) {
   const long long pi = h.pi;
   if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
-  cn.seg += (unsigned long long)h.nseg;
+  cn.finish(ev, h.nseg);
   if (ev == 0) {
     h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.y.store(a.p.y, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi);
     a.p.cx[pi] = h.xi; a.p.cy[pi] = h.yi;
@@ -706,8 +727,8 @@ __device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, Hist
   if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
   if (d.over()) atomicAdd(a.over_flag, 1ull);
 }
-template <class P>
-__device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, HistDraw<P>& d, Tally<P>& tal, Counters& cn) {
+template <class P, class D>
+__device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, Tally<P>& tal, Counters& cn) {
   using N = Num<P>;
   const N zero;
   const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
@@ -715,7 +736,7 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, HistDra
   const double TWO_PI = 2.0 * 3.141592653589793;
   const bool exact = a.tally.mode == IMC_TALLY_EXACT;
   ++h.nseg;
-  d.next_segment();
+  d.next_segment(a.rng);
   const long long c = (long long)h.xi + (long long)nx * h.yi;
   const CellProp2<P> cp = a.m.cp2[c];
   const N sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
@@ -725,14 +746,14 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, HistDra
   N dist_col = d.randexp() / sig_col;                                               // :561
   N dist_cen = (c_light * (dt - h.t)) * ds;                                         // :569
   N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                              // :571
-  if (is_nan(dist) || dist_col < zero) ++cn.errors;
+  if (is_nan(dist) || dist_col < zero) cn.error();
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   N newE = h.E * ex;                                                                // :580
   if (newE <= h.minE) {                                                             // :586-595
     // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
     // (EXACT), else E * (1/dx) * (1/dy) (<= 3 ulp from it; sums in these modes are order-dependent anyway)
     tal.add(h.kbase + c, exact ? (h.E / h.dxc) / h.dyc : h.E * h.ivol, h.rec_base + h.nseg - 1);
-    h.E = N::from_d(-1.0); ++cn.absorbed;
+    h.E = N::from_d(-1.0);
     return 1;
   }
   tal.add(h.kbase + c, exact ? ((-(h.E / h.dxc)) / h.dyc) * em1 : ((-h.E) * h.ivol) * em1, h.rec_base + h.nseg - 1);  // :599 / :607
@@ -764,25 +785,25 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, HistDra
     }
     if (side >= 0 && a.m.bc[side] != IMC_REFLECT) {                                 // VACUUM :629-636 ...
       cn.lose<P>(a.tally, h.E / h.escale, h.pi, h.E.d());
-      h.E = N::from_d(-1.0); ++cn.escaped;
+      h.E = N::from_d(-1.0);
       return 2;
     }
     return -1;                                                                      // `continue` :703 (Q15)
   }
-  if (dist == dist_col) { h.mu = N::from_d(TWO_PI * d.uniform().d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :706-710
-  if (dist == dist_cen) { h.t = zero; ++cn.census; return 0; }                      // :712-717
+  if (dist == dist_col) { h.mu = N::from_d(TWO_PI * d.uniform(a.rng).d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :706-710
+  if (dist == dist_cen) { h.t = zero; return 0; }                      // :712-717
   return -1;
 }
 
-template <class P>
+template <class P, bool TAPE>
 __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track2d(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  Tally<P> tal(a.tally, smem);
+  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
+  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
-  Counters cn;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
-    Hist2<P> h; HistDraw<P> d;
+    Hist2<P> h; HistDraw<P, TAPE> d;
     if (!load2d(a, pi, h, d, cn)) continue;
     int ev;
     while ((ev = seg2d(a, h, d, tal, cn)) < 0) {}
@@ -797,17 +818,17 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track2d
 // are idle (or all are), lane 0 claims that many consecutive particle indices with one atomicAdd and the
 // idle lanes load them.  Per-particle results do not depend on the lane that tracks them (Philox is keyed
 // by particle id, the tape by particle slot), so both schedules give identical particle state.
-template <class P, int GEOM>
+template <class P, int GEOM, bool TAPE>
 __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_refill(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  Tally<P> tal(a.tally, smem);
+  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
+  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
-  Counters cn;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   bool active = false, drained = false;
   unsigned iter = 0;
-  Hist1<P> h1; Hist2<P> h2; HistDraw<P> d;
+  Hist1<P> h1; Hist2<P> h2; HistDraw<P, TAPE> d;
   while (true) {
     const unsigned idle = __ballot_sync(IMC_FULL_MASK, !active);
     const int nidle = __popc(idle);
@@ -903,9 +924,9 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
   using N = Num<P>;
   using D = DynD<P>;
   extern __shared__ __align__(16) unsigned char smem[];
-  Tally<P> tal(a.tally, smem);
+  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
+  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
-  Counters cn;
   const N one = N::from_d(1.0), two = N::from_i(2), three = N::from_i(3), zero;
   const N dt(a.dt), c_light(a.m.c);
   const int nc = (int)a.m.nc;
@@ -924,7 +945,6 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
     Draw<P> d; d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
     int nseg = 0, ev = 0;
     const long long rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
-    ++cn.hist;
     while (true) {
       ++nseg;                                                                       // :265
       const CellProp1<P> cp = a.m.cp1[cell];
@@ -937,7 +957,7 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
       D R0 = dyn_min(dyn_abs(dyn_sub(D(dx), x)), dyn_abs(x));                       // :286
       N inv_sigma = N::from_i(1) / N::load(a.m.sigma_static, cell);                 // 1/mesh.sigma[cellindex] (Q4)
       if (R0.v > inv_sigma.d() && dist_col.v < R0.v) {                              // :289
-        ++cn.rw;
+        cn.rw();
         const N sa = N::load(a.m.sa, cell), f = N::load(a.m.fleck, cell);
         N u = d.uniform();                                                          // :290
         N Dc = c_light / ((three * sa) * (one - f));                                // :292
@@ -960,15 +980,15 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
         D newE = dyn_mul(E, D(ex));
         D depv = dyn_mul(dyn_mul(D(-one), dyn_div(E, D(dx))), D(em1));              // :317-320 / :352-356
         tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);  // Float64 deposits: converted on push! / added in Float64 on setindex!
-        if (newE.v != newE.v) ++cn.errors;
-        E0 = N::from_d(-1.0); ev = 3; ++cn.absorbed;
+        if (newE.v != newE.v) cn.error();
+        E0 = N::from_d(-1.0); ev = 3;
         break;
       }
       D newE = dyn_mul(E, D::w(dm::exp_d(neg_saf.d() * dist.v)));                   // :376 (Float64)
       if (newE.v <= minE.d()) newE = D(zero);                                       // :377-379
       D depv = dyn_sub(E, newE);                                                    // :383 / :385 (not / dx, Q2)
       tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);
-      if (newE.v == 0.0) { E0 = N::from_d(-1.0); ev = 1; ++cn.absorbed; break; }    // :390-394
+      if (newE.v == 0.0) { E0 = N::from_d(-1.0); ev = 1; break; }    // :390-394
       x = dyn_add(x, dyn_mul(D(mu), dist));                                         // :397
       t = dyn_add(t, dyn_div(dist, D(c_light)));                                    // :398
       E = newE;                                                                     // :399
@@ -985,19 +1005,19 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
       }
       if (dead) {                                                                   // :414 / :433
         if (a.tally.mode == IMC_TALLY_EXACT) { if (a.tally.pass == 2) a.tally.lost_val[pi] = E.v; }
-        else if (E.wide) { if (a.tally.mode == IMC_TALLY_FIXED) cn.lost_fx += __double2ll_rn((E.v / escale.d()) * a.tally.fx_mul_lost); else cn.lost += E.v / escale.d(); }
+        else if (E.wide) cn.lose_value(a.tally, E.v / escale.d());
         else cn.lose<P>(a.tally, E.narrow() / escale);
-        E0 = N::from_d(-1.0); ev = 2; ++cn.escaped;
+        E0 = N::from_d(-1.0); ev = 2;
         break;
       }
       if (dist.v == dist_col.v) {                                                   // :446-453
         mu = one - two * d.uniform();
         while (mu == zero) mu = one - two * d.uniform();
       }
-      if (dist.v == dist_cen.v) { ev = 0; ++cn.census; break; }                     // :455-463
+      if (dist.v == dist_cen.v) { ev = 0; break; }                     // :455-463
     }
     if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = nseg; continue; }
-    cn.seg += (unsigned long long)nseg;
+    cn.finish(ev, nseg);
     if (ev == 0) {
       zero.store(a.p.t, pi); N::from_d(x.v).store(a.p.x, pi); mu.store(a.p.mu, pi); N::from_d(E.v).store(a.p.E, pi); a.p.cx[pi] = cell;
     } else E0.store(a.p.E0, pi);

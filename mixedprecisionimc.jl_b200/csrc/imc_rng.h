@@ -127,36 +127,44 @@ struct PhiloxDraw {
 // `while mu == 0` resampling come from a separate sequential stream.
 template <class P>
 struct SegDraw {
-  uint32_t key[2], ctr[4], buf[4];
-  uint32_t n;       // current segment (0-based); 0xffffffff before the first
-  bool extra_used;
-  PhiloxStream extra;
-  IMC_HD void init(uint64_t seed, uint64_t id, uint32_t step) {
-    key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
-    ctr[0] = (uint32_t)id; ctr[1] = (uint32_t)(id >> 32); ctr[2] = step; ctr[3] = STREAM_TRACK << 28;
+  uint32_t buf[4];
+  uint32_t id_lo, id_hi;
+  uint32_t n;        // current segment (0-based); 0xffffffff before the first
+  uint32_t extra_n;  // bit 31: the segment's reserved uniform is used; low bits: extra words consumed so far
+  IMC_HD void init(uint64_t id) {
+    id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32);
     buf[0] = buf[1] = buf[2] = buf[3] = 0u;
     n = 0xffffffffu;
-    extra_used = false;
-    extra.init(seed, id, step, STREAM_TRACK_EXTRA);
+    extra_n = 0u;
   }
-  IMC_HD void next_segment() {
+  // seed / step are passed in (kernel-uniform values) instead of being carried per thread
+  IMC_HD void next_segment(uint64_t seed, uint32_t step) {
     n += 1u;
+    extra_n &= 0x7fffffffu;
     if (P::id == 2 || (n & 1u) == 0u) {
-      uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3] | (P::id == 2 ? n : (n >> 1))};
+      uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+      uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? n : (n >> 1))};
       Philox::block(c, key, buf);
     }
-    extra_used = false;
   }
-  IMC_HD Num<P> randexp() {
+  IMC_HD Num<P> randexp() const {
     if constexpr (P::id == 2) return Num<P>(randexp64_from_word(((uint64_t)buf[1] << 32) | buf[0]));
     else return Num<P>(P::rnd(randexp32_from_word((n & 1u) ? buf[2] : buf[0])));
   }
-  IMC_HD Num<P> uniform() {
-    if (extra_used) {  // second and later uniforms of one segment (1-D `while mu == 0`)
-      if constexpr (P::id == 2) return uniform_from_word<P>(extra.next_u64());
-      else return uniform_from_word<P>((uint64_t)extra.next_u32());
+  IMC_HD uint32_t extra_word(uint64_t seed, uint32_t step) {  // sequential words of the extra stream, block made on demand
+    uint32_t j = extra_n & 0x7fffffffu;
+    extra_n += 1u;
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK_EXTRA << 28) | (j >> 2)}, o[4];
+    Philox::block(c, key, o);
+    return (j & 3u) == 0u ? o[0] : (j & 3u) == 1u ? o[1] : (j & 3u) == 2u ? o[2] : o[3];
+  }
+  IMC_HD Num<P> uniform(uint64_t seed, uint32_t step) {
+    if (extra_n & 0x80000000u) {  // second and later uniforms of one segment (1-D `while mu == 0`)
+      if constexpr (P::id == 2) { uint64_t lo = extra_word(seed, step); uint64_t hi = extra_word(seed, step); return uniform_from_word<P>((hi << 32) | lo); }
+      else return uniform_from_word<P>((uint64_t)extra_word(seed, step));
     }
-    extra_used = true;
+    extra_n |= 0x80000000u;
     if constexpr (P::id == 2) return uniform_from_word<P>(((uint64_t)buf[3] << 32) | buf[2]);
     else return uniform_from_word<P>((uint64_t)((n & 1u) ? buf[3] : buf[1]));
   }

@@ -609,17 +609,17 @@ struct Oracle : EngineBase {
 
   // MC / MC2D: per-segment reserved Philox words (SegDraw); MC_RW: sequential Philox stream; replay: tape
   struct TDraws {
-    bool tape, seg; PhiloxDraw<P> ph; SegDraw<P> sg; TapeDraw<P> tp;
-    void next_segment() { if (!tape && seg) sg.next_segment(); }
-    N uniform() { return tape ? tp.uniform() : seg ? sg.uniform() : ph.uniform(); }
+    bool tape, seg; PhiloxDraw<P> ph; SegDraw<P> sg; TapeDraw<P> tp; uint64_t seed; uint32_t step;
+    void next_segment() { if (!tape && seg) sg.next_segment(seed, step); }
+    N uniform() { return tape ? tp.uniform() : seg ? sg.uniform(seed, step) : ph.uniform(); }
     N randexp() { return tape ? tp.randexp() : seg ? sg.randexp() : ph.randexp(); }
     double randexp64() { return tape ? tp.randexp64() : ph.randexp64(); }
     bool over() const { return tape && tp.exhausted(); }
   };
   TDraws track_draws(size_t slot, int64_t step, bool per_segment = true) {
-    TDraws d; d.tape = cfg.rng_mode == IMC_RNG_TAPE; d.seg = per_segment;
+    TDraws d; d.tape = cfg.rng_mode == IMC_RNG_TAPE; d.seg = per_segment; d.seed = (uint64_t)cfg.seed; d.step = (uint32_t)step;
     if (d.tape) d.tp.init(tt_uni.data(), tt_nuni, tt_exp.data(), tt_nexp, (size_t)tt_slots, slot);
-    else if (per_segment) d.sg.init((uint64_t)cfg.seed, ids[slot], (uint32_t)step);
+    else if (per_segment) d.sg.init(ids[slot]);
     else d.ph.init((uint64_t)cfg.seed, ids[slot], (uint32_t)step, STREAM_TRACK);
     return d;
   }
