@@ -86,7 +86,7 @@ def graded_nodes_1d(length: float, n_cells: int, dx_min: float) -> np.ndarray:
     """Nodes on [0, length] with geometric grading toward x = 0 (first cell dx_min), Float64."""
     if n_cells * dx_min >= length:
         return np.linspace(0.0, length, n_cells + 1)
-    lo, hi = 1.0 + 1e-12, 2.0
+    lo, hi = 1.0 + 1e-12, float(np.exp(600.0 / n_cells))  # keep r ** n_cells finite
     f = lambda r: dx_min * (r ** n_cells - 1.0) / (r - 1.0) - length
     for _ in range(200):
         mid = 0.5 * (lo + hi)
