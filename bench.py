@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tally", default="auto", choices=["auto", "atomic", "fixed"])
-    ap.add_argument("--track", default="auto", choices=["auto", "history", "refill"], help="tracking schedule (auto = measured)")
+    ap.add_argument("--track", default="auto", choices=["auto", "history", "refill", "event"], help="tracking schedule (auto = measured)")
     args = ap.parse_args()
 
     w = WORKLOADS[args.workload]
@@ -160,7 +160,7 @@ def main():
                           f"{particles} particles per GPU (NMAX), NINPUT = NMAX/2, PAIRWISE FALSE",
               "mesh": list(mesh), "particles_per_gpu": particles, "precision": w["precision"],
               "l2_policy": "inputs larger than L2 (particle state >> 126 MB); no explicit flush",
-              "tally_mode": args.tally, "tracking": f"history-based, schedule {args.track} (static grid-stride | warp refill), 256 threads/block"}
+              "tally_mode": args.tally, "tracking": f"schedule {args.track} (history static grid-stride | history warp-refill | event-based), 256 threads/block"}
 
     # ---------------------------------------------------------------- reference arm (CPU oracle)
     if args.impl == "reference":
@@ -198,7 +198,7 @@ def main():
     glib = lib.ImcLib(entry.LIB)
     tally_mode = {"auto": lib.TALLY_AUTO, "atomic": lib.TALLY_ATOMIC, "fixed": lib.TALLY_FIXED}[args.tally]
     inputs = make_inputs(w, particles * world, mesh, world)  # NMAX / NINPUT are global; each rank emits its stripe
-    track_mode = {"auto": lib.TRACK_AUTO, "history": lib.TRACK_HISTORY, "refill": lib.TRACK_REFILL}[args.track]
+    track_mode = {"auto": lib.TRACK_AUTO, "history": lib.TRACK_HISTORY, "refill": lib.TRACK_REFILL, "event": lib.TRACK_EVENT}[args.track]
     sim = driver.setup(inputs, glib, device=local_rank, rank=rank, world=world, tally_mode=tally_mode, track_mode=track_mode)
     sim.save_history = False
     eng = sim.engine
@@ -242,7 +242,7 @@ def main():
     for _ in range(args.steps):
         r = step_resident()
         seg += r["transport"]["segments"]; hist += r["transport"]["histories"]; kms += r["transport"]["kernel_ms"]
-        variants.append({1: "static", 2: "refill"}.get(r["transport"]["variant"], "?"))
+        variants.append({1: "static", 2: "refill", 3: "event"}.get(r["transport"]["variant"], "?"))
     barrier()
     ev1.record()
     torch.cuda.synchronize()

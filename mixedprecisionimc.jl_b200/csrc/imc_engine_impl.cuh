@@ -116,6 +116,12 @@ struct EngineT : EngineBase {
   DBuf<double> rec_val[2], lost_val, lost_scratch;
   DBuf<unsigned char> sort_temp;
   int last_mode = IMC_TALLY_ATOMIC;
+  // event-based schedule
+  DBuf<unsigned> ev_list[2], ev_extra;
+  DBuf<int> ev_nseg;
+  DBuf<unsigned long long> ev_count;
+  double rate_event = 0;
+  int ev_launches = 0;
   // outcomes
   DBuf<signed char> out_event;
   DBuf<int> out_nseg;
@@ -472,7 +478,33 @@ struct EngineT : EngineBase {
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
+  // event-based schedule: one segment per launch, survivors compacted into the next launch's index list
+  int launch_event(TrackArgs<P>& a, size_t smem) {
+    IMC_CK(ev_list[0].ensure((size_t)n_part)); IMC_CK(ev_list[1].ensure((size_t)n_part));
+    IMC_CK(ev_nseg.ensure((size_t)n_part)); IMC_CK(ev_extra.ensure((size_t)n_part)); IMC_CK(ev_count.ensure(1));
+    a.ev_nseg = ev_nseg.p; a.ev_extra = ev_extra.p; a.ev_count = ev_count.p;
+    long long n_active = n_part;
+    int it = 0;
+    smem += COUNTER_SMEM_BYTES;
+    while (n_active > 0) {
+      a.ev_in = it == 0 ? nullptr : ev_list[it & 1].p;
+      a.ev_out = ev_list[(it + 1) & 1].p;
+      IMC_CK(cudaMemsetAsync(ev_count.p, 0, sizeof(unsigned long long), stream));
+      unsigned grid = (unsigned)std::min<long long>((n_active + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * IMC_TRACK_MIN_BLOCKS);
+      if (geom == 1) k_track_event<P, 1><<<grid, TRACK_THREADS, smem, stream>>>(a, n_active, it == 0);
+      else k_track_event<P, 2><<<grid, TRACK_THREADS, smem, stream>>>(a, n_active, it == 0);
+      ++n_launch; ++it;
+      IMC_CK(cudaGetLastError());
+      unsigned long long cnt = 0;
+      IMC_CK(cudaMemcpyAsync(&cnt, ev_count.p, sizeof cnt, cudaMemcpyDeviceToHost, stream));
+      IMC_CK(cudaStreamSynchronize(stream));
+      n_active = (long long)cnt;
+    }
+    ev_launches = it;
+    return IMC_OK;
+  }
   int launch_track(TrackArgs<P>& a, int variant, unsigned grid, size_t smem) {
+    if (variant == IMC_TRACK_EVENT) return launch_event(a, smem);
     IMC_CK(cudaMemsetAsync(over_flag.p + 1, 0, sizeof(unsigned long long), stream));
     smem += COUNTER_SMEM_BYTES;
     const bool tape = a.rng.tape != 0;
@@ -523,15 +555,23 @@ struct EngineT : EngineBase {
     // schedule: static grid-stride or dynamic warp refill.  AUTO measures both (alternating on the first
     // steps, re-probing every 32 calls) and keeps the one with the higher segments/s.
     int variant = cfg.track_mode;
-    if (variant == IMC_TRACK_EVENT) variant = IMC_TRACK_AUTO;  // event-based variant: DESIGN.md (not built yet)
+    const bool event_ok = !(geom == 1 && cfg.randomwalk) && mode != IMC_TALLY_EXACT && cfg.rng_mode != IMC_RNG_TAPE && n_part < (1ll << 32);
     if (geom == 1 && cfg.randomwalk) variant = IMC_TRACK_HISTORY;
+    if (variant == IMC_TRACK_EVENT && !event_ok) variant = IMC_TRACK_AUTO;
     if (variant == IMC_TRACK_AUTO) {
+      // measured selection: the first calls try static, refill and (once) event-based; afterwards the two
+      // history schedules are re-probed every 32 calls and the fastest known variant runs in between
       long long phase = n_transport_calls % 32;
       if (phase == 0) variant = IMC_TRACK_HISTORY;
       else if (phase == 1) variant = IMC_TRACK_REFILL;
-      else variant = rate_static >= rate_refill ? IMC_TRACK_HISTORY : IMC_TRACK_REFILL;
+      else if (n_transport_calls == 2 && event_ok) variant = IMC_TRACK_EVENT;
+      else {
+        variant = rate_static >= rate_refill ? IMC_TRACK_HISTORY : IMC_TRACK_REFILL;
+        if (event_ok && rate_event > rate_static && rate_event > rate_refill) variant = IMC_TRACK_EVENT;
+      }
     }
     ++n_transport_calls;
+    a.ev_in = nullptr; a.ev_out = nullptr; a.ev_count = nullptr; a.ev_nseg = nullptr; a.ev_extra = nullptr;
     a.queue = over_flag.p + 1;
     a.refill_min = refill_min_env();
     if (n_part > 0) {
@@ -589,7 +629,7 @@ struct EngineT : EngineBase {
     iterations += cnt(RB_SEG);
     if (ms > 0) {
       double rate = (double)cnt(RB_SEG) / ms;
-      if (variant == IMC_TRACK_REFILL) rate_refill = rate; else rate_static = rate;
+      if (variant == IMC_TRACK_REFILL) rate_refill = rate; else if (variant == IMC_TRACK_EVENT) rate_event = rate; else rate_static = rate;
     }
     if (out) {
       out->lostenergy = (double)P::from_d(lost);

@@ -96,6 +96,7 @@ template <class P>
 struct HistDraw<P, false> {
   SegDraw<P> sg;
   __device__ __forceinline__ void init(const RngArgs&, unsigned long long id, long long) { sg.init(id); }
+  __device__ __forceinline__ void resume(unsigned long long id, unsigned next, unsigned extra) { sg.resume(id, next, extra); }
   __device__ __forceinline__ void next_segment(const RngArgs& r) { sg.next_segment(r.seed, r.step); }
   __device__ __forceinline__ Num<P> uniform(const RngArgs& r) { return sg.uniform(r.seed, r.step); }
   __device__ __forceinline__ Num<P> randexp() { return sg.randexp(); }
@@ -569,6 +570,12 @@ struct TrackArgs {
   // random-walk tables (MC_RW)
   const typename P::store_t *aVals, *ptVals;
   int n_rw_table;
+  // event-based schedule: one segment per particle per launch
+  const unsigned* ev_in;      // active particle indices (nullptr: 0..n-1)
+  unsigned* ev_out;           // particles still in flight after this launch
+  unsigned long long* ev_count;  // [0] = entries written to ev_out
+  int* ev_nseg;               // [n] segments tracked so far
+  unsigned* ev_extra;         // [n] extra-stream words consumed so far
   // dynamic schedule
   unsigned long long* queue;  // next unclaimed particle index
   int refill_min;             // refill when at least this many lanes of a warp are idle
@@ -856,6 +863,60 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
       int ev;
       if constexpr (GEOM == 1) { ev = seg1d(a, h1, d, tal, cn); if (ev >= 0) { store1d(a, h1, d, ev, cn); active = false; } }
       else { ev = seg2d(a, h2, d, tal, cn); if (ev >= 0) { store2d(a, h2, d, ev, cn); active = false; } }
+    }
+  }
+  tal.flush();
+  cn.commit(a.tally);
+}
+
+
+// ---- event-based schedule: every launch advances each in-flight particle by ONE segment -----------------
+// State is re-read and re-written every segment (B_hist per segment instead of per history) and the direction
+// vector / Philox block are recomputed, in exchange for warps whose lanes all do the same amount of work.
+// Survivors are appended to the next launch's index list with one warp-aggregated atomic.  Philox only (the
+// replay tape has per-particle cursors); EXACT tallies use the history schedules.
+template <class P, int GEOM>
+__global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_event(TrackArgs<P> a, long long n_active, int first) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
+  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
+  tal.zero();
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_round = (n_active + 31) & ~31ll;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    bool cont = false;
+    long long pi = 0;
+    if (i < n_active) {
+      pi = a.ev_in ? (long long)a.ev_in[i] : i;
+      Hist1<P> h1; Hist2<P> h2; HistDraw<P, false> d;
+      bool ok;
+      if constexpr (GEOM == 1) ok = load1d(a, pi, h1, d, cn); else ok = load2d(a, pi, h2, d, cn);
+      if (ok) {
+        const int done = first ? 0 : a.ev_nseg[pi];
+        if (!first) d.resume(a.p.id[pi], (unsigned)done, a.ev_extra[pi]);
+        int ev;
+        if constexpr (GEOM == 1) {
+          h1.nseg = done;
+          ev = seg1d(a, h1, d, tal, cn);
+          if (ev >= 0) store1d(a, h1, d, ev, cn);
+          else { h1.t.store(a.p.t, pi); h1.x.store(a.p.x, pi); h1.mu.store(a.p.mu, pi); h1.E.store(a.p.E, pi); a.p.cx[pi] = h1.cell; a.ev_nseg[pi] = h1.nseg; }
+        } else {
+          h2.nseg = done;
+          ev = seg2d(a, h2, d, tal, cn);
+          if (ev >= 0) store2d(a, h2, d, ev, cn);
+          else { h2.t.store(a.p.t, pi); h2.x.store(a.p.x, pi); h2.y.store(a.p.y, pi); h2.mu.store(a.p.mu, pi); h2.E.store(a.p.E, pi);
+                 a.p.cx[pi] = h2.xi; a.p.cy[pi] = h2.yi; a.ev_nseg[pi] = h2.nseg; }
+        }
+        if (ev < 0) { a.ev_extra[pi] = d.sg.extra_n & 0x3fffffffu; cont = true; }
+      }
+    }
+    const unsigned m = __ballot_sync(IMC_FULL_MASK, cont);
+    if (m) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.ev_count, (unsigned long long)__popc(m));
+      base = __shfl_sync(IMC_FULL_MASK, base, 0);
+      if (cont) a.ev_out[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)pi;
     }
   }
   tal.flush();

@@ -138,10 +138,18 @@ struct SegDraw {
     extra_n = 0u;
   }
   // seed / step are passed in (kernel-uniform values) instead of being carried per thread
+  // continue a history at segment `next` (event-based tracking reloads the particle every segment): the block
+  // of the current pair is regenerated on the next call whatever its parity
+  IMC_HD void resume(uint64_t id, uint32_t next, uint32_t extra_words) {
+    init(id);
+    n = next - 1u;
+    extra_n = extra_words | 0x40000000u;  // bit 30: buffer invalid
+  }
   IMC_HD void next_segment(uint64_t seed, uint32_t step) {
     n += 1u;
-    extra_n &= 0x7fffffffu;
-    if (P::id == 2 || (n & 1u) == 0u) {
+    const bool stale = (extra_n & 0x40000000u) != 0u;
+    extra_n &= 0x3fffffffu;
+    if (P::id == 2 || (n & 1u) == 0u || stale) {
       uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
       uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? n : (n >> 1))};
       Philox::block(c, key, buf);
@@ -152,7 +160,7 @@ struct SegDraw {
     else return Num<P>(P::rnd(randexp32_from_word((n & 1u) ? buf[2] : buf[0])));
   }
   IMC_HD uint32_t extra_word(uint64_t seed, uint32_t step) {  // sequential words of the extra stream, block made on demand
-    uint32_t j = extra_n & 0x7fffffffu;
+    uint32_t j = extra_n & 0x3fffffffu;
     extra_n += 1u;
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK_EXTRA << 28) | (j >> 2)}, o[4];
