@@ -559,12 +559,15 @@ struct EngineT : EngineBase {
     if (geom == 1 && cfg.randomwalk) variant = IMC_TRACK_HISTORY;
     if (variant == IMC_TRACK_EVENT && !event_ok) variant = IMC_TRACK_AUTO;
     if (variant == IMC_TRACK_AUTO) {
-      // measured selection: the first calls try static, refill and (once) event-based; afterwards the two
-      // history schedules are re-probed every 32 calls and the fastest known variant runs in between
+      // measured selection: the two history schedules are probed on the first two calls and re-probed every
+      // 32 calls; the fastest known variant runs in between.  The event-based variant joins the probe only when
+      // IMC_AUTO_PROBE_EVENT=1: measured on B200 it is 17x (Su-Olson) to 40x (crooked pipe) slower, because the
+      // last few long histories need thousands of nearly empty launches.
+      static const bool probe_event = getenv("IMC_AUTO_PROBE_EVENT") && atoi(getenv("IMC_AUTO_PROBE_EVENT")) != 0;
       long long phase = n_transport_calls % 32;
       if (phase == 0) variant = IMC_TRACK_HISTORY;
       else if (phase == 1) variant = IMC_TRACK_REFILL;
-      else if (n_transport_calls == 2 && event_ok) variant = IMC_TRACK_EVENT;
+      else if (n_transport_calls == 2 && event_ok && probe_event) variant = IMC_TRACK_EVENT;
       else {
         variant = rate_static >= rate_refill ? IMC_TRACK_HISTORY : IMC_TRACK_REFILL;
         if (event_ok && rate_event > rate_static && rate_event > rate_refill) variant = IMC_TRACK_EVENT;
