@@ -1,0 +1,89 @@
+"""The two non-replay correctness modes of BASELINE.json on the GPU engine.
+
+Statistical mode: time-dependent material / radiation energy and temperature fields of the CUDA engine lie
+within 3 sigma of a multi-seed ensemble of the oracle (different seeds on the two sides, so this does not rest
+on the shared RNG).  Benchmark mode: the Su-Olson radiation energy density at t = 1 matches the table embedded
+in the reference deck (src/inputs/SuOlson.txt:71-72) within the Monte Carlo error; the infinite-medium deck
+relaxes to its analytic equilibrium."""
+import numpy as np
+import pytest
+
+from mpimc_b200 import decks, driver, lib
+
+pytestmark = pytest.mark.gpu
+
+
+def run(inputs, library, steps, seed, **cfg):
+    d = dict(inputs); d["SEED"] = str(seed)
+    sim = driver.setup(d, library, **cfg)
+    sim.save_history = False
+    for _ in range(steps):
+        sim.advance()
+    return {k: sim.engine.field(k) for k in ("temp", "matenergydens", "radenergydens")}
+
+
+def coarse(f, n=20):
+    f = f.reshape(-1)
+    m = (f.size // n) * n
+    return f[:m].reshape(n, -1).mean(axis=1)
+
+
+@pytest.mark.parametrize("case", ["suolson-f64", "suolson-f32", "suolson-f16", "crooked-f32"])
+def test_statistical_mode_within_3_sigma_of_oracle_ensemble(gpu_lib, oracle_lib, case):
+    deck, prec = case.split("-")
+    precision = {"f64": "FLOAT64", "f32": "FLOAT32", "f16": "FLOAT16"}[prec]
+    if deck == "suolson":
+        inputs, steps = decks.suolson(precision=precision, n_input=4000, n_max=60000), 40
+    else:
+        inputs, steps = decks.crooked_pipe(precision=precision, n_input=6000, n_max=60000, cellmin=1, pairwise="FALSE"), 12
+    ref = [run(inputs, oracle_lib, steps, 1000 + s) for s in range(10)]
+    gpu = [run(inputs, gpu_lib, steps, 2000 + s) for s in range(4)]
+    for name in ("temp", "matenergydens", "radenergydens"):
+        r = np.array([coarse(x[name]) for x in ref])
+        g = np.array([coarse(x[name]) for x in gpu])
+        mean, sd = r.mean(axis=0), r.std(axis=0, ddof=1)
+        # the mean of 4 GPU runs against the ensemble mean: sigma^2 (1/4 + 1/10), plus a floor for bins with no noise
+        tol = 3.0 * sd * np.sqrt(1 / 4 + 1 / 10) + 1e-3 * np.abs(mean).max() + (5e-3 * np.abs(mean) if prec == "f16" else 0)
+        dev = np.abs(g.mean(axis=0) - mean)
+        assert np.all(dev <= tol), (name, float((dev / tol).max()))
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32"])
+def test_suolson_benchmark_on_gpu(gpu_lib, precision):
+    sim = driver.setup(decks.suolson(precision=precision, n_input=40000, n_max=2000000), gpu_lib)
+    sim.save_history = False
+    while float(sim.simvars.t) < 1.0 - 1e-6:
+        r = sim.advance()
+    assert sim.simvars.step == 500
+    rad = sim.engine.field("radenergydens")
+    cent = np.asarray(sim.mesh.centers, dtype=float)
+    for x, y in zip(decks.SUOLSON_XBENCH, decks.SUOLSON_YBENCH):
+        i = int(np.argmin(np.abs(cent - x)))
+        got = rad[max(0, i - 2):i + 3].mean()
+        # IMC time discretisation (dt = 0.002, alpha = 4) + Monte Carlo noise: the reference's own accuracy class
+        assert abs(got - y) < 0.02 + 0.04 * y, (x, y, got)
+    assert abs(r["energy"]["energy_error"]) < (1e-9 if precision == "FLOAT64" else 1e-3)
+
+
+def test_infinite_medium_equilibrium_on_gpu(gpu_lib):
+    sim = driver.setup(decks.infinite_medium(precision="FLOAT32", n_input=20000, n_max=200000), gpu_lib)
+    sim.save_history = False
+    for _ in range(80):
+        sim.advance()
+    assert abs(sim.engine.field("temp").mean() - 0.98698) < 1e-3
+    assert abs(sim.engine.field("radenergydens").mean() - 0.013019) < 4e-4
+
+
+def test_mixed_precision_error_study_shape(gpu_lib):
+    """BASELINE config 4 in miniature: Su-Olson in Float16 / Float32 against Float64 — the relative error of the
+    radiation field grows as the precision drops, and Float32 stays close to Float64."""
+    out = {}
+    for precision in ("FLOAT64", "FLOAT32", "FLOAT16"):
+        sim = driver.setup(decks.suolson(precision=precision, n_input=20000, n_max=400000, pairwise="TRUE"), gpu_lib, tally_mode=lib.TALLY_FIXED)
+        sim.save_history = False
+        for _ in range(100):
+            sim.advance()
+        out[precision] = coarse(sim.engine.field("radenergydens")[:200], 10)
+    err = lambda a: np.linalg.norm(out[a] - out["FLOAT64"]) / np.linalg.norm(out["FLOAT64"])
+    assert err("FLOAT32") < 0.03
+    assert err("FLOAT16") < 0.25
