@@ -68,8 +68,9 @@ typedef enum { IMC_RNG_PHILOX = 0, IMC_RNG_TAPE = 1 } imc_rng_mode;
  *   EXACT  : reference order — per-deposit records sorted by (cell, particle, segment) and summed
  *            sequentially (PAIRWISE = FALSE, imc_transport.jl:120) or with Julia's pairwise
  *            sum (PAIRWISE = TRUE, imc_transport.jl:198-205); O(segments) memory
- *   AUTO   : PAIRWISE = FALSE -> ATOMIC; PAIRWISE = TRUE -> EXACT when the records fit the
- *            budget, else FIXED */
+ *   AUTO   : PAIRWISE = TRUE or PRECISION = FLOAT16 (summation order is part of the reference's result)
+ *            -> EXACT while the records fit exact_record_budget, else FIXED (PAIRWISE) / ATOMIC;
+ *            otherwise ATOMIC */
 typedef enum { IMC_TALLY_AUTO = 0, IMC_TALLY_ATOMIC = 1, IMC_TALLY_FIXED = 2, IMC_TALLY_EXACT = 3 } imc_tally_mode;
 /* tracking kernel variant */
 typedef enum { IMC_TRACK_AUTO = 0, IMC_TRACK_HISTORY = 1, IMC_TRACK_REFILL = 2, IMC_TRACK_EVENT = 3 } imc_track_mode;

@@ -412,7 +412,9 @@ struct EngineT : EngineBase {
     int mode = cfg.tally_mode;
     // AUTO: PAIRWISE = TRUE asks for the deterministic tree -> EXACT (Julia's pairwise order) while the deposit
     // records fit the budget, else the order-free fixed-point accumulation; PAIRWISE = FALSE -> float atomics
-    if (mode == IMC_TALLY_AUTO) mode = cfg.pairwise ? IMC_TALLY_EXACT : IMC_TALLY_ATOMIC;
+    // Float16 decks: sequential Float16 accumulation stagnates, i.e. the summation order is part of the
+    // reference's result (it is what the mixed-precision study measures) -> EXACT as well, within the budget.
+    if (mode == IMC_TALLY_AUTO) mode = (cfg.pairwise || P::id == 0) ? IMC_TALLY_EXACT : IMC_TALLY_ATOMIC;
     return mode;
   }
   // smallest cell volume / scale, for fixed-point scaling
@@ -595,10 +597,10 @@ struct EngineT : EngineBase {
         long long budget = cfg.exact_record_budget > 0 ? cfg.exact_record_budget : (1ll << 28);
         if (R > budget) {
           if (cfg.tally_mode == IMC_TALLY_EXACT) { err = "EXACT tally mode: deposit records exceed exact_record_budget"; return IMC_ERR_NOMEM; }
-          mode = IMC_TALLY_FIXED;  // AUTO: fall back to the order-free fixed-point accumulation
-          if (!red_fixed) { IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream)); red_fixed = true; }
+          mode = cfg.pairwise ? IMC_TALLY_FIXED : IMC_TALLY_ATOMIC;  // AUTO: fall back to order-free fixed point / float atomics
+          if (mode == IMC_TALLY_FIXED && !red_fixed) { IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream)); red_fixed = true; }
           a.tally.mode = mode; a.tally.pass = 0;
-          IMC_RC(prepare_fixed(a.tally));
+          if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
           smem = smem_for(mode, nc * ns); a.tally.use_smem = smem <= 48 * 1024 ? 1 : 0; if (!a.tally.use_smem) smem = 0;
           IMC_RC(launch_track(a, variant, grid, smem));
         } else {
