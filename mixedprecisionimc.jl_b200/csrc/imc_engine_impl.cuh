@@ -81,7 +81,7 @@ struct EngineT : EngineBase {
   DBuf<double> temp;
   DBuf<CellProp1<P>> cp1;
   DBuf<CellProp2<P>> cp2;
-  DBuf<AxisProp<P>> axx, axy;
+  DBuf<AxisProp<P>> axx;   // x entries, then y entries
   MeshDev<P> m;
   // particles (double buffer for the stable compaction)
   PartBufs<P> pb[2];
@@ -246,6 +246,7 @@ struct EngineT : EngineBase {
     RngArgs r;
     r.tape = cfg.rng_mode == IMC_RNG_TAPE;
     r.seed = (unsigned long long)cfg.seed;
+    Philox::round_keys(r.seed, r.rk);
     r.step = (unsigned int)step;
     if (source) { r.uni = st_uni.p; r.ex = nullptr; r.n_uni = st_nuni; r.n_exp = 0; r.stride = st_slots; }
     else { r.uni = tt_uni.p; r.ex = tt_exp.p; r.n_uni = tt_nuni; r.n_exp = tt_nexp; r.stride = tt_slots; }
@@ -265,7 +266,7 @@ struct EngineT : EngineBase {
     }
     IMC_RC(upload(dx, dx_, nx));
     if (geom == 2) IMC_RC(upload(dy, dy_, ny)); else { double one = 1.0; IMC_RC(upload(dy, &one, 1)); }
-    IMC_CK(wx.alloc(nx)); IMC_CK(wy.alloc(ny)); IMC_CK(axx.alloc(nx)); IMC_CK(axy.alloc(ny));
+    IMC_CK(wx.alloc(nx)); IMC_CK(wy.alloc(ny)); IMC_CK(axx.alloc(nx + ny));
     IMC_RC(upload(sa_c, sac, nc)); IMC_RC(upload(sa_p, sap, nc)); IMC_RC(upload(ss_c, ssc, nc)); IMC_RC(upload(ss_p, ssp, nc));
     IMC_RC(upload(sa, sac, nc)); IMC_RC(upload(ss, ssc, nc));
     IMC_RC(upload(sigma_static, sstat, nc));
@@ -299,7 +300,7 @@ struct EngineT : EngineBase {
     m.matenergydens = matenergydens.p; m.radenergydens = radenergydens.p; m.nrg_inc = nrg_inc.p;
     m.energydep = energydep.p; m.emittedenergy = emittedenergy.p;
     for (int k = 0; k < 4; ++k) m.tsurf[k] = tsurf[k].p;
-    m.cp1 = cp1.p; m.cp2 = cp2.p; m.axx = axx.p; m.axy = axy.p;
+    m.cp1 = cp1.p; m.cp2 = cp2.p; m.axx = axx.p; m.axy = axx.p + nx;
     for (int k = 0; k < IMC_MAX_SCALES; ++k) { m.scales[k] = k < ns ? P::from_d(cfg.energyscales[k]) : (Cc)1; m.scales_d[k] = (double)m.scales[k]; }
     m.ds = P::from_d(cfg.distancescale); m.c = P::from_d(cfg.phys_c); m.a = P::from_d(cfg.phys_a); m.alpha = P::from_d(cfg.alpha);
     for (int k = 0; k < 4; ++k) m.bc[k] = cfg.bc[k];
@@ -505,16 +506,30 @@ struct EngineT : EngineBase {
     ev_launches = it;
     return IMC_OK;
   }
+  // history kernels: schedule x geometry x draw source x tally kind.  The Philox kernels with ATOMIC / FIXED tallies
+  // are compiled per tally kind (no mode tests in the segment loop); EXACT passes and replay tapes read TallyArgs.
+  template <bool TAPE, int TK>
+  void launch_history(TrackArgs<P>& a, int variant, unsigned grid, size_t smem) {
+    if (variant == IMC_TRACK_REFILL) {
+      if (geom == 1) k_track_refill<P, 1, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      else k_track_refill<P, 2, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    } else {
+      if (geom == 1) k_track1d<P, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      else k_track2d<P, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
+    }
+  }
   int launch_track(TrackArgs<P>& a, int variant, unsigned grid, size_t smem) {
     if (variant == IMC_TRACK_EVENT) return launch_event(a, smem);
     IMC_CK(cudaMemsetAsync(over_flag.p + 1, 0, sizeof(unsigned long long), stream));
     smem += COUNTER_SMEM_BYTES;
     const bool tape = a.rng.tape != 0;
     if (geom == 1 && cfg.randomwalk) k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
-    else if (variant == IMC_TRACK_REFILL && geom == 1) { if (tape) k_track_refill<P, 1, true><<<grid, TRACK_THREADS, smem, stream>>>(a); else k_track_refill<P, 1, false><<<grid, TRACK_THREADS, smem, stream>>>(a); }
-    else if (variant == IMC_TRACK_REFILL) { if (tape) k_track_refill<P, 2, true><<<grid, TRACK_THREADS, smem, stream>>>(a); else k_track_refill<P, 2, false><<<grid, TRACK_THREADS, smem, stream>>>(a); }
-    else if (geom == 1) { if (tape) k_track1d<P, true><<<grid, TRACK_THREADS, smem, stream>>>(a); else k_track1d<P, false><<<grid, TRACK_THREADS, smem, stream>>>(a); }
-    else { if (tape) k_track2d<P, true><<<grid, TRACK_THREADS, smem, stream>>>(a); else k_track2d<P, false><<<grid, TRACK_THREADS, smem, stream>>>(a); }
+    else if (tape) launch_history<true, TK_RUNTIME>(a, variant, grid, smem);
+    else if (a.tally.mode == IMC_TALLY_ATOMIC && !a.tally.use_smem) launch_history<false, TK_ATOMIC_G>(a, variant, grid, smem);
+    else if (a.tally.mode == IMC_TALLY_ATOMIC) launch_history<false, TK_ATOMIC_S>(a, variant, grid, smem);
+    else if (a.tally.mode == IMC_TALLY_FIXED && !a.tally.use_smem) launch_history<false, TK_FIXED_G>(a, variant, grid, smem);
+    else if (a.tally.mode == IMC_TALLY_FIXED) launch_history<false, TK_FIXED_S>(a, variant, grid, smem);
+    else launch_history<false, TK_RUNTIME>(a, variant, grid, smem);
     ++n_launch;
     IMC_CK(cudaGetLastError());
     return IMC_OK;

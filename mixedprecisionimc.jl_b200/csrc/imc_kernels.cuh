@@ -68,6 +68,7 @@ struct RngArgs {
   int tape;
   unsigned long long seed;
   unsigned int step;
+  unsigned int rk[20];   // Philox round keys of `seed` (Philox::round_keys)
   const double *uni, *ex;
   int n_uni, n_exp;
   long long stride;
@@ -97,7 +98,7 @@ struct HistDraw<P, false> {
   SegDraw<P> sg;
   __device__ __forceinline__ void init(const RngArgs&, unsigned long long id, long long) { sg.init(id); }
   __device__ __forceinline__ void resume(unsigned long long id, unsigned next, unsigned extra) { sg.resume(id, next, extra); }
-  __device__ __forceinline__ void next_segment(const RngArgs& r) { sg.next_segment(r.seed, r.step); }
+  __device__ __forceinline__ void next_segment(const RngArgs& r) { sg.next_segment_rk(r.rk, r.step); }
   __device__ __forceinline__ Num<P> uniform(const RngArgs& r) { return sg.uniform(r.seed, r.step); }
   __device__ __forceinline__ Num<P> randexp() { return sg.randexp(); }
   __device__ __forceinline__ bool over() const { return false; }
@@ -466,38 +467,50 @@ struct TallyArgs {
   double* lost_val;         // [n] energy lost through a VACUUM boundary (NaN = none)
 };
 
-template <class P>
+// Tally kind of a tracking kernel.  TK_RUNTIME reads TallyArgs (EXACT passes, replay tape, MC_RW, event schedule,
+// census tally); the four other kinds hard-wire the accumulator representation and its location, so the hot
+// Philox history kernels carry no mode tests in the segment loop.
+enum { TK_RUNTIME = -1, TK_ATOMIC_G = 0, TK_ATOMIC_S = 1, TK_FIXED_G = 2, TK_FIXED_S = 3 };
+template <int TK>
+struct TKind {
+  static __device__ __forceinline__ bool exact(const TallyArgs& a) { if constexpr (TK == TK_RUNTIME) return a.mode == IMC_TALLY_EXACT; else return false; }
+  static __device__ __forceinline__ bool fixed(const TallyArgs& a) { if constexpr (TK == TK_RUNTIME) return a.mode == IMC_TALLY_FIXED; else return TK == TK_FIXED_G || TK == TK_FIXED_S; }
+  static __device__ __forceinline__ bool smem(const TallyArgs& a) { if constexpr (TK == TK_RUNTIME) return a.use_smem != 0; else return TK == TK_ATOMIC_S || TK == TK_FIXED_S; }
+};
+
+template <class P, int TK = TK_RUNTIME>
 struct Tally {
   using A = typename AccType<P>::type;
+  using K = TKind<TK>;
   const TallyArgs& a;
   A* s_acc; unsigned long long* s_fx;
   __device__ __forceinline__ Tally(const TallyArgs& a_, unsigned char* smem) : a(a_) {
     s_acc = reinterpret_cast<A*>(smem); s_fx = reinterpret_cast<unsigned long long*>(smem);
   }
   __device__ __forceinline__ void zero() {
-    if (!a.use_smem || a.mode == IMC_TALLY_EXACT) return;
-    if (a.mode == IMC_TALLY_FIXED) { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_fx[i] = 0ull; }
+    if (!K::smem(a) || K::exact(a)) return;
+    if (K::fixed(a)) { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_fx[i] = 0ull; }
     else { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_acc[i] = (A)0; }
     __syncthreads();
   }
   __device__ __forceinline__ void add(long long idx, Num<P> v, long long rec = 0, bool wide = false, double wide_v = 0.0) {
-    if (a.mode == IMC_TALLY_EXACT) {
+    if (K::exact(a)) {
       if (a.pass == 2) { a.rec_key[rec] = (unsigned)idx | (wide ? 0x80000000u : 0u); a.rec_val[rec] = wide ? wide_v : v.d(); }
       return;
     }
-    if (a.mode == IMC_TALLY_FIXED) {
+    if (K::fixed(a)) {
       long long q = __double2ll_rn(v.d() * a.fx_mul);
-      if (a.use_smem) atomicAdd(&s_fx[idx], (unsigned long long)q);
+      if (K::smem(a)) atomicAdd(&s_fx[idx], (unsigned long long)q);
       else atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + idx, (unsigned long long)q);
     } else {
-      if (a.use_smem) atomicAdd(&s_acc[idx], (A)v.v);
+      if (K::smem(a)) atomicAdd(&s_acc[idx], (A)v.v);
       else atomicAdd(a.g_acc + idx, v.d());
     }
   }
   __device__ __forceinline__ void flush() {
-    if (!a.use_smem || a.mode == IMC_TALLY_EXACT) return;
+    if (!K::smem(a) || K::exact(a)) return;
     __syncthreads();
-    if (a.mode == IMC_TALLY_FIXED) {
+    if (K::fixed(a)) {
       for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) { unsigned long long q = s_fx[i]; if (q) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + i, q); }
     } else {
       for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) { A q = s_acc[i]; if (q != (A)0) atomicAdd(a.g_acc + i, (double)q); }
@@ -532,21 +545,23 @@ struct Counters {
   }
   __device__ __forceinline__ void error() { atomicAdd(&s[RB_ERRORS], 1ull); }
   __device__ __forceinline__ void rw() { atomicAdd(&s[RB_RW], 1ull); }
+  template <int TK = TK_RUNTIME>
   __device__ __forceinline__ void lose_value(const TallyArgs& a, double e_over_scale) {
-    if (a.mode == IMC_TALLY_FIXED) atomicAdd(&s[RB_LOST], (unsigned long long)__double2ll_rn(e_over_scale * a.fx_mul_lost));
+    if (TKind<TK>::fixed(a)) atomicAdd(&s[RB_LOST], (unsigned long long)__double2ll_rn(e_over_scale * a.fx_mul_lost));
     else atomicAdd(reinterpret_cast<double*>(&s[RB_LOST]), e_over_scale);
   }
-  template <class P>
+  template <class P, int TK = TK_RUNTIME>
   __device__ __forceinline__ void lose(const TallyArgs& a, Num<P> e_over_scale, long long pi = 0, double e_raw = 0.0) {
-    if (a.mode == IMC_TALLY_EXACT) { if (a.pass == 2) a.lost_val[pi] = e_raw; return; }
-    lose_value(a, e_over_scale.d());
+    if (TKind<TK>::exact(a)) { if (a.pass == 2) a.lost_val[pi] = e_raw; return; }
+    lose_value<TK>(a, e_over_scale.d());
   }
+  template <int TK = TK_RUNTIME>
   __device__ __forceinline__ void commit(const TallyArgs& a) {
     __syncthreads();
-    if (a.mode == IMC_TALLY_EXACT && a.pass == 1) return;
+    if (TKind<TK>::exact(a) && a.pass == 1) return;
     const int k = threadIdx.x;
     if (k >= RB_NSCALARS || s[k] == 0ull) return;
-    if (a.mode == IMC_TALLY_FIXED) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + a.sc0 + k, s[k]);
+    if (TKind<TK>::fixed(a)) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + a.sc0 + k, s[k]);
     else if (k == RB_LOST) atomicAdd(a.g_acc + a.sc0 + k, *reinterpret_cast<double*>(&s[k]));
     else atomicAdd(a.g_acc + a.sc0 + k, (double)s[k]);
   }
@@ -590,11 +605,11 @@ struct TrackArgs {
 // seg*() returns -1 to continue, or the outcome 0 census / 1 absorbed / 2 escaped.
 template <class P>
 struct Hist1 {
-  Num<P> t, x, mu, E, E0, minE, escale;
+  Num<P> t, x, mu, E, E0, minE;
   int cell, k, nseg;
-  long long kbase, pi, rec_base;
+  long long pi, rec_base;
 };
-template <class P, class D>
+template <class P, class D, int TK>
 __device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist1<P>& h, D& d, Counters& cn) {
   using N = Num<P>;
   h.E0 = N::load(a.p.E0, pi);
@@ -603,26 +618,24 @@ __device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist
   h.t = N::load(a.p.t, pi); h.x = N::load(a.p.x, pi); h.mu = N::load(a.p.mu, pi); h.E = N::load(a.p.E, pi);
   h.cell = a.p.cx[pi];
   h.k = a.p.ks[pi];
-  h.escale = N(a.m.scales[h.k]);
   h.minE = N::from_d(0.01 * h.E0.d());                                              // :61
-  h.kbase = a.m.nc * h.k;
   h.nseg = 0;
-  h.rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
+  h.rec_base = (TKind<TK>::exact(a.tally) && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], pi);
   return true;
 }
-template <class P, class D>
+template <class P, class D, int TK>
 __device__ __forceinline__ void store1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, int ev, Counters& cn) {
   const long long pi = h.pi;
-  if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
+  if (TKind<TK>::exact(a.tally) && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
   cn.finish(ev, h.nseg);
   if (ev == 0) { h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi); a.p.cx[pi] = h.cell; }
   else h.E0.store(a.p.E0, pi);  // dead: only the flag is written; the other slots stay stale (Q16)
   if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
   if (d.over()) atomicAdd(a.over_flag, 1ull);
 }
-template <class P, class D>
-__device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, Tally<P>& tal, Counters& cn) {
+template <class P, class D, int TK>
+__device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, Tally<P, TK>& tal, Counters& cn) {
   using N = Num<P>;
   const N one = N::from_d(1.0), two = N::from_i(2), zero;
   const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
@@ -638,17 +651,22 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   N newE = h.E * ex;                                                                // :95
   if (is_nan(newE) || is_nan(dist)) cn.error();
-  const bool exact = a.tally.mode == IMC_TALLY_EXACT;
+  const bool exact = TKind<TK>::exact(a.tally);
+  const long long acc = (long long)h.k * nc + h.cell;
+  // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
+  // (EXACT), else E * (1/dx) (<= 1.5 ulp from it; sums in these modes are order-dependent anyway)
   const N idx = exact ? N() : N(P::unpack(a.m.axx[h.cell].inv));
   if (newE <= h.minE) {                                                             // :97-106
-    tal.add(h.kbase + h.cell, exact ? h.E / dx : h.E * idx, h.rec_base + h.nseg - 1);
+    tal.add(acc, exact ? h.E / dx : h.E * idx, h.rec_base + h.nseg - 1);
     h.E0 = N::from_d(-1.0);
     return 1;
   }
-  tal.add(h.kbase + h.cell, exact ? (-(h.E / dx)) * em1 : ((-h.E) * idx) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
+  tal.add(acc, exact ? (-(h.E / dx)) * em1 : ((-h.E) * idx) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
   h.x = h.x + h.mu * dist;                                                          // :124
-  { N dd = a.m.ds_is_one ? dist : dist / ds;                                          // :125 (x / 1 == x exactly)
-    h.t = h.t + (a.m.c_is_one ? dd : dd / c_light); }
+  { N dd = dist;                                                                    // :125 (x / 1 == x exactly)
+    if (!a.m.ds_is_one) dd = dd / ds;
+    if (!a.m.c_is_one) dd = dd / c_light;
+    h.t = h.t + dd; }
   h.E = newE;                                                                       // :126
   bool dead = false;
   if (dist == dist_b) {                                                             // :130-170
@@ -664,7 +682,7 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
       } else { h.cell -= 1; h.x = N::load(a.m.wx, h.cell); }
     }
   }
-  if (dead) { cn.lose<P>(a.tally, h.E / h.escale, h.pi, h.E.d()); h.E0 = N::from_d(-1.0); return 2; }  // :141 / :160
+  if (dead) { cn.lose<P, TK>(a.tally, h.E / N(a.m.scales[h.k]), h.pi, h.E.d()); h.E0 = N::from_d(-1.0); return 2; }  // :141 / :160
   if (dist == dist_col) {                                                           // :174-183
     h.mu = zero;
     while (h.mu == zero) h.mu = one - two * d.uniform(a.rng);
@@ -673,34 +691,37 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   return -1;
 }
 
-template <class P, bool TAPE>
+template <class P, bool TAPE, int TK>
 __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track1d(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
-  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
+  Tally<P, TK> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
     Hist1<P> h; HistDraw<P, TAPE> d;
-    if (!load1d(a, pi, h, d, cn)) continue;
+    if (!load1d<P, HistDraw<P, TAPE>, TK>(a, pi, h, d, cn)) continue;
     int ev;
     while ((ev = seg1d(a, h, d, tal, cn)) < 0) {}
-    store1d(a, h, d, ev, cn);
+    store1d<P, HistDraw<P, TAPE>, TK>(a, h, d, ev, cn);
   }
   tal.flush();
-  cn.commit(a.tally);
+  cn.commit<TK>(a.tally);
 }
 
 // ======================================================================================
 // Transport.MC2D — 2-D history-based tracking
 // ======================================================================================
+// qx / qy: 1/dx and 1/dy of the current cell — or dx and dy themselves when the deposits keep the reference's
+// expression (E/dx)/dy (EXACT tallies).  The per-axis constants {d, w = d*ds, 1/d} of both axes sit in ONE table
+// (x entries, then y entries), so a face crossing in either direction is the same code with a different index.
 template <class P>
 struct Hist2 {
-  Num<P> t, x, y, mu, E, E0, minE, escale, vx, vy, dxc, dyc, wxc, wyc, ivol;  // ivol = (1/dx)*(1/dy), fast deposits only
+  Num<P> t, x, y, mu, E, E0, minE, vx, vy, wxc, wyc, qx, qy;
   int xi, yi, k, nseg;
-  long long kbase, pi, rec_base;
+  long long pi, rec_base;
 };
-template <class P, class D>
+template <class P, class D, int TK>
 __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, D& d, Counters& cn) {
   using N = Num<P>;
   h.E = N::load(a.p.E, pi);
@@ -710,22 +731,21 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   h.t = N::load(a.p.t, pi); h.x = N::load(a.p.x, pi); h.y = N::load(a.p.y, pi); h.mu = N::load(a.p.mu, pi);
   h.xi = a.p.cx[pi]; h.yi = a.p.cy[pi];
   h.k = a.p.ks[pi];
-  h.escale = N(a.m.scales[h.k]);
   h.minE = N::from_d(0.01 * h.E0.d());                                              // :531
-  h.kbase = a.m.nc * h.k;
   h.nseg = 0;
-  h.rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
+  const bool exact = TKind<TK>::exact(a.tally);
+  h.rec_base = (exact && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], pi);
   MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
-  { const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axy[h.yi];
-    h.dxc = N(P::unpack(ax.d)); h.wxc = N(P::unpack(ax.w)); h.dyc = N(P::unpack(ay.d)); h.wyc = N(P::unpack(ay.w));
-    h.ivol = N(P::unpack(ax.inv)) * N(P::unpack(ay.inv)); }
+  { const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axx[a.m.nx + h.yi];
+    h.wxc = N(P::unpack(ax.w)); h.wyc = N(P::unpack(ay.w));
+    h.qx = N(P::unpack(exact ? ax.d : ax.inv)); h.qy = N(P::unpack(exact ? ay.d : ay.inv)); }
   return true;
 }
-template <class P, class D>
+template <class P, class D, int TK>
 __device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, int ev, Counters& cn) {
   const long long pi = h.pi;
-  if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
+  if (TKind<TK>::exact(a.tally) && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
   cn.finish(ev, h.nseg);
   if (ev == 0) {
     h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.y.store(a.p.y, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi);
@@ -734,139 +754,153 @@ __device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, D& d
   if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
   if (d.over()) atomicAdd(a.over_flag, 1ull);
 }
-template <class P, class D>
-__device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, Tally<P>& tal, Counters& cn) {
+template <class P, class D, int TK>
+__device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, Tally<P, TK>& tal, Counters& cn) {
   using N = Num<P>;
   const N zero;
   const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
-  const int nx = a.m.nx, ny = a.m.ny;
-  const double TWO_PI = 2.0 * 3.141592653589793;
-  const bool exact = a.tally.mode == IMC_TALLY_EXACT;
+  const int nx = a.m.nx;
+  const bool exact = TKind<TK>::exact(a.tally);
   ++h.nseg;
   d.next_segment(a.rng);
   const long long c = (long long)h.xi + (long long)nx * h.yi;
   const CellProp2<P> cp = a.m.cp2[c];
   const N sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
-  N dist_bx = h.vx > zero ? nabs((h.wxc - h.x) / h.vx) : nabs(h.x / h.vx);          // :538-542
-  N dist_by = h.vy > zero ? nabs((h.wyc - h.y) / h.vy) : nabs(h.y / h.vy);          // :544-548
-  N dist_b = is_nan(dist_bx) ? dist_by : is_nan(dist_by) ? dist_bx : jl_min(dist_bx, dist_by);  // :551-557
-  N dist_col = d.randexp() / sig_col;                                               // :561
-  N dist_cen = (c_light * (dt - h.t)) * ds;                                         // :569
-  N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                              // :571
+  const N dist_bx = nabs((h.vx > zero ? h.wxc - h.x : h.x) / h.vx);                 // :538-542
+  const N dist_by = nabs((h.vy > zero ? h.wyc - h.y : h.y) / h.vy);                 // :544-548
+  const N dist_b = min_nonnan(dist_bx, dist_by);                                    // :551-557
+  const N dist_col = d.randexp() / sig_col;                                         // :561
+  const N dist_cen = (c_light * (dt - h.t)) * ds;                                   // :569
+  const N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                        // :571
   if (is_nan(dist) || dist_col < zero) cn.error();
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
-  N newE = h.E * ex;                                                                // :580
+  const N newE = h.E * ex;                                                          // :580
+  const long long acc = (long long)h.k * a.m.nc + c;
+  // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
+  // (EXACT), else E * ((1/dx) * (1/dy)) (<= 3 ulp from it; sums in these modes are order-dependent anyway)
   if (newE <= h.minE) {                                                             // :586-595
-    // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
-    // (EXACT), else E * (1/dx) * (1/dy) (<= 3 ulp from it; sums in these modes are order-dependent anyway)
-    tal.add(h.kbase + c, exact ? (h.E / h.dxc) / h.dyc : h.E * h.ivol, h.rec_base + h.nseg - 1);
+    tal.add(acc, exact ? (h.E / h.qx) / h.qy : h.E * (h.qx * h.qy), h.rec_base + h.nseg - 1);
     h.E = N::from_d(-1.0);
     return 1;
   }
-  tal.add(h.kbase + c, exact ? ((-(h.E / h.dxc)) / h.dyc) * em1 : ((-h.E) * h.ivol) * em1, h.rec_base + h.nseg - 1);  // :599 / :607
+  tal.add(acc, exact ? ((-(h.E / h.qx)) / h.qy) * em1 : ((-h.E) * (h.qx * h.qy)) * em1, h.rec_base + h.nseg - 1);  // :599 / :607
   h.x = h.x + dist * h.vx;                                                          // :615
   h.y = h.y + dist * h.vy;                                                          // :616
-  { N dd = a.m.ds_is_one ? dist : dist / ds;                                          // :617 (x / 1 == x exactly)
-    h.t = h.t + (a.m.c_is_one ? dd : dd / c_light); }
+  { N dd = dist;                                                                    // :617 (x / 1 == x exactly)
+    if (!a.m.ds_is_one) dd = dd / ds;
+    if (!a.m.c_is_one) dd = dd / c_light;
+    h.t = h.t + dd; }
   h.E = newE;                                                                       // :618
   if (dist == dist_bx || dist == dist_by) {                                         // :621
-    int side = -1;
-    if (dist_bx < dist_by) {                                                        // :622
-      if (h.vx > zero) { if (h.xi == nx - 1) side = IMC_BC_RIGHT; else { h.xi += 1; h.x = zero; } }
-      else { if (h.xi == 0) side = IMC_BC_LEFT; else { h.xi -= 1; } }
-      if (side < 0) {
-        const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axy[h.yi];
-        h.dxc = N(P::unpack(ax.d)); h.wxc = N(P::unpack(ax.w)); h.ivol = N(P::unpack(ax.inv)) * N(P::unpack(ay.inv));
-        if (!(h.vx > zero)) h.x = h.wxc;
-      }
-      else if (a.m.bc[side] == IMC_REFLECT) { h.mu = MathDet::atan2<P>(h.vy, -h.vx); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :626-628
-    } else {
-      if (h.vy > zero) { if (h.yi == ny - 1) side = IMC_BC_TOP; else { h.yi += 1; h.y = zero; } }
-      else { if (h.yi == 0) side = IMC_BC_BOTTOM; else { h.yi -= 1; } }
-      if (side < 0) {
-        const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axy[h.yi];
-        h.dyc = N(P::unpack(ay.d)); h.wyc = N(P::unpack(ay.w)); h.ivol = N(P::unpack(ax.inv)) * N(P::unpack(ay.inv));
-        if (!(h.vy > zero)) h.y = h.wyc;
-      }
-      else if (a.m.bc[side] == IMC_REFLECT) { h.mu = MathDet::atan2<P>(-h.vy, h.vx); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :666-668
+    // one code path for the four faces: axis = x if dist_bx < dist_by (:622, false on NaN -> y), direction from
+    // the sign of that axis' direction cosine (:623 / :643 / :663 / :683)
+    const bool isx = dist_bx < dist_by;
+    const bool pos = (isx ? h.vx : h.vy) > zero;
+    const int idx = isx ? h.xi : h.yi;
+    const int last = (isx ? nx : a.m.ny) - 1;
+    if (pos ? idx != last : idx != 0) {                                             // interior face: neighbour cell
+      const int ni = pos ? idx + 1 : idx - 1;
+      const AxisProp<P> ax = a.m.axx[(isx ? 0 : nx) + ni];
+      const N w(P::unpack(ax.w)), q(P::unpack(exact ? ax.d : ax.inv));
+      const N np = pos ? zero : w;                                                  // enters at 0 or at the far edge dx*ds
+      if (isx) { h.xi = ni; h.x = np; h.wxc = w; h.qx = q; } else { h.yi = ni; h.y = np; h.wyc = w; h.qy = q; }
+      return -1;                                                                    // `continue` :703 (Q15)
     }
-    if (side >= 0 && a.m.bc[side] != IMC_REFLECT) {                                 // VACUUM :629-636 ...
-      cn.lose<P>(a.tally, h.E / h.escale, h.pi, h.E.d());
-      h.E = N::from_d(-1.0);
-      return 2;
+    const int side = isx ? (pos ? IMC_BC_RIGHT : IMC_BC_LEFT) : (pos ? IMC_BC_TOP : IMC_BC_BOTTOM);
+    if (a.m.bc[side] == IMC_REFLECT) {                                              // :626-628 / :666-668
+      h.mu = isx ? MathDet::atan2<P>(h.vy, -h.vx) : MathDet::atan2<P>(-h.vy, h.vx);
+      MathDet::sincos<P>(h.mu, &h.vy, &h.vx);
+      return -1;
     }
-    return -1;                                                                      // `continue` :703 (Q15)
+    cn.lose<P, TK>(a.tally, h.E / N(a.m.scales[h.k]), h.pi, h.E.d());               // VACUUM :629-636 ...
+    h.E = N::from_d(-1.0);
+    return 2;
   }
-  if (dist == dist_col) { h.mu = N::from_d(TWO_PI * d.uniform(a.rng).d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :706-710
+  if (dist == dist_col) { h.mu = N::from_d(6.283185307179586 * d.uniform(a.rng).d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :706-710
   if (dist == dist_cen) { h.t = zero; return 0; }                      // :712-717
   return -1;
 }
 
-template <class P, bool TAPE>
+template <class P, bool TAPE, int TK>
 __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track2d(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
-  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
+  Tally<P, TK> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
     Hist2<P> h; HistDraw<P, TAPE> d;
-    if (!load2d(a, pi, h, d, cn)) continue;
+    if (!load2d<P, HistDraw<P, TAPE>, TK>(a, pi, h, d, cn)) continue;
     int ev;
     while ((ev = seg2d(a, h, d, tal, cn)) < 0) {}
-    store2d(a, h, d, ev, cn);
+    store2d<P, HistDraw<P, TAPE>, TK>(a, h, d, ev, cn);
   }
   tal.flush();
-  cn.commit(a.tally);
+  cn.commit<TK>(a.tally);
 }
 
 // ---- dynamic schedule: warp-level refill from a global particle queue --------------------------------
 // Every loop iteration each active lane tracks one segment.  When at least `refill_min` lanes of the warp
-// are idle (or all are), lane 0 claims that many consecutive particle indices with one atomicAdd and the
-// idle lanes load them.  Per-particle results do not depend on the lane that tracks them (Philox is keyed
-// by particle id, the tape by particle slot), so both schedules give identical particle state.
-template <class P, int GEOM, bool TAPE>
+// are idle (or all are), the idle lanes first write back the histories they finished (together: one
+// warp-aggregated counter update, coalescing stores), then lane 0 claims that many consecutive particle indices
+// with one atomicAdd and the idle lanes load them.  Per-particle results do not depend on the lane that tracks
+// them (Philox is keyed by particle id, the tape by particle slot), so both schedules give identical particle state.
+template <class P, int GEOM, bool TAPE, int TK>
 __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_refill(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
   Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
-  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
+  Tally<P, TK> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
+  using Dr = HistDraw<P, TAPE>;
+  constexpr int ST_EMPTY = -2, ST_ACTIVE = -1;   // >= 0: history finished with that outcome, not yet written back
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  bool active = false, drained = false;
+  int st = ST_EMPTY;
+  bool drained = false;
   unsigned iter = 0;
-  Hist1<P> h1; Hist2<P> h2; HistDraw<P, TAPE> d;
+  Hist1<P> h1; Hist2<P> h2; Dr d;
   while (true) {
-    const unsigned idle = __ballot_sync(IMC_FULL_MASK, !active);
+    const unsigned idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
     const int nidle = __popc(idle);
     // new histories start on even iterations only: SegDraw makes one Philox block per two segments (Float16/32),
     // so all lanes of the warp then generate their blocks in the same iterations
-    if (!drained && (iter & 1u) == 0u && (nidle >= a.refill_min || idle == IMC_FULL_MASK)) {
-      long long base = 0;
-      if (lane == 0) base = (long long)atomicAdd(a.queue, (unsigned long long)nidle);
-      base = __shfl_sync(IMC_FULL_MASK, base, 0);
-      if (!active) {
-        long long pi = base + __popc(idle & lt_mask);
-        if (pi < a.n) {
-          if constexpr (GEOM == 1) active = load1d(a, pi, h1, d, cn); else active = load2d(a, pi, h2, d, cn);
-        }
+    if ((iter & 1u) == 0u && (nidle >= a.refill_min || idle == IMC_FULL_MASK)) {
+      if (st >= 0) {
+        if constexpr (GEOM == 1) store1d<P, Dr, TK>(a, h1, d, st, cn); else store2d<P, Dr, TK>(a, h2, d, st, cn);
+        st = ST_EMPTY;
       }
-      if (base + nidle >= a.n) drained = true;
+      if (!drained) {
+        long long base = 0;
+        if (lane == 0) base = (long long)atomicAdd(a.queue, (unsigned long long)nidle);
+        base = __shfl_sync(IMC_FULL_MASK, base, 0);
+        if (st != ST_ACTIVE) {
+          long long pi = base + __popc(idle & lt_mask);
+          if (pi < a.n) {
+            bool ok;
+            if constexpr (GEOM == 1) ok = load1d<P, Dr, TK>(a, pi, h1, d, cn); else ok = load2d<P, Dr, TK>(a, pi, h2, d, cn);
+            if (ok) st = ST_ACTIVE;
+          }
+        }
+        if (base + nidle >= a.n) drained = true;
+      }
     }
     ++iter;
-    if (__ballot_sync(IMC_FULL_MASK, active) == 0u) {
+    if (__ballot_sync(IMC_FULL_MASK, st == ST_ACTIVE) == 0u) {
       if (drained) break;
       iter = 0;
       continue;
     }
-    if (active) {
+    if (st == ST_ACTIVE) {
       int ev;
-      if constexpr (GEOM == 1) { ev = seg1d(a, h1, d, tal, cn); if (ev >= 0) { store1d(a, h1, d, ev, cn); active = false; } }
-      else { ev = seg2d(a, h2, d, tal, cn); if (ev >= 0) { store2d(a, h2, d, ev, cn); active = false; } }
+      if constexpr (GEOM == 1) ev = seg1d(a, h1, d, tal, cn); else ev = seg2d(a, h2, d, tal, cn);
+      if (ev >= 0) st = ev;
     }
   }
+  if (st >= 0) {   // histories that finished after the last refill
+    if constexpr (GEOM == 1) store1d<P, Dr, TK>(a, h1, d, st, cn); else store2d<P, Dr, TK>(a, h2, d, st, cn);
+  }
   tal.flush();
-  cn.commit(a.tally);
+  cn.commit<TK>(a.tally);
 }
 
 
@@ -891,7 +925,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_e
       pi = a.ev_in ? (long long)a.ev_in[i] : i;
       Hist1<P> h1; Hist2<P> h2; HistDraw<P, false> d;
       bool ok;
-      if constexpr (GEOM == 1) ok = load1d(a, pi, h1, d, cn); else ok = load2d(a, pi, h2, d, cn);
+      if constexpr (GEOM == 1) ok = load1d<P, HistDraw<P, false>, TK_RUNTIME>(a, pi, h1, d, cn); else ok = load2d<P, HistDraw<P, false>, TK_RUNTIME>(a, pi, h2, d, cn);
       if (ok) {
         const int done = first ? 0 : a.ev_nseg[pi];
         if (!first) d.resume(a.p.id[pi], (unsigned)done, a.ev_extra[pi]);
@@ -899,12 +933,12 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_e
         if constexpr (GEOM == 1) {
           h1.nseg = done;
           ev = seg1d(a, h1, d, tal, cn);
-          if (ev >= 0) store1d(a, h1, d, ev, cn);
+          if (ev >= 0) store1d<P, HistDraw<P, false>, TK_RUNTIME>(a, h1, d, ev, cn);
           else { h1.t.store(a.p.t, pi); h1.x.store(a.p.x, pi); h1.mu.store(a.p.mu, pi); h1.E.store(a.p.E, pi); a.p.cx[pi] = h1.cell; a.ev_nseg[pi] = h1.nseg; }
         } else {
           h2.nseg = done;
           ev = seg2d(a, h2, d, tal, cn);
-          if (ev >= 0) store2d(a, h2, d, ev, cn);
+          if (ev >= 0) store2d<P, HistDraw<P, false>, TK_RUNTIME>(a, h2, d, ev, cn);
           else { h2.t.store(a.p.t, pi); h2.x.store(a.p.x, pi); h2.y.store(a.p.y, pi); h2.mu.store(a.p.mu, pi); h2.E.store(a.p.E, pi);
                  a.p.cx[pi] = h2.xi; a.p.cy[pi] = h2.yi; a.ev_nseg[pi] = h2.nseg; }
         }

@@ -126,7 +126,14 @@ struct Num {
 
 template <class P> IMC_HD bool is_nan(Num<P> a) { return a.v != a.v; }
 template <class P> IMC_HD bool is_inf(Num<P> a) { return a.v == a.v && a.v - a.v != a.v - a.v; }
-template <class P> IMC_HD Num<P> nabs(Num<P> a) { return Num<P>(a.v < 0 ? -a.v : (a.v == 0 ? (typename P::comp_t)0 : a.v)); }
+// Julia's abs: abs(-0.0) = 0.0, NaN stays NaN — on the device one |x| operand modifier
+template <class P> IMC_HD Num<P> nabs(Num<P> a) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (P::id == 2) return Num<P>(fabs(a.v)); else return Num<P>(fabsf(a.v));
+#else
+  return Num<P>(a.v < 0 ? -a.v : (a.v == 0 ? (typename P::comp_t)0 : a.v));
+#endif
+}
 
 IMC_HD bool sign_bit(double x) {
 #if defined(__CUDA_ARCH__)
@@ -136,13 +143,26 @@ IMC_HD bool sign_bit(double x) {
 #endif
 }
 // Julia's min(x, y) for floats: NaN-propagating; min(-0.0, 0.0) = -0.0.
+// Device, Float16/Float32: one FMNMX.NAN — PTX min.NaN.f32 returns NaN if either input is NaN and orders
+// -0.0 < +0.0 (PTX ISA "min": "if both inputs are 0.0 then +0.0 > -0.0"); checked on B200 by tests/test_gpu_parity.py.
 template <class P> IMC_HD Num<P> jl_min(Num<P> a, Num<P> b) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (P::id != 2) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a.v), "f"(b.v)); return Num<P>(r); }
+#endif
   if (a.v != a.v) return a;
   if (b.v != b.v) return b;
   if (a.v < b.v) return a;
   if (b.v < a.v) return b;
   // equal (or +-0): prefer the one with the sign bit set
   return Num<P>(sign_bit((double)a.v) ? a.v : b.v);
+}
+// the smaller of two non-negative values, or the one that is not NaN when exactly one is (the NaN guards of
+// imc_transport.jl:551-557 around min(dist_bx, dist_by)); both NaN -> NaN
+template <class P> IMC_HD Num<P> min_nonnan(Num<P> a, Num<P> b) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (P::id != 2) return Num<P>(fminf(a.v, b.v));
+#endif
+  return a.v != a.v ? b : (b.v != b.v ? a : jl_min(a, b));
 }
 template <class P> IMC_HD Num<P> jl_max(Num<P> a, Num<P> b) {
   if (a.v != a.v) return a;

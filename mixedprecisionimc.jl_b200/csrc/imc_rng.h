@@ -44,6 +44,25 @@ struct Philox {
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
   }
+  // the same block function with the ten round keys precomputed (kernel-uniform: they sit in the constant bank
+  // and enter the xor as an operand, instead of two additions per round per thread)
+  static IMC_HD void round_keys(uint64_t seed, uint32_t rk[20]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  }
+  static IMC_HD void block_rk(const uint32_t ctr[4], const uint32_t* rk, uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(0xD2511F53u, c0, &hi0, &lo0);
+      mulhilo(0xCD9E8D57u, c2, &hi1, &lo1);
+      uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+      uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
 };
 
 enum : uint32_t { STREAM_SOURCE = 0u, STREAM_TRACK = 1u, STREAM_TRACK_EXTRA = 2u };
@@ -153,6 +172,15 @@ struct SegDraw {
       uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
       uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? n : (n >> 1))};
       Philox::block(c, key, buf);
+    }
+  }
+  IMC_HD void next_segment_rk(const uint32_t* rk, uint32_t step) {  // as next_segment, round keys precomputed
+    n += 1u;
+    const bool stale = (extra_n & 0x40000000u) != 0u;
+    extra_n &= 0x3fffffffu;
+    if (P::id == 2 || (n & 1u) == 0u || stale) {
+      uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? n : (n >> 1))};
+      Philox::block_rk(c, rk, buf);
     }
   }
   IMC_HD Num<P> randexp() const {
