@@ -305,6 +305,9 @@ struct EngineT : EngineBase {
     m.ds = P::from_d(cfg.distancescale); m.c = P::from_d(cfg.phys_c); m.a = P::from_d(cfg.phys_a); m.alpha = P::from_d(cfg.alpha);
     for (int k = 0; k < 4; ++k) m.bc[k] = cfg.bc[k];
     m.ds_is_one = (double)m.ds == 1.0; m.c_is_one = (double)m.c == 1.0;
+    m.n_tdiv = 0; m.tdiv[0] = m.tdiv[1] = (Cc)1;
+    if (!m.ds_is_one) m.tdiv[m.n_tdiv++] = m.ds;
+    if (!m.c_is_one) m.tdiv[m.n_tdiv++] = m.c;
     k_widths<P><<<grid_for(std::max(nx, ny), 256), 256, 0, stream>>>(m); ++n_launch;
     IMC_CK(cudaGetLastError());
     IMC_CK(cudaStreamSynchronize(stream));

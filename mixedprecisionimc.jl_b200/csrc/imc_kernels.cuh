@@ -31,7 +31,7 @@ enum { RB_LOST = 0, RB_SEG, RB_HIST, RB_CENSUS, RB_ABSORBED, RB_ESCAPED, RB_RW, 
 
 template <class P> struct CellProp1 { typename P::store_t w, dx, sig_col, neg_saf; };   // w = dx*ds
 template <class P> struct CellProp2 { typename P::store_t sig_col, neg_saf; };
-template <class P> struct alignas(4 * sizeof(typename P::store_t)) AxisProp { typename P::store_t d, w, inv, pad; };  // dx, dx*ds, 1/dx
+template <class P> struct alignas(4 * sizeof(typename P::store_t)) AxisProp { typename P::store_t w, inv, d, pad; };  // dx*ds, 1/dx, dx (w and inv share one load)
 
 template <class P>
 struct MeshDev {
@@ -48,6 +48,8 @@ struct MeshDev {
   CellProp2<P>* cp2;
   AxisProp<P>*axx, *axy;   // per x / y index
   int ds_is_one, c_is_one;  // x / 1 == x exactly: the divisions by distancescale / phys_c can be skipped
+  int n_tdiv; Cc tdiv[2];   // the divisors of `(dist / ds) / c` that are not 1, in that order (a counted loop: the compiler
+                            // turns `if (!is_one) x = x / d` into a division plus a select)
   Cc scales[IMC_MAX_SCALES];
   double scales_d[IMC_MAX_SCALES];
   Cc ds, c, a, alpha;
@@ -663,9 +665,8 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   }
   tal.add(acc, exact ? (-(h.E / dx)) * em1 : ((-h.E) * idx) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
   h.x = h.x + h.mu * dist;                                                          // :124
-  { N dd = dist;                                                                    // :125 (x / 1 == x exactly)
-    if (!a.m.ds_is_one) dd = dd / ds;
-    if (!a.m.c_is_one) dd = dd / c_light;
+  { N dd = dist;                                                                    // :125 (dist / ds) / c; x / 1 == x exactly
+    for (int r = 0; r < a.m.n_tdiv; ++r) dd = dd / N(a.m.tdiv[r]);
     h.t = h.t + dd; }
   h.E = newE;                                                                       // :126
   bool dead = false;
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track1d
 // (x entries, then y entries), so a face crossing in either direction is the same code with a different index.
 template <class P>
 struct Hist2 {
-  Num<P> t, x, y, mu, E, E0, minE, vx, vy, wxc, wyc, qx, qy;
+  Num<P> t, x, y, mu, E, E0, minE, vx, vy, wxc, wyc, qx, qy, sig_col, neg_saf;
   int xi, yi, k, nseg;
   long long pi, rec_base;
 };
@@ -740,6 +741,8 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   { const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axx[a.m.nx + h.yi];
     h.wxc = N(P::unpack(ax.w)); h.wyc = N(P::unpack(ay.w));
     h.qx = N(P::unpack(exact ? ax.d : ax.inv)); h.qy = N(P::unpack(exact ? ay.d : ay.inv)); }
+  { const CellProp2<P> cp = a.m.cp2[(long long)h.xi + (long long)a.m.nx * h.yi];
+    h.sig_col = N(P::unpack(cp.sig_col)); h.neg_saf = N(P::unpack(cp.neg_saf)); }
   return true;
 }
 template <class P, class D, int TK>
@@ -763,9 +766,9 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   const bool exact = TKind<TK>::exact(a.tally);
   ++h.nseg;
   d.next_segment(a.rng);
-  const long long c = (long long)h.xi + (long long)nx * h.yi;
-  const CellProp2<P> cp = a.m.cp2[c];
-  const N sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
+  // the cell's {sigma_a (1 - f) + sigma_s, -sigma_a f} stay in registers; they are re-read when the particle enters
+  // another cell, at the END of that segment, so the load is in flight while the next segment draws and divides
+  const N sig_col = h.sig_col, neg_saf = h.neg_saf;
   const N dist_bx = nabs((h.vx > zero ? h.wxc - h.x : h.x) / h.vx);                 // :538-542
   const N dist_by = nabs((h.vy > zero ? h.wyc - h.y : h.y) / h.vy);                 // :544-548
   const N dist_b = min_nonnan(dist_bx, dist_by);                                    // :551-557
@@ -775,7 +778,7 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   if (is_nan(dist) || dist_col < zero) cn.error();
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   const N newE = h.E * ex;                                                          // :580
-  const long long acc = (long long)h.k * a.m.nc + c;
+  const long long acc = (long long)h.k * a.m.nc + ((long long)h.xi + (long long)nx * h.yi);
   // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
   // (EXACT), else E * ((1/dx) * (1/dy)) (<= 3 ulp from it; sums in these modes are order-dependent anyway)
   if (newE <= h.minE) {                                                             // :586-595
@@ -786,9 +789,8 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   tal.add(acc, exact ? ((-(h.E / h.qx)) / h.qy) * em1 : ((-h.E) * (h.qx * h.qy)) * em1, h.rec_base + h.nseg - 1);  // :599 / :607
   h.x = h.x + dist * h.vx;                                                          // :615
   h.y = h.y + dist * h.vy;                                                          // :616
-  { N dd = dist;                                                                    // :617 (x / 1 == x exactly)
-    if (!a.m.ds_is_one) dd = dd / ds;
-    if (!a.m.c_is_one) dd = dd / c_light;
+  { N dd = dist;                                                                    // :617 (dist / ds) / c; x / 1 == x exactly
+    for (int r = 0; r < a.m.n_tdiv; ++r) dd = dd / N(a.m.tdiv[r]);
     h.t = h.t + dd; }
   h.E = newE;                                                                       // :618
   if (dist == dist_bx || dist == dist_by) {                                         // :621
@@ -803,7 +805,11 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
       const AxisProp<P> ax = a.m.axx[(isx ? 0 : nx) + ni];
       const N w(P::unpack(ax.w)), q(P::unpack(exact ? ax.d : ax.inv));
       const N np = pos ? zero : w;                                                  // enters at 0 or at the far edge dx*ds
-      if (isx) { h.xi = ni; h.x = np; h.wxc = w; h.qx = q; } else { h.yi = ni; h.y = np; h.wyc = w; h.qy = q; }
+      h.xi = isx ? ni : h.xi; h.yi = isx ? h.yi : ni;
+      { const CellProp2<P> cp = a.m.cp2[(long long)h.xi + (long long)nx * h.yi];
+        h.sig_col = N(P::unpack(cp.sig_col)); h.neg_saf = N(P::unpack(cp.neg_saf)); }
+      h.x = isx ? np : h.x; h.wxc = isx ? w : h.wxc; h.qx = isx ? q : h.qx;
+      h.y = isx ? h.y : np; h.wyc = isx ? h.wyc : w; h.qy = isx ? h.qy : q;
       return -1;                                                                    // `continue` :703 (Q15)
     }
     const int side = isx ? (pos ? IMC_BC_RIGHT : IMC_BC_LEFT) : (pos ? IMC_BC_TOP : IMC_BC_BOTTOM);
@@ -860,16 +866,17 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
   unsigned iter = 0;
   Hist1<P> h1; Hist2<P> h2; Dr d;
   while (true) {
-    const unsigned idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
-    const int nidle = __popc(idle);
+    unsigned idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
     // new histories start on even iterations only: SegDraw makes one Philox block per two segments (Float16/32),
-    // so all lanes of the warp then generate their blocks in the same iterations
-    if ((iter & 1u) == 0u && (nidle >= a.refill_min || idle == IMC_FULL_MASK)) {
+    // so all lanes of the warp then generate their blocks in the same iterations.  refill_min <= 32, so a warp
+    // with no active lane always refills.
+    if ((iter & 1u) == 0u && __popc(idle) >= a.refill_min) {
       if (st >= 0) {
         if constexpr (GEOM == 1) store1d<P, Dr, TK>(a, h1, d, st, cn); else store2d<P, Dr, TK>(a, h2, d, st, cn);
         st = ST_EMPTY;
       }
       if (!drained) {
+        const int nidle = __popc(idle);
         long long base = 0;
         if (lane == 0) base = (long long)atomicAdd(a.queue, (unsigned long long)nidle);
         base = __shfl_sync(IMC_FULL_MASK, base, 0);
@@ -882,10 +889,11 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
           }
         }
         if (base + nidle >= a.n) drained = true;
+        idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
       }
     }
     ++iter;
-    if (__ballot_sync(IMC_FULL_MASK, st == ST_ACTIVE) == 0u) {
+    if (idle == IMC_FULL_MASK) {
       if (drained) break;
       iter = 0;
       continue;

@@ -174,6 +174,24 @@ IMC_HD double expm1_d(double x) {
 IMC_HD void exp_expm1_d(double x, double* e, double* em1) {
   if (!(x <= 709.0 && x >= -37.0)) { *e = exp_d(x); *em1 = expm1_d(x); return; }
   double ax = x < 0 ? -x : x;
+  if (rint_d(x * IMC_LOG2E_D) == 0.0) {  // n = 0: r = x, c = 0, scale 2^0 (see exp_expm1_f)
+    double q = 1.0 / 6227020800.0;
+    q = fma_d(q, x, 1.0 / 479001600.0);
+    q = fma_d(q, x, 1.0 / 39916800.0);
+    q = fma_d(q, x, 1.0 / 3628800.0);
+    q = fma_d(q, x, 1.0 / 362880.0);
+    q = fma_d(q, x, 1.0 / 40320.0);
+    q = fma_d(q, x, 1.0 / 5040.0);
+    q = fma_d(q, x, 1.0 / 720.0);
+    q = fma_d(q, x, 1.0 / 120.0);
+    q = fma_d(q, x, 1.0 / 24.0);
+    q = fma_d(q, x, 1.0 / 6.0);
+    q = fma_d(q, x, 0.5);
+    double em0 = fma_d(x * x, q, x);
+    *e = 1.0 + em0;
+    *em1 = (ax < 5.551115123125783e-17) ? x : em0;
+    return;
+  }
   int n;
   double em = exp_core_d(x, &n);
   *e = scale_d(1.0 + em, n);
@@ -423,6 +441,21 @@ IMC_HD float expm1_f(float x) {
 IMC_HD void exp_expm1_f(float x, float* e, float* em1) {
   if (!(x <= 88.0f && x >= -17.0f)) { *e = exp_f(x); *em1 = expm1_f(x); return; }
   float ax = x < 0 ? -x : x;
+  // |x| < ln2/2 (the usual case in tracking: one segment attenuates little): n = 0, so the reduction leaves
+  // r = x, c = 0 and the scaling is by 2^0 — the same operations as below with the no-ops removed, bit-identical
+  if (rint_f(x * IMC_LOG2E_F) == 0.0f) {
+    float q = 1.0f / 40320.0f;
+    q = fma_f(q, x, 1.0f / 5040.0f);
+    q = fma_f(q, x, 1.0f / 720.0f);
+    q = fma_f(q, x, 1.0f / 120.0f);
+    q = fma_f(q, x, 1.0f / 24.0f);
+    q = fma_f(q, x, 1.0f / 6.0f);
+    q = fma_f(q, x, 0.5f);
+    float em0 = fma_f(x * x, q, x);
+    *e = 1.0f + em0;
+    *em1 = (ax < 2.98023223876953125e-08f) ? x : em0;
+    return;
+  }
   int n;
   float em = exp_core_f(x, &n);
   *e = scale_f(1.0f + em, n);
@@ -442,6 +475,30 @@ IMC_HD float log_f(float x) {
   }
   ix += 0x3f800000u - 0x3f3504f3u;
   e += (int)(ix >> 23) - 0x7f;
+  ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+  float m = bits_f(ix);
+  float f = m - 1.0f;
+  float s = f / (2.0f + f);
+  float z = s * s;
+  float p = 1.0f / 13.0f;
+  p = fma_f(p, z, 1.0f / 11.0f);
+  p = fma_f(p, z, 1.0f / 9.0f);
+  p = fma_f(p, z, 1.0f / 7.0f);
+  p = fma_f(p, z, 1.0f / 5.0f);
+  p = fma_f(p, z, 1.0f / 3.0f);
+  float R = 2.0f * (z * p);
+  float hfsq = 0.5f * f * f;
+  float dk = (float)e;
+  const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
+  return fma_f(s, hfsq + R, dk * ln2_lo) - hfsq + f + dk * ln2_hi;
+}
+
+// log_f for a positive, normal, finite argument (the uniform of randexp): the same operations without the
+// special-case tests — bit-identical to log_f there
+IMC_HD float log_pos_normal_f(float x) {
+  uint32_t ix = f_bits(x);
+  ix += 0x3f800000u - 0x3f3504f3u;
+  int e = (int)(ix >> 23) - 0x7f;
   ix = (ix & 0x007fffffu) + 0x3f3504f3u;
   float m = bits_f(ix);
   float f = m - 1.0f;

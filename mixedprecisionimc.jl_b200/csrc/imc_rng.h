@@ -115,7 +115,7 @@ IMC_HD double randexp64_from_word(uint64_t w) {
 IMC_HD float randexp32_from_word(uint32_t w) {
   float u = (float)w * 2.3283064365386963e-10f + 1.1641532182693481e-10f;  // (0, 1]
   if (u > 1.0f) u = 1.0f;
-  return -dm::log_f(u);
+  return -dm::log_pos_normal_f(u);  // u in [2^-33, 1]: positive and normal
 }
 
 // RNG back-end 1: Philox.  Draw<P> API: uniform() -> rand(T); randexp() -> randexp(T);
