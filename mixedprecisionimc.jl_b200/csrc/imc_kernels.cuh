@@ -666,6 +666,7 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   tal.add(acc, exact ? (-(h.E / dx)) * em1 : ((-h.E) * idx) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
   h.x = h.x + h.mu * dist;                                                          // :124
   { N dd = dist;                                                                    // :125 (dist / ds) / c; x / 1 == x exactly
+#pragma unroll 1
     for (int r = 0; r < a.m.n_tdiv; ++r) dd = dd / N(a.m.tdiv[r]);
     h.t = h.t + dd; }
   h.E = newE;                                                                       // :126
@@ -790,6 +791,7 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   h.x = h.x + dist * h.vx;                                                          // :615
   h.y = h.y + dist * h.vy;                                                          // :616
   { N dd = dist;                                                                    // :617 (dist / ds) / c; x / 1 == x exactly
+#pragma unroll 1
     for (int r = 0; r < a.m.n_tdiv; ++r) dd = dd / N(a.m.tdiv[r]);
     h.t = h.t + dd; }
   h.E = newE;                                                                       // :618
