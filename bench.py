@@ -112,6 +112,19 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_from_profile(workload, mesh, particles):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tracking kernel (bytes per launch) from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json), or None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        for e in json.load(open(p)):
+            if e["workload"] == workload and list(e["mesh"]) == list(mesh) and e["particles_per_gpu"] == particles:
+                return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def cpu_port_run(w, mesh, sample_particles: int, steps: int, warmup: int):
     """Time the oracle (1 thread, like the reference) on a bounded sample of the workload."""
     import __graft_entry__ as entry
@@ -215,14 +228,17 @@ def main():
             return imc_dist.advance_sharded(sim)
         return sim.advance()
 
-    # pinned host buffers for the end-to-end path
-    pin = {k: torch.empty(nc, dtype=torch.float64).pin_memory().numpy() for k in ("temp", "matenergydens", "radenergydens")}
+    # pinned host buffers for the end-to-end path, in the fields' own element type (Array{T}, as the Julia shim
+    # passes pointer(mesh.x)); mesh.temp is 8-byte once a LINEARIZED deck has made it Float64 (Q12)
+    sim_dt = {k: eng.field_dtype(k) for k in ("temp", "matenergydens", "radenergydens")}
+    tdt = {np.float16: torch.float16, np.float32: torch.float32, np.float64: torch.float64}
+    pin = {k: torch.empty(nc, dtype=tdt[sim_dt[k]]).pin_memory().numpy() for k in sim_dt}
 
     def step_e2e():
-        eng.set_state(temp=pin["temp"], matenergydens=pin["matenergydens"], radenergydens=pin["radenergydens"])  # H2D
+        eng.set_state_native(temp=pin["temp"], matenergydens=pin["matenergydens"], radenergydens=pin["radenergydens"])  # H2D
         r = step_resident()
-        for k in pin:                                                                                            # D2H
-            eng.field(k, out=pin[k])
+        for k in pin:                                                                                                   # D2H
+            eng.field_native(k, out=pin[k])
         return r
 
     for _ in range(args.warmup):
@@ -236,41 +252,49 @@ def main():
     kms = 0.0
     variants = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    estream = torch.cuda.ExternalStream(eng.stream(), device=dev)   # the stream the engine launches its kernels on
     barrier()
-    ev0.record()
+    ev0.record(estream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = step_resident()
         seg += r["transport"]["segments"]; hist += r["transport"]["histories"]; kms += r["transport"]["kernel_ms"]
         variants.append({1: "static", 2: "refill", 3: "event"}.get(r["transport"]["variant"], "?"))
+    ev1.record(estream)
     barrier()
-    ev1.record()
-    torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3          # device time of the K steps on the engine's stream
     launches = eng.kernel_launches() - l0
     n_part = eng.num_particles()
     # end-to-end: same steps through host buffers
+    if pin["temp"].dtype != eng.field_dtype("temp"):   # mesh.temp turned Float64 during the resident steps (Q12)
+        pin["temp"] = torch.empty(nc, dtype=torch.float64).pin_memory().numpy()
     for k in pin:
-        eng.field(k, out=pin[k])
+        eng.field_native(k, out=pin[k])
     barrier()
+    ev2.record(estream)
     t1 = time.perf_counter()
     seg_e = 0
     for _ in range(args.steps):
         r = step_e2e()
         seg_e += r["transport"]["segments"]
+    ev3.record(estream)
     barrier()
     wall_e = time.perf_counter() - t1
+    dev_e_s = ev2.elapsed_time(ev3) * 1e-3
+    io_bytes = sum(int(v.nbytes) for v in pin.values())
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
     tot = torch.tensor([seg, hist, seg_e, n_part], dtype=torch.float64, device=dev)
-    mx = torch.tensor([wall, wall_e, kms], dtype=torch.float64, device=dev)
+    mx = torch.tensor([dev_s, dev_e_s, kms, wall, wall_e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     seg_g, hist_g, seg_e_g, n_part_g = tot.tolist()
-    wall_g, wall_e_g, kms_g = mx.tolist()
+    wall_g, wall_e_g, kms_g, host_wall_g, host_wall_e_g = mx.tolist()   # the first two are CUDA-event times (max over ranks)
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -285,11 +309,12 @@ def main():
             "config": config,
             "histories_per_s": hist_g / wall_g, "segments_per_history": sph, "particles_resident": n_part_g,
             "tracking_kernel_ms_per_step": kms_g / args.steps, "tracking_kernel_share_of_step": kms_g / (1e3 * wall_g),
-            "cuda_event_ms_per_step": ev0.elapsed_time(ev1) / args.steps,
-            "e2e": {"value": seg_e_g / wall_e_g, "unit": "segments/s", "h2d_bytes_per_step": 3 * nc * 8, "d2h_bytes_per_step": 3 * nc * 8,
-                    "ms_per_step": 1e3 * wall_e_g / args.steps},
+            "timing": "CUDA events on the engine's stream, max over ranks", "host_wall_ms_per_step": 1e3 * host_wall_g / args.steps,
+            "e2e": {"value": seg_e_g / wall_e_g, "unit": "segments/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
+                    "ms_per_step": 1e3 * wall_e_g / args.steps, "host_wall_ms_per_step": 1e3 * host_wall_e_g / args.steps,
+                    "path": "imc_set_state_native (pinned Array{T} -> device) + the step + imc_get_field_native x3 (device -> pinned Array{T})"},
             "gpu_launches": launches, "schedule_per_step": variants,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_from_profile(args.workload, mesh, particles),
                          "kernel": "k_track2d" if w["geom"] == 2 else ("k_track1d_rw" if w["deck"] == "marshak" else "k_track1d"),
                          "bytes_per_segment": bps, "peak_source": peak_src},
             "clocks": sampler.summary(),

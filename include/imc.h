@@ -211,6 +211,20 @@ int imc_get_field(imc_handle h, int32_t field, double* dst, int64_t n);
 /* overwrite mesh.temp (and optionally matenergydens when non-NULL): lets a host restart from saved fields */
 int imc_set_state(imc_handle h, const double* temp, const double* matenergydens, const double* radenergydens);
 
+/* The same two transfers in the field's own element type, with no Float64 staging on either side: the Julia
+ * host's arrays are Array{T} (mesh.matenergydens, mesh.radenergydens, mesh.fleck ...; imc_mesh.jl:117-160), so
+ * the shim passes pointer(mesh.x) straight through.  imc_field_elsize returns the element size in bytes:
+ * sizeof(T) (2 / 4 / 8) for every field except IMC_FIELD_TEMP, which is 8 once the reference's mesh.temp has
+ * turned Float64 (after the first LINEARIZED tally, imc_tally.jl:72) and sizeof(T) before.
+ * `bytes` must equal n_elements * elsize.  Host buffers may be pageable or pinned. */
+int32_t imc_field_elsize(imc_handle h, int32_t field);
+int imc_get_field_native(imc_handle h, int32_t field, void* dst, int64_t bytes);
+int imc_set_state_native(imc_handle h, const void* temp, const void* matenergydens, const void* radenergydens);
+
+/* The CUDA stream (cudaStream_t) every kernel of this engine is launched on, so that a host can bracket
+ * calls with its own events; NULL for the oracle. */
+void* imc_stream(imc_handle h);
+
 /* Particle population in the reference's array-of-slots layout:
  *   1-D: 9 slots  [origin, time, cellindex, position, mu, freq, energy, startenergy, energyscale]
  *   2-D: 10 slots [time, xindex, yindex, xpos, ypos, mu, frq, energy, startenergy, energyscale]

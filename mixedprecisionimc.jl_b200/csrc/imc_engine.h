@@ -25,6 +25,10 @@ struct EngineBase {
   virtual int reduce_buffer(void**, int64_t*, int32_t*) = 0;
   virtual int get_field(int, double*, int64_t) = 0;
   virtual int set_state(const double*, const double*, const double*) = 0;
+  virtual int field_elsize(int) = 0;
+  virtual int get_field_native(int, void*, int64_t) = 0;
+  virtual int set_state_native(const void*, const void*, const void*) = 0;
+  virtual void* stream_handle() = 0;
   virtual int64_t num_particles() = 0;
   virtual int64_t launches() = 0;
   virtual int get_particles(double*, uint64_t*, int64_t) = 0;

@@ -814,6 +814,69 @@ struct EngineT : EngineBase {
     if (n != len) { err = "get_field: size"; return IMC_ERR_ARG; }
     return download(src, (size_t)len, dst);
   }
+  // ---- native-precision transfers (no Float64 staging): the field's device buffer <-> the host's Array{T} ----
+  const S* field_ptr(int f, long long* len) {
+    *len = nc;
+    switch (f) {
+      case IMC_FIELD_FLECK: return fleck.p;
+      case IMC_FIELD_BETA: return beta.p;
+      case IMC_FIELD_BEE: return bee.p;
+      case IMC_FIELD_SIGMA_A: return sa.p;
+      case IMC_FIELD_SIGMA_S: return ss.p;
+      case IMC_FIELD_ENERGYDEP: *len = nc * ns; return energydep.p;
+      case IMC_FIELD_EMITTEDENERGY: *len = nc * ns; return emittedenergy.p;
+      case IMC_FIELD_MATENERGYDENS: return matenergydens.p;
+      case IMC_FIELD_RADENERGYDENS: return radenergydens.p;
+      case IMC_FIELD_NRG_INC: return nrg_inc.p;
+      default: return nullptr;
+    }
+  }
+  int field_elsize(int f) override {
+    if (f < 0 || f >= IMC_FIELD_COUNT_) return 0;
+    return (f == IMC_FIELD_TEMP && temp_wide) ? 8 : (int)sizeof(S);
+  }
+  DBuf<S> stage_t;  // device staging for mesh.temp (kept as its Float64 image on the device) in T
+  int get_field_native(int f, void* dst, int64_t bytes) override {
+    if (!have_mesh) { err = "get_field before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    if (f == IMC_FIELD_TEMP) {
+      if (bytes != nc * field_elsize(f)) { err = "get_field_native: size"; return IMC_ERR_ARG; }
+      if (temp_wide) IMC_CK(cudaMemcpyAsync(dst, temp.p, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+      else {
+        IMC_CK(stage_t.ensure((size_t)nc));
+        k_from_f64<P><<<grid_for(nc, 256), 256, 0, stream>>>(temp.p, nc, stage_t.p); ++n_launch;
+        IMC_CK(cudaMemcpyAsync(dst, stage_t.p, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+      }
+      IMC_CK(cudaStreamSynchronize(stream));
+      return IMC_OK;
+    }
+    long long len = 0;
+    const S* src = field_ptr(f, &len);
+    if (!src) { err = "get_field_native: unknown field"; return IMC_ERR_ARG; }
+    if (bytes != len * (long long)sizeof(S)) { err = "get_field_native: size"; return IMC_ERR_ARG; }
+    IMC_CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    return IMC_OK;
+  }
+  int set_state_native(const void* temp_, const void* mat, const void* rad) override {
+    if (!have_mesh) { err = "set_state before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    if (temp_) {
+      if (temp_wide) IMC_CK(cudaMemcpyAsync(temp.p, temp_, nc * sizeof(double), cudaMemcpyHostToDevice, stream));
+      else {
+        IMC_CK(stage_t.ensure((size_t)nc));
+        IMC_CK(cudaMemcpyAsync(stage_t.p, temp_, nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+        k_to_f64<P><<<grid_for(nc, 256), 256, 0, stream>>>(stage_t.p, nc, temp.p); ++n_launch;
+      }
+    }
+    if (mat) IMC_CK(cudaMemcpyAsync(matenergydens.p, mat, nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+    if (rad) IMC_CK(cudaMemcpyAsync(radenergydens.p, rad, nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+    IMC_CK(cudaGetLastError());
+    IMC_CK(cudaStreamSynchronize(stream));
+    return IMC_OK;
+  }
+  void* stream_handle() override { return (void*)stream; }
+
   int set_state(const double* temp_, const double* mat, const double* rad) override {
     if (!have_mesh) { err = "set_state before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());

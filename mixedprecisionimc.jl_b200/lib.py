@@ -108,6 +108,10 @@ ABI = [
     ("imc_reduce_buffer", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     ("imc_get_field", C.c_int, [C.c_void_p, C.c_int32, _DP, C.c_int64]),
     ("imc_set_state", C.c_int, [C.c_void_p, _DP, _DP, _DP]),
+    ("imc_field_elsize", C.c_int32, [C.c_void_p, C.c_int32]),
+    ("imc_get_field_native", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    ("imc_set_state_native", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("imc_stream", C.c_void_p, [C.c_void_p]),
     ("imc_num_particles", C.c_int64, [C.c_void_p]),
     ("imc_kernel_launches", C.c_int64, [C.c_void_p]),
     ("imc_get_particles", C.c_int, [C.c_void_p, _DP, C.POINTER(C.c_uint64), C.c_int64]),
@@ -330,6 +334,34 @@ class Engine:
     def set_state(self, temp=None, matenergydens=None, radenergydens=None):
         arrs = [None if a is None else _f64(a, self.nc) for a in (temp, matenergydens, radenergydens)]
         self._check(self.lib.dll.imc_set_state(self._h, *[_dp(a) for a in arrs]))
+
+    # ---- the same transfers in the field's own element type (what the Julia shim does with pointer(mesh.x)) ----
+    def field_dtype(self, name: str):
+        es = int(self.lib.dll.imc_field_elsize(self._h, FIELDS[name]))
+        return {2: np.float16, 4: np.float32, 8: np.float64}[es]
+
+    def field_native(self, name: str, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Download a field in its own element type (Array{T}); `out` may be a caller-owned (pinned) flat buffer."""
+        n = self.nc * (self.ns if name in _MULTISCALE else 1)
+        dt = self.field_dtype(name)
+        if out is None:
+            out = np.empty(n, dtype=dt)
+        assert out.size == n and out.dtype == dt and out.flags["C_CONTIGUOUS"]
+        self._check(self.lib.dll.imc_get_field_native(self._h, FIELDS[name], out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def set_state_native(self, temp=None, matenergydens=None, radenergydens=None):
+        def ptr(a, name):
+            if a is None:
+                return None
+            assert a.size == self.nc and a.dtype == self.field_dtype(name) and a.flags["C_CONTIGUOUS"], name
+            return a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.dll.imc_set_state_native(self._h, ptr(temp, "temp"), ptr(matenergydens, "matenergydens"),
+                                                      ptr(radenergydens, "radenergydens")))
+
+    def stream(self) -> int:
+        """cudaStream_t of the engine as an integer (0 for the oracle)."""
+        return int(self.lib.dll.imc_stream(self._h) or 0)
 
     def num_particles(self) -> int:
         return int(self.lib.dll.imc_num_particles(self._h))

@@ -147,6 +147,9 @@ struct EngineBase {
   virtual int reduce_buffer(void**, int64_t*, int32_t*) = 0;
   virtual int get_field(int, double*, int64_t) = 0;
   virtual int set_state(const double*, const double*, const double*) = 0;
+  virtual int field_elsize(int) = 0;
+  virtual int get_field_native(int, void*, int64_t) = 0;
+  virtual int set_state_native(const void*, const void*, const void*) = 0;
   virtual int64_t num_particles() = 0;
   virtual int get_particles(double*, uint64_t*, int64_t) = 0;
   virtual int set_particles(const double*, const uint64_t*, int64_t) = 0;
@@ -1013,6 +1016,36 @@ struct Oracle : EngineBase {
     if (mat) for (size_t i = 0; i < nc; ++i) matenergydens[i] = N::from_d(mat[i]);
     if (rad) for (size_t i = 0; i < nc; ++i) radenergydens[i] = N::from_d(rad[i]);
     return IMC_OK;
+  }
+  // native-precision variants of the two calls above (include/imc.h): elements of type T, mesh.temp as Float64
+  // once it has turned Float64 (Q12)
+  int field_elsize(int f) override {
+    if (f < 0 || f >= IMC_FIELD_COUNT_) return 0;
+    return (f == IMC_FIELD_TEMP && temp_wide) ? 8 : P::bytes;
+  }
+  static void pack_native(double v, void* dst, size_t i, int elsize) {
+    if (elsize == 8) static_cast<double*>(dst)[i] = v;
+    else { typename P::store_t q = P::pack(P::from_d(v)); memcpy(static_cast<char*>(dst) + i * sizeof q, &q, sizeof q); }
+  }
+  static double unpack_native(const void* src, size_t i, int elsize) {
+    if (elsize == 8) return static_cast<const double*>(src)[i];
+    typename P::store_t q; memcpy(&q, static_cast<const char*>(src) + i * sizeof q, sizeof q); return (double)P::unpack(q);
+  }
+  int get_field_native(int f, void* dst, int64_t bytes) override {
+    const int es = field_elsize(f);
+    if (es == 0 || bytes % es != 0) return IMC_ERR_ARG;
+    std::vector<double> tmp((size_t)(bytes / es));
+    int rc = get_field(f, tmp.data(), (int64_t)tmp.size());
+    if (rc) return rc;
+    for (size_t i = 0; i < tmp.size(); ++i) pack_native(tmp[i], dst, i, es);
+    return IMC_OK;
+  }
+  int set_state_native(const void* temp_, const void* mat, const void* rad) override {
+    std::vector<double> a, b, c;
+    if (temp_) { a.resize(nc); const int es = field_elsize(IMC_FIELD_TEMP); for (size_t i = 0; i < nc; ++i) a[i] = unpack_native(temp_, i, es); }
+    if (mat) { b.resize(nc); for (size_t i = 0; i < nc; ++i) b[i] = unpack_native(mat, i, P::bytes); }
+    if (rad) { c.resize(nc); for (size_t i = 0; i < nc; ++i) c[i] = unpack_native(rad, i, P::bytes); }
+    return set_state(temp_ ? a.data() : nullptr, mat ? b.data() : nullptr, rad ? c.data() : nullptr);
   }
   int64_t num_particles() override { return (int64_t)particles.size(); }
   int get_particles(double* slots, uint64_t* ids_out, int64_t cap) override {

@@ -74,6 +74,11 @@ int imc_step(imc_handle h, double t, double dt, int64_t n_input, double cellmin,
 int imc_reduce_buffer(imc_handle h, void** p, int64_t* n, int32_t* is_int) { GUARD(h->e->reduce_buffer(p, n, is_int)); }
 int imc_get_field(imc_handle h, int32_t f, double* dst, int64_t n) { GUARD(h->e->get_field(f, dst, n)); }
 int imc_set_state(imc_handle h, const double* t, const double* m, const double* r) { GUARD(h->e->set_state(t, m, r)); }
+// native-precision transfers: the oracle keeps Float64 images of its T-valued fields, so these convert on the host
+int32_t imc_field_elsize(imc_handle h, int32_t f) { return h ? h->e->field_elsize(f) : 0; }
+int imc_get_field_native(imc_handle h, int32_t f, void* dst, int64_t bytes) { GUARD(h->e->get_field_native(f, dst, bytes)); }
+int imc_set_state_native(imc_handle h, const void* t, const void* m, const void* r) { GUARD(h->e->set_state_native(t, m, r)); }
+void* imc_stream(imc_handle) { return nullptr; }
 int64_t imc_num_particles(imc_handle h) { return h ? h->e->num_particles() : -1; }
 int64_t imc_kernel_launches(imc_handle h) { return h ? 0 : -1; }
 int imc_get_particles(imc_handle h, double* s, uint64_t* ids, int64_t cap) { GUARD(h->e->get_particles(s, ids, cap)); }

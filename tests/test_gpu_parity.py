@@ -252,3 +252,28 @@ def test_exact_tally_mode_is_bit_exact_without_sync(gpu_lib, oracle_lib, case, p
         assert ra["energy"] == rb["energy"]
     for name in FIELDS_EXACT + FIELDS_TALLIED + ("bee",):
         assert np.array_equal(a.engine.field(name), b.engine.field(name)), name
+
+
+@pytest.mark.parametrize("precision", ["FLOAT16", "FLOAT32", "FLOAT64"])
+@pytest.mark.parametrize("deck", ["suolson", "crooked"])
+def test_native_precision_field_transfers_on_gpu(gpu_lib, precision, deck):
+    """imc_get_field_native / imc_set_state_native (Array{T} straight from / to the device buffers) agree with the
+    Float64 calls, before and after mesh.temp turns Float64 (LINEARIZED decks, Q12)."""
+    inputs = (decks.suolson(precision=precision, n_input=500, n_max=5000) if deck == "suolson"
+              else decks.crooked_pipe(precision=precision, n_input=2000, n_max=20000))
+    sim = driver.setup(inputs, gpu_lib)
+    eng = sim.engine
+    T = lib.PRECISION_DTYPES[{"FLOAT16": lib.F16, "FLOAT32": lib.F32, "FLOAT64": lib.F64}[precision]]
+    assert eng.field_dtype("temp") == T
+    assert np.array_equal(eng.field_native("temp").astype(np.float64), eng.field("temp").reshape(-1, order="F"))
+    sim.advance()
+    assert eng.field_dtype("temp") == (np.float64 if deck == "suolson" else T)
+    for name in ("temp", "fleck", "sigma_a", "matenergydens", "radenergydens", "energydep", "emittedenergy", "nrg_inc"):
+        a, b = eng.field_native(name), eng.field(name).reshape(-1, order="F")
+        assert a.dtype == eng.field_dtype(name)
+        assert np.array_equal(a.astype(np.float64), b), name
+    t, m, r = eng.field_native("temp"), eng.field_native("matenergydens"), eng.field_native("radenergydens")
+    eng.set_state_native(temp=t * 2, matenergydens=m * 2, radenergydens=r * 2)
+    assert np.array_equal(eng.field_native("temp"), t * 2) and np.array_equal(eng.field_native("matenergydens"), m * 2)
+    assert np.array_equal(eng.field("radenergydens").reshape(-1, order="F"), (r * 2).astype(np.float64))
+    assert eng.stream() != 0

@@ -184,3 +184,27 @@ def test_crooked_pipe_materials_and_lattice_deck():
     # Lattice.txt is stale (no NINPUT/NMAX/CELLMIN): main would throw KeyError
     lat = deck.read_inputs(os.path.join(REF_INPUTS, "Lattice.txt"))
     assert "NINPUT" not in lat
+
+
+@pytest.mark.parametrize("precision", ["FLOAT16", "FLOAT32", "FLOAT64"])
+def test_native_precision_field_transfers(oracle_lib, precision):
+    """imc_get_field_native / imc_set_state_native move Array{T} images: same values as the Float64 calls; mesh.temp
+    switches to 8-byte elements once the LINEARIZED tally has made it Float64 (Q12)."""
+    sim = driver.setup(decks.suolson(precision=precision, n_input=500, n_max=5000), oracle_lib)
+    eng = sim.engine
+    T = lib.PRECISION_DTYPES[{"FLOAT16": lib.F16, "FLOAT32": lib.F32, "FLOAT64": lib.F64}[precision]]
+    assert eng.field_dtype("temp") == T and eng.field_dtype("matenergydens") == T
+    sim.advance()
+    assert eng.field_dtype("temp") == np.float64            # Su-Olson is LINEARIZED
+    for name in ("temp", "fleck", "sigma_a", "matenergydens", "radenergydens", "energydep", "emittedenergy", "nrg_inc"):
+        a, b = eng.field_native(name), eng.field(name).reshape(-1, order="F")
+        assert a.dtype == eng.field_dtype(name)
+        assert np.array_equal(a.astype(np.float64), b), name
+    t, m, r = eng.field_native("temp"), eng.field_native("matenergydens"), eng.field_native("radenergydens")
+    eng.set_state_native(temp=t * 2, matenergydens=m * 2, radenergydens=r * 2)
+    assert np.array_equal(eng.field_native("temp"), t * 2) and np.array_equal(eng.field_native("matenergydens"), m * 2)
+    assert np.array_equal(eng.field_native("radenergydens"), r * 2)
+    with pytest.raises(lib.ImcError):
+        eng.lib.dll.imc_get_field_native  # wrong byte count
+        eng._check(eng.lib.dll.imc_get_field_native(eng._h, lib.FIELDS["fleck"], t.ctypes.data, 3))
+    assert eng.stream() == 0
