@@ -81,7 +81,7 @@ struct EngineT : EngineBase {
   DBuf<double> temp;
   DBuf<CellProp1<P>> cp1;
   DBuf<CellProp2<P>> cp2;
-  DBuf<AxisProp<P>> axx;   // x entries, then y entries
+  DBuf<AxisProp<P>> ax_inv, ax_d;   // x entries, then y entries
   MeshDev<P> m;
   // particles (double buffer for the stable compaction)
   PartBufs<P> pb[2];
@@ -159,6 +159,7 @@ struct EngineT : EngineBase {
       return IMC_ERR_CUDA;
     }
     if (cfg.device < 0 || cfg.device >= ndev) { err = "bad device ordinal"; return IMC_ERR_ARG; }
+    if (nc >= (1ll << 31)) { err = "mesh has 2^31 or more cells (cell indices are 32-bit)"; return IMC_ERR_ARG; }
     IMC_CK(cudaSetDevice(cfg.device));
     cudaDeviceProp prop;
     IMC_CK(cudaGetDeviceProperties(&prop, cfg.device));
@@ -266,7 +267,7 @@ struct EngineT : EngineBase {
     }
     IMC_RC(upload(dx, dx_, nx));
     if (geom == 2) IMC_RC(upload(dy, dy_, ny)); else { double one = 1.0; IMC_RC(upload(dy, &one, 1)); }
-    IMC_CK(wx.alloc(nx)); IMC_CK(wy.alloc(ny)); IMC_CK(axx.alloc(nx + ny));
+    IMC_CK(wx.alloc(nx)); IMC_CK(wy.alloc(ny)); IMC_CK(ax_inv.alloc(nx + ny)); IMC_CK(ax_d.alloc(nx + ny));
     IMC_RC(upload(sa_c, sac, nc)); IMC_RC(upload(sa_p, sap, nc)); IMC_RC(upload(ss_c, ssc, nc)); IMC_RC(upload(ss_p, ssp, nc));
     IMC_RC(upload(sa, sac, nc)); IMC_RC(upload(ss, ssc, nc));
     IMC_RC(upload(sigma_static, sstat, nc));
@@ -300,7 +301,7 @@ struct EngineT : EngineBase {
     m.matenergydens = matenergydens.p; m.radenergydens = radenergydens.p; m.nrg_inc = nrg_inc.p;
     m.energydep = energydep.p; m.emittedenergy = emittedenergy.p;
     for (int k = 0; k < 4; ++k) m.tsurf[k] = tsurf[k].p;
-    m.cp1 = cp1.p; m.cp2 = cp2.p; m.axx = axx.p; m.axy = axx.p + nx;
+    m.cp1 = cp1.p; m.cp2 = cp2.p; m.ax_inv = ax_inv.p; m.ax_d = ax_d.p;
     for (int k = 0; k < IMC_MAX_SCALES; ++k) { m.scales[k] = k < ns ? P::from_d(cfg.energyscales[k]) : (Cc)1; m.scales_d[k] = (double)m.scales[k]; }
     m.ds = P::from_d(cfg.distancescale); m.c = P::from_d(cfg.phys_c); m.a = P::from_d(cfg.phys_a); m.alpha = P::from_d(cfg.alpha);
     for (int k = 0; k < 4; ++k) m.bc[k] = cfg.bc[k];

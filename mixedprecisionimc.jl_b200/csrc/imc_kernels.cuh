@@ -31,7 +31,20 @@ enum { RB_LOST = 0, RB_SEG, RB_HIST, RB_CENSUS, RB_ABSORBED, RB_ESCAPED, RB_RW, 
 
 template <class P> struct CellProp1 { typename P::store_t w, dx, sig_col, neg_saf; };   // w = dx*ds
 template <class P> struct CellProp2 { typename P::store_t sig_col, neg_saf; };
-template <class P> struct alignas(4 * sizeof(typename P::store_t)) AxisProp { typename P::store_t w, inv, d, pad; };  // dx*ds, 1/dx, dx (w and inv share one load)
+// per-axis-index constants {w = d*ds, q}: q = 1/d in the table the ATOMIC / FIXED tallies read (deposit = E (1/dx)(1/dy) ..),
+// q = d in the table the EXACT tallies read (deposit = (E/dx)/dy as the reference writes it); one 2-element load
+template <class P> struct alignas(2 * sizeof(typename P::store_t)) AxisProp { typename P::store_t w, q; };
+
+// The per-cell constants are gathered by cell index, once per cell entered: read through L2 only (ld.global.cg),
+// so that the gathers do not evict the small per-axis tables and the particle stream from L1.
+template <class P>
+__device__ __forceinline__ CellProp2<P> load_cell2(const CellProp2<P>* tab, int c) {
+  CellProp2<P> r;
+  if constexpr (P::id == 0) { const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(tab) + c); r.sig_col = (uint16_t)(v & 0xffffu); r.neg_saf = (uint16_t)(v >> 16); }
+  else if constexpr (P::id == 1) { const float2 v = __ldcg(reinterpret_cast<const float2*>(tab) + c); r.sig_col = v.x; r.neg_saf = v.y; }
+  else { const double2 v = __ldcg(reinterpret_cast<const double2*>(tab) + c); r.sig_col = v.x; r.neg_saf = v.y; }
+  return r;
+}
 
 template <class P>
 struct MeshDev {
@@ -46,7 +59,7 @@ struct MeshDev {
   S* tsurf[4];  // bottom, top, left, right (1-D: left = [2][0], right = [3][0])
   CellProp1<P>* cp1;
   CellProp2<P>* cp2;
-  AxisProp<P>*axx, *axy;   // per x / y index
+  AxisProp<P>*ax_inv, *ax_d;   // [nx + ny]: x entries, then y entries
   int ds_is_one, c_is_one;  // x / 1 == x exactly: the divisions by distancescale / phys_c can be skipped
   int n_tdiv; Cc tdiv[2];   // the divisors of `(dist / ds) / c` that are not 1, in that order (a counted loop: the compiler
                             // turns `if (!is_one) x = x / d` into a division plus a select)
@@ -176,14 +189,14 @@ __global__ void k_widths(MeshDev<P> m) {
   if (i < m.nx) {
     N d = N::load(m.dx, i), w = d * N(m.ds);
     w.store(m.wx, i);
-    AxisProp<P> a; a.d = P::pack(d.v); a.w = P::pack(w.v); a.inv = P::pack((N::from_d(1.0) / d).v); a.pad = a.d;
-    m.axx[i] = a;
+    AxisProp<P> a; a.w = P::pack(w.v); a.q = P::pack((N::from_d(1.0) / d).v); m.ax_inv[i] = a;
+    a.q = P::pack(d.v); m.ax_d[i] = a;
   }
   if (m.geom == 2 && i < m.ny) {
     N d = N::load(m.dy, i), w = d * N(m.ds);
     w.store(m.wy, i);
-    AxisProp<P> a; a.d = P::pack(d.v); a.w = P::pack(w.v); a.inv = P::pack((N::from_d(1.0) / d).v); a.pad = a.d;
-    m.axy[i] = a;
+    AxisProp<P> a; a.w = P::pack(w.v); a.q = P::pack((N::from_d(1.0) / d).v); m.ax_inv[m.nx + i] = a;
+    a.q = P::pack(d.v); m.ax_d[m.nx + i] = a;
   }
 }
 
@@ -657,7 +670,7 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   const long long acc = (long long)h.k * nc + h.cell;
   // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
   // (EXACT), else E * (1/dx) (<= 1.5 ulp from it; sums in these modes are order-dependent anyway)
-  const N idx = exact ? N() : N(P::unpack(a.m.axx[h.cell].inv));
+  const N idx = exact ? N() : N(P::unpack(a.m.ax_inv[h.cell].q));
   if (newE <= h.minE) {                                                             // :97-106
     tal.add(acc, exact ? h.E / dx : h.E * idx, h.rec_base + h.nseg - 1);
     h.E0 = N::from_d(-1.0);
@@ -739,10 +752,10 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   h.rec_base = (exact && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], pi);
   MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
-  { const AxisProp<P> ax = a.m.axx[h.xi], ay = a.m.axx[a.m.nx + h.yi];
-    h.wxc = N(P::unpack(ax.w)); h.wyc = N(P::unpack(ay.w));
-    h.qx = N(P::unpack(exact ? ax.d : ax.inv)); h.qy = N(P::unpack(exact ? ay.d : ay.inv)); }
-  { const CellProp2<P> cp = a.m.cp2[(long long)h.xi + (long long)a.m.nx * h.yi];
+  { const AxisProp<P>* tab = exact ? a.m.ax_d : a.m.ax_inv;
+    const AxisProp<P> ax = tab[h.xi], ay = tab[a.m.nx + h.yi];
+    h.wxc = N(P::unpack(ax.w)); h.wyc = N(P::unpack(ay.w)); h.qx = N(P::unpack(ax.q)); h.qy = N(P::unpack(ay.q)); }
+  { const CellProp2<P> cp = load_cell2(a.m.cp2, h.xi + a.m.nx * h.yi);
     h.sig_col = N(P::unpack(cp.sig_col)); h.neg_saf = N(P::unpack(cp.neg_saf)); }
   return true;
 }
@@ -779,7 +792,7 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   if (is_nan(dist) || dist_col < zero) cn.error();
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   const N newE = h.E * ex;                                                          // :580
-  const long long acc = (long long)h.k * a.m.nc + ((long long)h.xi + (long long)nx * h.yi);
+  const long long acc = (long long)h.k * a.m.nc + (h.xi + nx * h.yi);   // nc < 2^31 (checked at set_mesh)
   // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
   // (EXACT), else E * ((1/dx) * (1/dy)) (<= 3 ulp from it; sums in these modes are order-dependent anyway)
   if (newE <= h.minE) {                                                             // :586-595
@@ -804,11 +817,11 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
     const int last = (isx ? nx : a.m.ny) - 1;
     if (pos ? idx != last : idx != 0) {                                             // interior face: neighbour cell
       const int ni = pos ? idx + 1 : idx - 1;
-      const AxisProp<P> ax = a.m.axx[(isx ? 0 : nx) + ni];
-      const N w(P::unpack(ax.w)), q(P::unpack(exact ? ax.d : ax.inv));
+      const AxisProp<P> ax = (exact ? a.m.ax_d : a.m.ax_inv)[(isx ? 0 : nx) + ni];
+      const N w(P::unpack(ax.w)), q(P::unpack(ax.q));
       const N np = pos ? zero : w;                                                  // enters at 0 or at the far edge dx*ds
       h.xi = isx ? ni : h.xi; h.yi = isx ? h.yi : ni;
-      { const CellProp2<P> cp = a.m.cp2[(long long)h.xi + (long long)nx * h.yi];
+      { const CellProp2<P> cp = load_cell2(a.m.cp2, h.xi + nx * h.yi);
         h.sig_col = N(P::unpack(cp.sig_col)); h.neg_saf = N(P::unpack(cp.neg_saf)); }
       h.x = isx ? np : h.x; h.wxc = isx ? w : h.wxc; h.qx = isx ? q : h.qx;
       h.y = isx ? h.y : np; h.wyc = isx ? h.wyc : w; h.qy = isx ? h.qy : q;

@@ -517,6 +517,29 @@ IMC_HD float log_pos_normal_f(float x) {
   return fma_f(s, hfsq + R, dk * ln2_lo) - hfsq + f + dk * ln2_hi;
 }
 
+// -log(u) for u in (0, 1], positive and normal: the exponential sampler of the Float16 / Float32 tracking loops
+// (randexp32_from_word).  Division-free: log(m) = f + f^2 r(f), f = m - 1 in [sqrt(1/2) - 1, sqrt(2) - 1), r a
+// degree-8 fit of (log1p(f) - f) / f^2 at Chebyshev nodes (<= 1.3 ulp); -log(u) = (-e) ln2 - log(m), <= 3 ulp
+// overall — a sampling transform, not a math-library log (log_f above stays the 1-ulp one).
+IMC_HD float neglog_unit_f(float u) {
+  uint32_t ix = f_bits(u);
+  ix += 0x3f800000u - 0x3f3504f3u;
+  int e = (int)(ix >> 23) - 0x7f;
+  ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+  float f = bits_f(ix) - 1.0f;  // exact
+  float r = bits_f(0xbd9d27fbu);
+  r = fma_f(r, f, bits_f(0x3e0247b9u));
+  r = fma_f(r, f, bits_f(0xbe066d19u));
+  r = fma_f(r, f, bits_f(0x3e11752du));
+  r = fma_f(r, f, bits_f(0xbe2a41c1u));
+  r = fma_f(r, f, bits_f(0x3e4cd009u));
+  r = fma_f(r, f, bits_f(0xbe800106u));
+  r = fma_f(r, f, bits_f(0x3eaaaaaau));
+  r = fma_f(r, f, bits_f(0xbeffffffu));
+  float lg = fma_f(f * f, r, f);
+  return fma_f((float)(-e), 6.931471824645996094e-01f, -lg);
+}
+
 IMC_HD float sin_kernel_f(float r) {
   float z = r * r;
   float p = -1.0f / 39916800.0f;

@@ -8,7 +8,7 @@
 //
 // Draw conversions follow Julia's conventions: rand(T) is a multiple of 2^-11 / 2^-24 / 2^-53
 // in [0,1); randexp(T) for T < Float64 is drawn wider and converted (here: -log of a 32-bit
-// uniform in Float32; Julia draws Float64 — statistically equivalent, not bit-equivalent; the
+// uniform in Float32, by the division-free dm::neglog_unit_f; Julia draws Float64 — statistically equivalent, not bit-equivalent; the
 // Julia stream itself is not reproducible across Julia versions).
 #pragma once
 #include "imc_num.h"
@@ -115,7 +115,7 @@ IMC_HD double randexp64_from_word(uint64_t w) {
 IMC_HD float randexp32_from_word(uint32_t w) {
   float u = (float)w * 2.3283064365386963e-10f + 1.1641532182693481e-10f;  // (0, 1]
   if (u > 1.0f) u = 1.0f;
-  return -dm::log_pos_normal_f(u);  // u in [2^-33, 1]: positive and normal
+  return dm::neglog_unit_f(u);  // u in [2^-33, 1]: positive and normal
 }
 
 // RNG back-end 1: Philox.  Draw<P> API: uniform() -> rand(T); randexp() -> randexp(T);

@@ -1,0 +1,7 @@
+#!/bin/bash
+# occupancy sweep of the tracking kernels (crookedpipe_f32 default workload)
+run() { python bench.py --track refill --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('   seg/s %.4g  ms/step %.1f  kernel_ms %.1f' % (d['value'], d['ms_per_step'], d['tracking_kernel_ms_per_step']))"; }
+for cfg in "-DIMC_TRACK_MIN_BLOCKS=3" "-DIMC_TRACK_MIN_BLOCKS=5" "-DIMC_TRACK_THREADS=128 -DIMC_TRACK_MIN_BLOCKS=8" "-DIMC_TRACK_THREADS=512 -DIMC_TRACK_MIN_BLOCKS=2"; do
+  IMC_NVCC_EXTRA="$cfg" python -c "import __graft_entry__ as g; g.build_cuda(force=True)" > /dev/null 2>&1
+  echo "== $cfg"; run
+done
