@@ -309,6 +309,10 @@ struct EngineT : EngineBase {
     m.n_tdiv = 0; m.tdiv[0] = m.tdiv[1] = (Cc)1;
     if (!m.ds_is_one) m.tdiv[m.n_tdiv++] = m.ds;
     if (!m.c_is_one) m.tdiv[m.n_tdiv++] = m.c;
+    for (int r = 0; r < 2; ++r) {   // RN(1/divisor) for the cached-reciprocal division (imc_fastdiv.cuh); 0 outside its range
+      const double d = std::fabs((double)m.tdiv[r]);
+      m.tdiv_r[r] = (P::id != 2 && d >= 0x1p-40 && d < 0x1p40) ? (Cc)(1.0f / (float)m.tdiv[r]) : (Cc)0;
+    }
     k_widths<P><<<grid_for(std::max(nx, ny), 256), 256, 0, stream>>>(m); ++n_launch;
     IMC_CK(cudaGetLastError());
     IMC_CK(cudaStreamSynchronize(stream));
@@ -544,6 +548,7 @@ struct EngineT : EngineBase {
     IMC_RC(use_device());
     if (cfg.randomwalk && !have_rw) { err = "random-walk tables not set (imc_rw_table)"; return IMC_ERR_STATE; }
     if (cfg.rng_mode == IMC_RNG_TAPE && n_part > tt_slots) { err = "transport tape has fewer slots than particles"; return IMC_ERR_TAPE; }
+    if (n_part >= (1ll << 32)) { err = "more than 2^32 particles on one GPU"; return IMC_ERR_ARG; }
     int mode = resolve_tally_mode();
     if ((mode == IMC_TALLY_FIXED) != red_fixed) {  // representation change: start from a clean buffer
       IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream));

@@ -15,6 +15,7 @@
 // Float64.  Compiled with -fmad=false.  Particle state is structure-of-arrays.
 #pragma once
 #include "imc_device.cuh"
+#include "imc_fastdiv.cuh"
 
 namespace imc {
 
@@ -46,6 +47,16 @@ __device__ __forceinline__ CellProp2<P> load_cell2(const CellProp2<P>* tab, int 
   return r;
 }
 
+// a / b for a divisor whose refined reciprocal r is cached (imc_fastdiv.cuh): Float16 / Float32 only — Float16 divides in
+// Float32 and rounds, as Julia does; Float64 keeps the plain division
+template <class P> __device__ __forceinline__ typename P::comp_t recip_of(Num<P> b) {
+  if constexpr (P::id == 2) return 0.0; else return FastDivisor::recip(b.v);
+}
+template <class P> __device__ __forceinline__ Num<P> div_cached(Num<P> a, Num<P> b, typename P::comp_t r) {
+  if constexpr (P::id == 2) return a / b;
+  else { FastDivisor d; d.b = b.v; d.r = r; return Num<P>(P::rnd(d.divide(a.v))); }
+}
+
 template <class P>
 struct MeshDev {
   using S = typename P::store_t;
@@ -61,7 +72,7 @@ struct MeshDev {
   CellProp2<P>* cp2;
   AxisProp<P>*ax_inv, *ax_d;   // [nx + ny]: x entries, then y entries
   int ds_is_one, c_is_one;  // x / 1 == x exactly: the divisions by distancescale / phys_c can be skipped
-  int n_tdiv; Cc tdiv[2];   // the divisors of `(dist / ds) / c` that are not 1, in that order (a counted loop: the compiler
+  int n_tdiv; Cc tdiv[2], tdiv_r[2];   // tdiv_r: cached reciprocals (0 = take the plain division)   // the divisors of `(dist / ds) / c` that are not 1, in that order (a counted loop: the compiler
                             // turns `if (!is_one) x = x / d` into a division plus a select)
   Cc scales[IMC_MAX_SCALES];
   double scales_d[IMC_MAX_SCALES];
@@ -107,24 +118,34 @@ struct Draw {
 };
 // draw source of the MC / MC2D history loops, chosen at compile time: Philox words reserved per segment
 // (SegDraw) or the replay tape.  Only the needed state lives in registers.
-template <class P, bool TAPE> struct HistDraw;
+// `seg` is the 0-based segment index of the history (the caller's counter).
+template <class P, bool TAPE, bool LEAN = false> struct HistDraw;
 template <class P>
-struct HistDraw<P, false> {
+struct HistDraw<P, false, false> {
   SegDraw<P> sg;
   __device__ __forceinline__ void init(const RngArgs&, unsigned long long id, long long) { sg.init(id); }
   __device__ __forceinline__ void resume(unsigned long long id, unsigned next, unsigned extra) { sg.resume(id, next, extra); }
-  __device__ __forceinline__ void next_segment(const RngArgs& r) { sg.next_segment_rk(r.rk, r.step); }
-  __device__ __forceinline__ Num<P> uniform(const RngArgs& r) { return sg.uniform(r.seed, r.step); }
-  __device__ __forceinline__ Num<P> randexp() { return sg.randexp(); }
+  __device__ __forceinline__ void next_segment(const RngArgs& r, unsigned) { sg.next_segment_rk(r.rk, r.step); }
+  __device__ __forceinline__ Num<P> uniform(const RngArgs& r, unsigned) { return sg.uniform(r.seed, r.step); }
+  __device__ __forceinline__ Num<P> randexp(unsigned) { return sg.randexp(); }
   __device__ __forceinline__ bool over() const { return false; }
 };
 template <class P>
-struct HistDraw<P, true> {
+struct HistDraw<P, false, true> {   // MC2D history kernels
+  SegDrawLean<P> sg;
+  __device__ __forceinline__ void init(const RngArgs&, unsigned long long id, long long) { sg.init(id); }
+  __device__ __forceinline__ void next_segment(const RngArgs& r, unsigned seg) { sg.next_segment_rk(r.rk, r.step, seg); }
+  __device__ __forceinline__ Num<P> uniform(const RngArgs&, unsigned seg) { return sg.uniform(seg); }
+  __device__ __forceinline__ Num<P> randexp(unsigned seg) { return sg.randexp(seg); }
+  __device__ __forceinline__ bool over() const { return false; }
+};
+template <class P, bool LEAN>
+struct HistDraw<P, true, LEAN> {
   TapeDraw<P> tp;
   __device__ __forceinline__ void init(const RngArgs& r, unsigned long long, long long slot) { tp.init(r.uni, r.n_uni, r.ex, r.n_exp, (size_t)r.stride, (size_t)slot); }
-  __device__ __forceinline__ void next_segment(const RngArgs&) {}
-  __device__ __forceinline__ Num<P> uniform(const RngArgs&) { return tp.uniform(); }
-  __device__ __forceinline__ Num<P> randexp() { return tp.randexp(); }
+  __device__ __forceinline__ void next_segment(const RngArgs&, unsigned) {}
+  __device__ __forceinline__ Num<P> uniform(const RngArgs&, unsigned) { return tp.uniform(); }
+  __device__ __forceinline__ Num<P> randexp(unsigned) { return tp.randexp(); }
   __device__ __forceinline__ bool over() const { return tp.exhausted(); }
 };
 
@@ -622,14 +643,15 @@ template <class P>
 struct Hist1 {
   Num<P> t, x, mu, E, E0, minE;
   int cell, k, nseg;
-  long long pi, rec_base;
+  unsigned pi;          // position in the particle list (< 2^32, checked by the engine)
+  long long rec_base;
 };
 template <class P, class D, int TK>
 __device__ __forceinline__ bool load1d(const TrackArgs<P>& a, long long pi, Hist1<P>& h, D& d, Counters& cn) {
   using N = Num<P>;
   h.E0 = N::load(a.p.E0, pi);
   if (h.E0.v == (typename P::comp_t)-1) return false;  // flagged dead and not yet cleaned
-  h.pi = pi;
+  h.pi = (unsigned)pi;
   h.t = N::load(a.p.t, pi); h.x = N::load(a.p.x, pi); h.mu = N::load(a.p.mu, pi); h.E = N::load(a.p.E, pi);
   h.cell = a.p.cx[pi];
   h.k = a.p.ks[pi];
@@ -656,11 +678,12 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   const N dt(a.dt), c_light(a.m.c), ds(a.m.ds);
   const int nc = (int)a.m.nc;
   ++h.nseg;                                                                         // :73
-  d.next_segment(a.rng);
+  const unsigned seg = (unsigned)h.nseg - 1u;
+  d.next_segment(a.rng, seg);
   const CellProp1<P> cp = a.m.cp1[h.cell];
   const N w(P::unpack(cp.w)), dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
   N dist_b = h.mu > zero ? (w - h.x) / h.mu : nabs(h.x / h.mu);                     // :77-83
-  N dist_col = d.randexp() / sig_col;                                               // :87
+  N dist_col = d.randexp(seg) / sig_col;                                            // :87
   N dist_cen = (c_light * (dt - h.t)) * ds;                                         // :89
   N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                              // :92
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
@@ -680,7 +703,7 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   h.x = h.x + h.mu * dist;                                                          // :124
   { N dd = dist;                                                                    // :125 (dist / ds) / c; x / 1 == x exactly
 #pragma unroll 1
-    for (int r = 0; r < a.m.n_tdiv; ++r) dd = dd / N(a.m.tdiv[r]);
+    for (int r = 0; r < a.m.n_tdiv; ++r) dd = div_cached(dd, N(a.m.tdiv[r]), a.m.tdiv_r[r]);
     h.t = h.t + dd; }
   h.E = newE;                                                                       // :126
   bool dead = false;
@@ -700,7 +723,7 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   if (dead) { cn.lose<P, TK>(a.tally, h.E / N(a.m.scales[h.k]), h.pi, h.E.d()); h.E0 = N::from_d(-1.0); return 2; }  // :141 / :160
   if (dist == dist_col) {                                                           // :174-183
     h.mu = zero;
-    while (h.mu == zero) h.mu = one - two * d.uniform(a.rng);
+    while (h.mu == zero) h.mu = one - two * d.uniform(a.rng, seg);
   }
   if (dist == dist_cen) { h.t = zero; return 0; }                      // :185-193
   return -1;
@@ -733,15 +756,17 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track1d
 template <class P>
 struct Hist2 {
   Num<P> t, x, y, mu, E, E0, minE, vx, vy, wxc, wyc, qx, qy, sig_col, neg_saf;
+  typename P::comp_t rvx, rvy;   // cached reciprocals of vx, vy (they change only when mu does)
   int xi, yi, k, nseg;
-  long long pi, rec_base;
+  unsigned pi;          // position in the particle list (< 2^32, checked by the engine)
+  long long rec_base;
 };
 template <class P, class D, int TK>
 __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, D& d, Counters& cn) {
   using N = Num<P>;
   h.E = N::load(a.p.E, pi);
   if (h.E.v == (typename P::comp_t)-1) return false;  // 2-D dead flag lives in the energy slot (Q16)
-  h.pi = pi;
+  h.pi = (unsigned)pi;
   h.E0 = N::load(a.p.E0, pi);
   h.t = N::load(a.p.t, pi); h.x = N::load(a.p.x, pi); h.y = N::load(a.p.y, pi); h.mu = N::load(a.p.mu, pi);
   h.xi = a.p.cx[pi]; h.yi = a.p.cy[pi];
@@ -752,6 +777,7 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   h.rec_base = (exact && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], pi);
   MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
+  h.rvx = recip_of(h.vx); h.rvy = recip_of(h.vy);
   { const AxisProp<P>* tab = exact ? a.m.ax_d : a.m.ax_inv;
     const AxisProp<P> ax = tab[h.xi], ay = tab[a.m.nx + h.yi];
     h.wxc = N(P::unpack(ax.w)); h.wyc = N(P::unpack(ay.w)); h.qx = N(P::unpack(ax.q)); h.qy = N(P::unpack(ay.q)); }
@@ -779,20 +805,39 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   const int nx = a.m.nx;
   const bool exact = TKind<TK>::exact(a.tally);
   ++h.nseg;
-  d.next_segment(a.rng);
-  // the cell's {sigma_a (1 - f) + sigma_s, -sigma_a f} stay in registers; they are re-read when the particle enters
-  // another cell, at the END of that segment, so the load is in flight while the next segment draws and divides
+  const unsigned seg = (unsigned)h.nseg - 1u;
+  d.next_segment(a.rng, seg);
+  // the cell's {sigma_a (1 - f) + sigma_s, -sigma_a f} stay in registers and are re-read when the particle enters
+  // another cell
   const N sig_col = h.sig_col, neg_saf = h.neg_saf;
-  const N dist_bx = nabs((h.vx > zero ? h.wxc - h.x : h.x) / h.vx);                 // :538-542
-  const N dist_by = nabs((h.vy > zero ? h.wyc - h.y : h.y) / h.vy);                 // :544-548
+  const N dist_bx = nabs(div_cached(h.vx > zero ? h.wxc - h.x : h.x, h.vx, h.rvx)); // :538-542
+  const N dist_by = nabs(div_cached(h.vy > zero ? h.wyc - h.y : h.y, h.vy, h.rvy)); // :544-548
   const N dist_b = min_nonnan(dist_bx, dist_by);                                    // :551-557
-  const N dist_col = d.randexp() / sig_col;                                         // :561
+  const N dist_col = d.randexp(seg) / sig_col;                                      // :561
   const N dist_cen = (c_light * (dt - h.t)) * ds;                                   // :569
   const N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                        // :571
   if (is_nan(dist) || dist_col < zero) cn.error();
+  // The event follows from the distances alone (:621-622), so the constants of the cell the particle is about to enter
+  // are requested NOW and used at the end of the segment: the gather latency (L2) is covered by the attenuation,
+  // deposit and move below instead of stalling the next segment.  One code path for the four faces: axis = x if
+  // dist_bx < dist_by (:622, false on NaN -> y), direction from the sign of that axis' direction cosine
+  // (:623 / :643 / :663 / :683).
+  const bool face = dist == dist_bx || dist == dist_by;                             // :621
+  const bool isx = dist_bx < dist_by;
+  const bool pos = (isx ? h.vx : h.vy) > zero;
+  const int idx = isx ? h.xi : h.yi;
+  const bool interior = face && (pos ? idx != (isx ? nx : a.m.ny) - 1 : idx != 0);
+  const int ni = pos ? idx + 1 : idx - 1;
+  const int nxi = isx ? ni : h.xi, nyi = isx ? h.yi : ni;
+  const long long acc = (long long)h.k * a.m.nc + (h.xi + nx * h.yi);   // nc < 2^31 (checked at set_mesh)
+  AxisProp<P> nax; CellProp2<P> ncp;
+  nax.w = nax.q = ncp.sig_col = ncp.neg_saf = typename P::store_t(0);
+  if (interior) {
+    nax = (exact ? a.m.ax_d : a.m.ax_inv)[(isx ? 0 : nx) + ni];
+    ncp = load_cell2(a.m.cp2, nxi + nx * nyi);
+  }
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   const N newE = h.E * ex;                                                          // :580
-  const long long acc = (long long)h.k * a.m.nc + (h.xi + nx * h.yi);   // nc < 2^31 (checked at set_mesh)
   // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
   // (EXACT), else E * ((1/dx) * (1/dy)) (<= 3 ulp from it; sums in these modes are order-dependent anyway)
   if (newE <= h.minE) {                                                             // :586-595
@@ -805,24 +850,15 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   h.y = h.y + dist * h.vy;                                                          // :616
   { N dd = dist;                                                                    // :617 (dist / ds) / c; x / 1 == x exactly
 #pragma unroll 1
-    for (int r = 0; r < a.m.n_tdiv; ++r) dd = dd / N(a.m.tdiv[r]);
+    for (int r = 0; r < a.m.n_tdiv; ++r) dd = div_cached(dd, N(a.m.tdiv[r]), a.m.tdiv_r[r]);
     h.t = h.t + dd; }
   h.E = newE;                                                                       // :618
-  if (dist == dist_bx || dist == dist_by) {                                         // :621
-    // one code path for the four faces: axis = x if dist_bx < dist_by (:622, false on NaN -> y), direction from
-    // the sign of that axis' direction cosine (:623 / :643 / :663 / :683)
-    const bool isx = dist_bx < dist_by;
-    const bool pos = (isx ? h.vx : h.vy) > zero;
-    const int idx = isx ? h.xi : h.yi;
-    const int last = (isx ? nx : a.m.ny) - 1;
-    if (pos ? idx != last : idx != 0) {                                             // interior face: neighbour cell
-      const int ni = pos ? idx + 1 : idx - 1;
-      const AxisProp<P> ax = (exact ? a.m.ax_d : a.m.ax_inv)[(isx ? 0 : nx) + ni];
-      const N w(P::unpack(ax.w)), q(P::unpack(ax.q));
+  if (face) {
+    if (interior) {                                                                 // neighbour cell
+      const N w(P::unpack(nax.w)), q(P::unpack(nax.q));
       const N np = pos ? zero : w;                                                  // enters at 0 or at the far edge dx*ds
-      h.xi = isx ? ni : h.xi; h.yi = isx ? h.yi : ni;
-      { const CellProp2<P> cp = load_cell2(a.m.cp2, h.xi + nx * h.yi);
-        h.sig_col = N(P::unpack(cp.sig_col)); h.neg_saf = N(P::unpack(cp.neg_saf)); }
+      h.xi = nxi; h.yi = nyi;
+      h.sig_col = N(P::unpack(ncp.sig_col)); h.neg_saf = N(P::unpack(ncp.neg_saf));
       h.x = isx ? np : h.x; h.wxc = isx ? w : h.wxc; h.qx = isx ? q : h.qx;
       h.y = isx ? h.y : np; h.wyc = isx ? h.wyc : w; h.qy = isx ? h.qy : q;
       return -1;                                                                    // `continue` :703 (Q15)
@@ -831,13 +867,15 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
     if (a.m.bc[side] == IMC_REFLECT) {                                              // :626-628 / :666-668
       h.mu = isx ? MathDet::atan2<P>(h.vy, -h.vx) : MathDet::atan2<P>(-h.vy, h.vx);
       MathDet::sincos<P>(h.mu, &h.vy, &h.vx);
+      h.rvx = recip_of(h.vx); h.rvy = recip_of(h.vy);
       return -1;
     }
     cn.lose<P, TK>(a.tally, h.E / N(a.m.scales[h.k]), h.pi, h.E.d());               // VACUUM :629-636 ...
     h.E = N::from_d(-1.0);
     return 2;
   }
-  if (dist == dist_col) { h.mu = N::from_d(6.283185307179586 * d.uniform(a.rng).d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx); }  // :706-710
+  if (dist == dist_col) { h.mu = N::from_d(6.283185307179586 * d.uniform(a.rng, seg).d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx);
+                           h.rvx = recip_of(h.vx); h.rvy = recip_of(h.vy); }  // :706-710
   if (dist == dist_cen) { h.t = zero; return 0; }                      // :712-717
   return -1;
 }
@@ -850,11 +888,11 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track2d
   tal.zero();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
-    Hist2<P> h; HistDraw<P, TAPE> d;
-    if (!load2d<P, HistDraw<P, TAPE>, TK>(a, pi, h, d, cn)) continue;
+    Hist2<P> h; HistDraw<P, TAPE, true> d;
+    if (!load2d<P, HistDraw<P, TAPE, true>, TK>(a, pi, h, d, cn)) continue;
     int ev;
     while ((ev = seg2d(a, h, d, tal, cn)) < 0) {}
-    store2d<P, HistDraw<P, TAPE>, TK>(a, h, d, ev, cn);
+    store2d<P, HistDraw<P, TAPE, true>, TK>(a, h, d, ev, cn);
   }
   tal.flush();
   cn.commit<TK>(a.tally);
@@ -872,7 +910,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
   Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
   Tally<P, TK> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
-  using Dr = HistDraw<P, TAPE>;
+  using Dr = HistDraw<P, TAPE, GEOM == 2>;
   constexpr int ST_EMPTY = -2, ST_ACTIVE = -1;   // >= 0: history finished with that outcome, not yet written back
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;

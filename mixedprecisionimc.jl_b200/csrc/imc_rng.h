@@ -206,6 +206,33 @@ struct SegDraw {
   }
 };
 
+// RNG back-end 1c: SegDraw without cursor state, for MC2D — a 2-D segment draws exactly one exponential and at most
+// one uniform (no `while mu == 0` resampling), so the caller's segment counter selects the words and there is no
+// extra stream.  Same words as SegDraw for the same (seed, particle id, step, segment).
+template <class P>
+struct SegDrawLean {
+  uint32_t buf[4];
+  uint32_t id_lo, id_hi;
+  IMC_HD void init(uint64_t id) {
+    id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32);
+    buf[0] = buf[1] = buf[2] = buf[3] = 0u;
+  }
+  IMC_HD void next_segment_rk(const uint32_t* rk, uint32_t step, uint32_t seg) {   // seg: 0-based segment of the history
+    if (P::id == 2 || (seg & 1u) == 0u) {
+      uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? seg : (seg >> 1))};
+      Philox::block_rk(c, rk, buf);
+    }
+  }
+  IMC_HD Num<P> randexp(uint32_t seg) const {
+    if constexpr (P::id == 2) return Num<P>(randexp64_from_word(((uint64_t)buf[1] << 32) | buf[0]));
+    else return Num<P>(P::rnd(randexp32_from_word((seg & 1u) ? buf[2] : buf[0])));
+  }
+  IMC_HD Num<P> uniform(uint32_t seg) const {
+    if constexpr (P::id == 2) return uniform_from_word<P>(((uint64_t)buf[3] << 32) | buf[2]);
+    else return uniform_from_word<P>((uint64_t)((seg & 1u) ? buf[3] : buf[1]));
+  }
+};
+
 // RNG back-end 2: tape (replay mode).  Pre-drawn Float64 numbers, draw-major layout
 // tape[k * stride + slot]; uniforms must already be T-representable (they are rand(T) values),
 // exponentials are Float64 and are converted to T here exactly as randexp(T) does.

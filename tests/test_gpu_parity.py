@@ -277,3 +277,16 @@ def test_native_precision_field_transfers_on_gpu(gpu_lib, precision, deck):
     assert np.array_equal(eng.field_native("temp"), t * 2) and np.array_equal(eng.field_native("matenergydens"), m * 2)
     assert np.array_equal(eng.field("radenergydens").reshape(-1, order="F"), (r * 2).astype(np.float64))
     assert eng.stream() != 0
+
+
+def test_cached_reciprocal_division_is_ieee_exact(gpu_lib):
+    """imc_fastdiv.cuh: the division the 2-D tracking loop performs with a cached reciprocal equals the IEEE quotient
+    `a / b` for every operand pair tried on the device (random pairs, tracking-shaped pairs, pairs constructed next to
+    rounding boundaries and their neighbours)."""
+    import ctypes as C
+    f = gpu_lib.dll.imc_cuda_selftest_div
+    f.argtypes = [C.c_int, C.c_uint64, C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
+    bad, n = C.c_ulonglong(), C.c_ulonglong()
+    fb = (C.c_float * 4)()
+    assert f(0, 20261017, 100000, C.byref(bad), C.byref(n), fb) == 0
+    assert n.value > 1e11 and bad.value == 0, (n.value, bad.value, list(fb))
