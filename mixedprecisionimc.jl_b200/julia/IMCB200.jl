@@ -70,11 +70,16 @@ end
 engine(inputs, mesh, simvars) = get!(() -> attach!(inputs, mesh, simvars), ENGINES, mesh)
 engine(mesh) = ENGINES[mesh]
 
-function pull!(mesh, field::Symbol, id::Integer)   # imc_get_field into the reference's array (keeps its element type)
+function pull!(mesh, field::Symbol, id::Integer)   # imc_get_field_native straight into the reference's Array{T}
     dst = getfield(mesh, field)
-    buf = Vector{Float64}(undef, length(dst))
-    check(engine(mesh), ccall((:imc_get_field, libimc), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), engine(mesh), id, buf, length(buf)))
-    setfield!(mesh, field, reshape(eltype(dst).(buf), size(dst)))
+    h = engine(mesh)
+    es = ccall((:imc_field_elsize, libimc), Int32, (Ptr{Cvoid}, Int32), h, id)
+    if es != sizeof(eltype(dst))                     # mesh.temp turns Float64 after the first LINEARIZED tally (imc_tally.jl:72)
+        dst = Array{es == 8 ? Float64 : (es == 4 ? Float32 : Float16)}(undef, size(dst))
+        setfield!(mesh, field, dst)
+    end
+    GC.@preserve dst check(h, ccall((:imc_get_field_native, libimc), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64), h, id, pointer(dst), sizeof(dst)))
+    dst
 end
 
 """Stand-in for the reference's `particles` vector: the engine owns the population."""
