@@ -107,7 +107,7 @@ struct EngineT : EngineBase {
   DBuf<S> q_dep, q_tot, q_rad;
   DBuf<double> d_max;
   DBuf<int> d_flag;
-  DBuf<unsigned long long> over_flag;
+  DBuf<unsigned long long> over_flag, timeline;
   DBuf<long long> blk_cnt;
   // EXACT tally mode: deposit records
   DBuf<int> rec_cnt;
@@ -602,6 +602,14 @@ struct EngineT : EngineBase {
     ++n_transport_calls;
     a.ev_in = nullptr; a.ev_out = nullptr; a.ev_count = nullptr; a.ev_nseg = nullptr; a.ev_extra = nullptr;
     a.queue = over_flag.p + 1;
+    static const bool want_timeline = getenv("IMC_TRACK_TIMING") && atoi(getenv("IMC_TRACK_TIMING")) != 0;
+    a.timeline = nullptr;
+    if (want_timeline) {
+      IMC_CK(timeline.ensure(4));
+      const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
+      IMC_CK(cudaMemcpyAsync(timeline.p, init, sizeof init, cudaMemcpyHostToDevice, stream));
+      a.timeline = timeline.p;
+    }
     a.refill_min = refill_min_env();
     if (n_part > 0) {
       int blocks_per_sm = 2048 / TRACK_THREADS;
@@ -654,6 +662,14 @@ struct EngineT : EngineBase {
     };
     double lost;
     if (mode == IMC_TALLY_FIXED) { long long v; memcpy(&v, &sc[RB_LOST], 8); lost = (double)v / fx_mul_lost; } else lost = sc[RB_LOST];
+    if (a.timeline) {
+      unsigned long long tl[4];
+      IMC_CK(cudaMemcpy(tl, timeline.p, sizeof tl, cudaMemcpyDeviceToHost));
+      if (tl[0] != ~0ull && tl[2] != 0ull)
+        fprintf(stderr, "[imc timeline] step %lld variant %d: kernel %.2f ms, queue empty after %.2f ms, tail %.2f ms, %lld particles\n",
+                (long long)step, variant, (tl[2] - tl[0]) * 1e-6, tl[1] == ~0ull ? -1.0 : (tl[1] - tl[0]) * 1e-6,
+                tl[1] == ~0ull ? -1.0 : (tl[2] - tl[1]) * 1e-6, n_part);
+    }
     last_mode = mode;
     iterations += cnt(RB_SEG);
     if (ms > 0) {

@@ -22,6 +22,9 @@ namespace imc {
 #ifndef IMC_TRACK_THREADS
 #define IMC_TRACK_THREADS 256
 #endif
+#ifndef IMC_EARLY_NEXT_CELL
+#define IMC_EARLY_NEXT_CELL 1   // MC2D: request the next cell's constants as soon as the event is known (0: in the face branch)
+#endif
 #ifndef IMC_TRACK_MIN_BLOCKS
 #define IMC_TRACK_MIN_BLOCKS 4
 #endif
@@ -630,6 +633,9 @@ struct TrackArgs {
   // dynamic schedule
   unsigned long long* queue;  // next unclaimed particle index
   int refill_min;             // refill when at least this many lanes of a warp are idle
+  // optional timeline of the dynamic schedule (IMC_TRACK_TIMING=1): [0] first block start, [1] first time a warp found the
+  // queue empty, [2] last block exit (globaltimer ns)
+  unsigned long long* timeline;
 };
 
 // One particle's registers while it is being tracked, and one loop iteration ("segment") as a device
@@ -832,10 +838,12 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   const long long acc = (long long)h.k * a.m.nc + (h.xi + nx * h.yi);   // nc < 2^31 (checked at set_mesh)
   AxisProp<P> nax; CellProp2<P> ncp;
   nax.w = nax.q = ncp.sig_col = ncp.neg_saf = typename P::store_t(0);
+#if IMC_EARLY_NEXT_CELL
   if (interior) {
     nax = (exact ? a.m.ax_d : a.m.ax_inv)[(isx ? 0 : nx) + ni];
     ncp = load_cell2(a.m.cp2, nxi + nx * nyi);
   }
+#endif
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
   const N newE = h.E * ex;                                                          // :580
   // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
@@ -855,6 +863,10 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   h.E = newE;                                                                       // :618
   if (face) {
     if (interior) {                                                                 // neighbour cell
+#if !IMC_EARLY_NEXT_CELL
+      nax = (exact ? a.m.ax_d : a.m.ax_inv)[(isx ? 0 : nx) + ni];
+      ncp = load_cell2(a.m.cp2, nxi + nx * nyi);
+#endif
       const N w(P::unpack(nax.w)), q(P::unpack(nax.q));
       const N np = pos ? zero : w;                                                  // enters at 0 or at the far edge dx*ds
       h.xi = nxi; h.yi = nyi;
@@ -917,6 +929,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
   int st = ST_EMPTY;
   bool drained = false;
   unsigned iter = 0;
+  if (a.timeline && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(a.timeline, t); }
   Hist1<P> h1; Hist2<P> h2; Dr d;
   while (true) {
     unsigned idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
@@ -941,7 +954,10 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
             if (ok) st = ST_ACTIVE;
           }
         }
-        if (base + nidle >= a.n) drained = true;
+        if (base + nidle >= a.n) {
+          if (a.timeline && !drained && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(a.timeline + 1, t); }
+          drained = true;
+        }
         idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
       }
     }
@@ -960,6 +976,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, IMC_TRACK_MIN_BLOCKS) k_track_r
   if (st >= 0) {   // histories that finished after the last refill
     if constexpr (GEOM == 1) store1d<P, Dr, TK>(a, h1, d, st, cn); else store2d<P, Dr, TK>(a, h2, d, st, cn);
   }
+  if (a.timeline && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMax(a.timeline + 2, t); }
   tal.flush();
   cn.commit<TK>(a.tally);
 }
