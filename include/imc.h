@@ -221,6 +221,19 @@ int32_t imc_field_elsize(imc_handle h, int32_t field);
 int imc_get_field_native(imc_handle h, int32_t field, void* dst, int64_t bytes);
 int imc_set_state_native(imc_handle h, const void* temp, const void* matenergydens, const void* radenergydens);
 
+/* Per-step history kept by the engine — the reference's mesh.temp_saved / matenergy_saved / radenergy_saved /
+ * energyincrease_saved lists (imc_tally.jl:58, :138-142; written out by imc_output.jl:50-57).  After
+ * imc_history_enable(h, capacity) every imc_tally / imc_tally_finish appends one snapshot of IMC_FIELD_TEMP (always
+ * Float64: the exact image of the reference's value whatever its type at that step), IMC_FIELD_MATENERGYDENS,
+ * IMC_FIELD_RADENERGYDENS and IMC_FIELD_NRG_INC (element type T) to device memory, with no host round trip; the host
+ * fetches `count` consecutive snapshots when it wants them (end of run, or every k steps) with imc_history_get and may
+ * empty the buffer with imc_history_clear.  When `capacity` snapshots are stored further steps are not recorded and are
+ * counted in *dropped.  capacity == 0 frees the buffers and stops recording. */
+int imc_history_enable(imc_handle h, int64_t capacity);
+int imc_history_count(imc_handle h, int64_t* stored, int64_t* dropped);
+int imc_history_get(imc_handle h, int32_t field, int64_t first, int64_t count, void* dst, int64_t bytes);
+int imc_history_clear(imc_handle h);
+
 /* The CUDA stream (cudaStream_t) every kernel of this engine is launched on, so that a host can bracket
  * calls with its own events; NULL for the oracle. */
 void* imc_stream(imc_handle h);

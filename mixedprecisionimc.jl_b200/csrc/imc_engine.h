@@ -29,6 +29,10 @@ struct EngineBase {
   virtual int get_field_native(int, void*, int64_t) = 0;
   virtual int set_state_native(const void*, const void*, const void*) = 0;
   virtual void* stream_handle() = 0;
+  virtual int history_enable(int64_t) = 0;
+  virtual int history_count(int64_t*, int64_t*) = 0;
+  virtual int history_get(int, int64_t, int64_t, void*, int64_t) = 0;
+  virtual int history_clear() = 0;
   virtual int64_t num_particles() = 0;
   virtual int64_t launches() = 0;
   virtual int get_particles(double*, uint64_t*, int64_t) = 0;

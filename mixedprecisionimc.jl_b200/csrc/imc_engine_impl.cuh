@@ -774,6 +774,7 @@ struct EngineT : EngineBase {
     IMC_CK(cudaMemcpyAsync(&has_nan, d_flag.p, sizeof has_nan, cudaMemcpyDeviceToHost, stream));
     IMC_CK(cudaStreamSynchronize(stream));
     rad_total_h = (double)h2[2];
+    IMC_RC(history_push());
     if (out) {
       out->totalenergydep = totalenergydep; out->energy_increase = (double)h2[0];
       out->max_temp = has_nan ? NAN : mx; out->total_energy_density = (double)h2[1];
@@ -898,6 +899,58 @@ struct EngineT : EngineBase {
     return IMC_OK;
   }
   void* stream_handle() override { return (void*)stream; }
+
+  // ---- per-step history on the device (imc_tally.jl:58, :138-142) ---------------------------------------------
+  DBuf<double> hist_temp; DBuf<S> hist_mat, hist_rad, hist_inc;
+  long long hist_cap = 0, hist_n = 0, hist_dropped = 0;
+  int history_enable(int64_t cap) override {
+    if (!have_mesh) { err = "history_enable before set_mesh"; return IMC_ERR_STATE; }
+    if (cap < 0) { err = "history_enable: negative capacity"; return IMC_ERR_ARG; }
+    IMC_RC(use_device());
+    IMC_CK(cudaStreamSynchronize(stream));
+    hist_temp.release(); hist_mat.release(); hist_rad.release(); hist_inc.release();
+    hist_cap = hist_n = hist_dropped = 0;
+    if (cap > 0) {
+      const size_t n = (size_t)cap * (size_t)nc;
+      IMC_CK(hist_temp.alloc(n, false)); IMC_CK(hist_mat.alloc(n, false)); IMC_CK(hist_rad.alloc(n, false)); IMC_CK(hist_inc.alloc(n, false));
+      hist_cap = cap;
+    }
+    return IMC_OK;
+  }
+  int history_push() {   // end of Tally.tally
+    if (hist_cap == 0) return IMC_OK;
+    if (hist_n == hist_cap) { ++hist_dropped; return IMC_OK; }
+    const size_t off = (size_t)hist_n * (size_t)nc;
+    IMC_CK(cudaMemcpyAsync(hist_temp.p + off, temp.p, nc * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    IMC_CK(cudaMemcpyAsync(hist_mat.p + off, matenergydens.p, nc * sizeof(S), cudaMemcpyDeviceToDevice, stream));
+    IMC_CK(cudaMemcpyAsync(hist_rad.p + off, radenergydens.p, nc * sizeof(S), cudaMemcpyDeviceToDevice, stream));
+    IMC_CK(cudaMemcpyAsync(hist_inc.p + off, nrg_inc.p, nc * sizeof(S), cudaMemcpyDeviceToDevice, stream));
+    ++hist_n;
+    return IMC_OK;
+  }
+  int history_count(int64_t* stored, int64_t* dropped) override {
+    if (stored) *stored = hist_n;
+    if (dropped) *dropped = hist_dropped;
+    return IMC_OK;
+  }
+  int history_get(int f, int64_t first, int64_t count, void* dst, int64_t bytes) override {
+    IMC_RC(use_device());
+    if (first < 0 || count < 0 || first + count > hist_n) { err = "history_get: snapshot range outside the stored history"; return IMC_ERR_ARG; }
+    const void* src = nullptr; size_t es = sizeof(S);
+    switch (f) {
+      case IMC_FIELD_TEMP: src = hist_temp.p; es = sizeof(double); break;
+      case IMC_FIELD_MATENERGYDENS: src = hist_mat.p; break;
+      case IMC_FIELD_RADENERGYDENS: src = hist_rad.p; break;
+      case IMC_FIELD_NRG_INC: src = hist_inc.p; break;
+      default: err = "history_get: field has no history (temp, matenergydens, radenergydens, nrg_inc)"; return IMC_ERR_ARG;
+    }
+    if (bytes != (int64_t)(count * nc * (long long)es)) { err = "history_get: size"; return IMC_ERR_ARG; }
+    if (count == 0) return IMC_OK;
+    IMC_CK(cudaMemcpyAsync(dst, static_cast<const char*>(src) + (size_t)first * (size_t)nc * es, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    return IMC_OK;
+  }
+  int history_clear() override { hist_n = 0; hist_dropped = 0; return IMC_OK; }
 
   int set_state(const double* temp_, const double* mat, const double* rad) override {
     if (!have_mesh) { err = "set_state before set_mesh"; return IMC_ERR_STATE; }

@@ -144,6 +144,7 @@ class MeshStruct:
     temp_saved: List[np.ndarray] = field(default_factory=list)
     radenergy_saved: List[np.ndarray] = field(default_factory=list)
     matenergy_saved: List[np.ndarray] = field(default_factory=list)
+    energyincrease_saved: List[np.ndarray] = field(default_factory=list)
     engine: Any = None          # the imc engine that owns the device copy
 
     @property

@@ -250,6 +250,25 @@ class Simulation:
     def engine(self) -> _lib.Engine:
         return self.mesh.engine
 
+    def fetch_history(self, clear: bool = True):
+        """Append the snapshots the engine recorded (``engine.history_enable``) to the reference's lists
+        ``mesh.temp_saved / matenergy_saved / radenergy_saved / energyincrease_saved`` (imc_tally.jl:58, :138-142), in
+        the reference's array shapes, and leave the latest fields in ``mesh.temp`` etc. — one download at the end of a
+        run (or every k steps) instead of three per step."""
+        eng, mesh = self.engine, self.mesh
+        n, _ = eng.history_count()
+        if n == 0:
+            return 0
+        shape = (eng.cfg.nx, eng.cfg.ny) if eng.cfg.geometry == 2 else (eng.cfg.nx,)
+        for name, lst in (("temp", mesh.temp_saved), ("matenergydens", mesh.matenergy_saved), ("radenergydens", mesh.radenergy_saved),
+                          ("nrg_inc", mesh.energyincrease_saved)):
+            h = eng.history(name).astype(np.float64)
+            lst.extend(h[k].reshape(shape, order="F") for k in range(n))
+        mesh.temp, mesh.matenergydens, mesh.radenergydens = mesh.temp_saved[-1], mesh.matenergy_saved[-1], mesh.radenergy_saved[-1]
+        if clear:
+            eng.history_clear()
+        return n
+
     def done(self) -> bool:
         return not (self.simvars.t <= self.simvars.t_end)
 

@@ -149,6 +149,23 @@ module Tally
     end
 end
 
+"""Deferred variant of the per-step pulls: `IMCB200.history_enable(mesh, nsteps)` once, then `Tally.tally` may skip
+`pull!`/`push!` and `IMCB200.fetch_history!(mesh)` appends every recorded step to the reference's `*_saved` lists at
+the end of the run (imc_history_* in include/imc.h)."""
+history_enable(mesh, nsteps::Integer) = check(engine(mesh), ccall((:imc_history_enable, libimc), Cint, (Ptr{Cvoid}, Int64), engine(mesh), nsteps))
+function fetch_history!(mesh)
+    h = engine(mesh); n = Ref{Int64}(0); dropped = Ref{Int64}(0)
+    check(h, ccall((:imc_history_count, libimc), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), h, n, dropped))
+    T = eltype(mesh.matenergydens); shape = size(mesh.matenergydens)
+    for (id, lst, E) in ((0, mesh.temp_saved, Float64), (8, mesh.matenergy_saved, T), (9, mesh.radenergy_saved, T), (10, mesh.energyincrease_saved, T))
+        buf = Array{E}(undef, prod(shape), n[])
+        GC.@preserve buf check(h, ccall((:imc_history_get, libimc), Cint, (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Cvoid}, Int64), h, id, 0, n[], pointer(buf), sizeof(buf)))
+        for k in 1:n[]; push!(lst, reshape(buf[:, k], shape)); end
+    end
+    check(h, ccall((:imc_history_clear, libimc), Cint, (Ptr{Cvoid},), h))
+    return n[]
+end
+
 module EnergyCheck
     import ..IMCB200: engine, check, libimc, EnergyStats, STEP
     function energychecker(inputs, mesh, simvars, particles)                  # imc_energycheck.jl:10

@@ -112,6 +112,10 @@ ABI = [
     ("imc_get_field_native", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
     ("imc_set_state_native", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("imc_stream", C.c_void_p, [C.c_void_p]),
+    ("imc_history_enable", C.c_int, [C.c_void_p, C.c_int64]),
+    ("imc_history_count", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("imc_history_get", C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
+    ("imc_history_clear", C.c_int, [C.c_void_p]),
     ("imc_num_particles", C.c_int64, [C.c_void_p]),
     ("imc_kernel_launches", C.c_int64, [C.c_void_p]),
     ("imc_get_particles", C.c_int, [C.c_void_p, _DP, C.POINTER(C.c_uint64), C.c_int64]),
@@ -358,6 +362,27 @@ class Engine:
             return a.ctypes.data_as(C.c_void_p)
         self._check(self.lib.dll.imc_set_state_native(self._h, ptr(temp, "temp"), ptr(matenergydens, "matenergydens"),
                                                       ptr(radenergydens, "radenergydens")))
+
+    # ---- per-step history kept by the engine (mesh.temp_saved / matenergy_saved / radenergy_saved / energyincrease_saved) ----
+    def history_enable(self, capacity: int):
+        self._check(self.lib.dll.imc_history_enable(self._h, int(capacity)))
+
+    def history_count(self):
+        n, d = C.c_int64(), C.c_int64()
+        self._check(self.lib.dll.imc_history_count(self._h, C.byref(n), C.byref(d)))
+        return n.value, d.value
+
+    def history(self, name: str, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """[count, Nc] snapshots of `name` (temp: Float64; matenergydens / radenergydens / nrg_inc: the deck precision)."""
+        if count is None:
+            count = self.history_count()[0] - first
+        dt = np.float64 if name == "temp" else PRECISION_DTYPES[self.cfg.precision]
+        out = np.empty((count, self.nc), dtype=dt)
+        self._check(self.lib.dll.imc_history_get(self._h, FIELDS[name], int(first), int(count), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def history_clear(self):
+        self._check(self.lib.dll.imc_history_clear(self._h))
 
     def stream(self) -> int:
         """cudaStream_t of the engine as an integer (0 for the oracle)."""

@@ -150,6 +150,10 @@ struct EngineBase {
   virtual int field_elsize(int) = 0;
   virtual int get_field_native(int, void*, int64_t) = 0;
   virtual int set_state_native(const void*, const void*, const void*) = 0;
+  virtual int history_enable(int64_t) = 0;
+  virtual int history_count(int64_t*, int64_t*) = 0;
+  virtual int history_get(int, int64_t, int64_t, void*, int64_t) = 0;
+  virtual int history_clear() = 0;
   virtual int64_t num_particles() = 0;
   virtual int get_particles(double*, uint64_t*, int64_t) = 0;
   virtual int set_particles(const double*, const uint64_t*, int64_t) = 0;
@@ -960,6 +964,10 @@ struct Oracle : EngineBase {
       if (temp[i] > max_temp || temp[i] != temp[i]) max_temp = temp[i];
     }
     if (cfg.linearized && P::id != 2) temp_wide = true;
+    if (hist_cap > 0) {   // push!(mesh.temp_saved, copy(mesh.temp)) ... (:58, :138-142)
+      if ((int64_t)hist_temp.size() == hist_cap) ++hist_dropped;
+      else { hist_temp.push_back(temp); hist_mat.push_back(matenergydens); hist_rad.push_back(radenergydens); hist_inc.push_back(nrg_inc); }
+    }
     if (out) {
       out->totalenergydep = totalenergydep.d();
       out->energy_increase = jl_sum(nrg_inc).d();
@@ -1047,6 +1055,35 @@ struct Oracle : EngineBase {
     if (rad) { c.resize(nc); for (size_t i = 0; i < nc; ++i) c[i] = unpack_native(rad, i, P::bytes); }
     return set_state(temp_ ? a.data() : nullptr, mat ? b.data() : nullptr, rad ? c.data() : nullptr);
   }
+  // per-step history (include/imc.h): the reference's *_saved lists
+  int64_t hist_cap = 0, hist_dropped = 0;
+  std::vector<std::vector<double>> hist_temp;
+  std::vector<std::vector<N>> hist_mat, hist_rad, hist_inc;
+  int history_enable(int64_t cap) override {
+    if (cap < 0) return IMC_ERR_ARG;
+    hist_cap = cap; hist_dropped = 0; hist_temp.clear(); hist_mat.clear(); hist_rad.clear(); hist_inc.clear();
+    return IMC_OK;
+  }
+  int history_count(int64_t* stored, int64_t* dropped) override {
+    if (stored) *stored = (int64_t)hist_temp.size();
+    if (dropped) *dropped = hist_dropped;
+    return IMC_OK;
+  }
+  int history_get(int f, int64_t first, int64_t count, void* dst, int64_t bytes) override {
+    if (first < 0 || count < 0 || first + count > (int64_t)hist_temp.size()) return IMC_ERR_ARG;
+    if (f == IMC_FIELD_TEMP) {
+      if (bytes != count * (int64_t)nc * 8) return IMC_ERR_ARG;
+      for (int64_t s = 0; s < count; ++s) memcpy(static_cast<double*>(dst) + s * nc, hist_temp[first + s].data(), nc * 8);
+      return IMC_OK;
+    }
+    const std::vector<std::vector<N>>* src = f == IMC_FIELD_MATENERGYDENS ? &hist_mat : f == IMC_FIELD_RADENERGYDENS ? &hist_rad
+                                             : f == IMC_FIELD_NRG_INC ? &hist_inc : nullptr;
+    if (!src || bytes != count * (int64_t)nc * P::bytes) return IMC_ERR_ARG;
+    for (int64_t s = 0; s < count; ++s)
+      for (size_t i = 0; i < nc; ++i) pack_native((*src)[first + s][i].d(), dst, (size_t)s * nc + i, P::bytes);
+    return IMC_OK;
+  }
+  int history_clear() override { hist_dropped = 0; hist_temp.clear(); hist_mat.clear(); hist_rad.clear(); hist_inc.clear(); return IMC_OK; }
   int64_t num_particles() override { return (int64_t)particles.size(); }
   int get_particles(double* slots, uint64_t* ids_out, int64_t cap) override {
     if (cap < (int64_t)particles.size()) return IMC_ERR_ARG;

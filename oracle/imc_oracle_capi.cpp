@@ -79,6 +79,10 @@ int32_t imc_field_elsize(imc_handle h, int32_t f) { return h ? h->e->field_elsiz
 int imc_get_field_native(imc_handle h, int32_t f, void* dst, int64_t bytes) { GUARD(h->e->get_field_native(f, dst, bytes)); }
 int imc_set_state_native(imc_handle h, const void* t, const void* m, const void* r) { GUARD(h->e->set_state_native(t, m, r)); }
 void* imc_stream(imc_handle) { return nullptr; }
+int imc_history_enable(imc_handle h, int64_t cap) { GUARD(h->e->history_enable(cap)); }
+int imc_history_count(imc_handle h, int64_t* n, int64_t* dropped) { GUARD(h->e->history_count(n, dropped)); }
+int imc_history_get(imc_handle h, int32_t f, int64_t first, int64_t count, void* dst, int64_t bytes) { GUARD(h->e->history_get(f, first, count, dst, bytes)); }
+int imc_history_clear(imc_handle h) { GUARD(h->e->history_clear()); }
 int64_t imc_num_particles(imc_handle h) { return h ? h->e->num_particles() : -1; }
 int64_t imc_kernel_launches(imc_handle h) { return h ? 0 : -1; }
 int imc_get_particles(imc_handle h, double* s, uint64_t* ids, int64_t cap) { GUARD(h->e->get_particles(s, ids, cap)); }

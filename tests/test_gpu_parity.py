@@ -290,3 +290,24 @@ def test_cached_reciprocal_division_is_ieee_exact(gpu_lib):
     fb = (C.c_float * 4)()
     assert f(0, 20261017, 100000, C.byref(bad), C.byref(n), fb) == 0
     assert n.value > 1e11 and bad.value == 0, (n.value, bad.value, list(fb))
+
+
+@pytest.mark.parametrize("deck,precision", [("suolson", "FLOAT16"), ("suolson", "FLOAT64"), ("crooked", "FLOAT32")])
+def test_engine_side_history_on_gpu(gpu_lib, deck, precision):
+    """imc_history_* on the device: snapshots recorded at the end of every tally equal the per-step downloads."""
+    inputs = (decks.suolson(precision=precision, n_input=500, n_max=5000) if deck == "suolson"
+              else decks.crooked_pipe(precision=precision, n_input=2000, n_max=20000))
+    sim = driver.setup(inputs, gpu_lib)
+    sim.save_history = False
+    eng = sim.engine
+    eng.history_enable(3)
+    want = {k: [] for k in ("temp", "matenergydens", "radenergydens", "nrg_inc")}
+    for _ in range(5):
+        sim.advance()
+        for k in want:
+            want[k].append(eng.field(k).reshape(-1, order="F").copy())
+    assert eng.history_count() == (3, 2)
+    for k in want:
+        assert np.array_equal(eng.history(k).astype(np.float64), np.array(want[k][:3])), k
+    assert np.array_equal(eng.history("radenergydens", first=2, count=1).astype(np.float64), np.array(want["radenergydens"][2:3]))
+    assert sim.fetch_history() == 3 and eng.history_count() == (0, 0)

@@ -208,3 +208,37 @@ def test_native_precision_field_transfers(oracle_lib, precision):
         eng.lib.dll.imc_get_field_native  # wrong byte count
         eng._check(eng.lib.dll.imc_get_field_native(eng._h, lib.FIELDS["fleck"], t.ctypes.data, 3))
     assert eng.stream() == 0
+
+
+@pytest.mark.parametrize("deck", ["suolson", "crooked"])
+def test_engine_side_history_matches_per_step_downloads(oracle_lib, deck):
+    """imc_history_*: the snapshots the engine records at the end of every Tally.tally (the reference's temp_saved /
+    matenergy_saved / radenergy_saved / energyincrease_saved lists, imc_tally.jl:58, :138-142) equal the fields a host
+    would download step by step; a full buffer stops recording and counts the dropped steps."""
+    inputs = (decks.suolson(precision="FLOAT32", n_input=500, n_max=5000) if deck == "suolson"
+              else decks.crooked_pipe(precision="FLOAT32", n_input=2000, n_max=20000))
+    sim = driver.setup(inputs, oracle_lib)
+    sim.save_history = False
+    eng = sim.engine
+    eng.history_enable(4)
+    want = {k: [] for k in ("temp", "matenergydens", "radenergydens", "nrg_inc")}
+    for _ in range(6):
+        sim.advance()
+        for k in want:
+            want[k].append(eng.field(k).reshape(-1, order="F").copy())
+    assert eng.history_count() == (4, 2)
+    for k in want:
+        h = eng.history(k)
+        assert h.shape == (4, eng.nc) and h.dtype == (np.float64 if k == "temp" else np.float32)
+        assert np.array_equal(h.astype(np.float64), np.array(want[k][:4])), k
+    assert np.array_equal(eng.history("matenergydens", first=1, count=2).astype(np.float64), np.array(want["matenergydens"][1:3]))
+    n0 = len(sim.mesh.temp_saved)
+    assert sim.fetch_history() == 4 and len(sim.mesh.temp_saved) == n0 + 4 and eng.history_count() == (0, 0)
+    assert np.array_equal(np.asarray(sim.mesh.matenergy_saved[-1]).reshape(-1, order="F"), want["matenergydens"][3])
+    with pytest.raises(lib.ImcError):
+        eng.history("temp", first=0, count=1)       # nothing stored any more
+    with pytest.raises(lib.ImcError):
+        eng._check(eng.lib.dll.imc_history_get(eng._h, lib.FIELDS["fleck"], 0, 0, None, 0))
+    eng.history_enable(0)
+    sim.advance()
+    assert eng.history_count() == (0, 0)
