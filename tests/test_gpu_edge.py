@@ -1,0 +1,115 @@
+"""Edge cases of the transport step on the GPU, against the oracle (bit-exact particles, events and counts) or through
+size-independent properties at the full BASELINE size:
+empty population, degenerate meshes (1 x 1, 1 x N, N x 1), every boundary VACUUM, distance scale != 1 together with
+c != 1 (both time divisors), population sizes that are not multiples of the warp / block size, and the 4096 x 4096,
+1.25e8-particle crooked pipe (conservation, outcome bookkeeping, schedule independence of the FIXED tallies)."""
+import numpy as np
+import pytest
+
+from mpimc_b200 import decks, driver, lib
+from test_gpu_parity import assert_step_parity, run_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def degenerate_2d(precision, nx, ny, bcs, n_input=400, distancescale="1.0"):
+    f16 = precision == "FLOAT16"   # NMAX must be Float16-representable (Q10); scaled energies keep the weights normal
+    d = decks.small_2d(precision=precision, n_input=n_input, n_max=60000 if f16 else 100000, bcs=bcs, energyscales=(1024.0,) if f16 else (1.0,))
+    d["XMESHNODES"] = np.linspace(0.0, 1.0, nx + 1).round(10)
+    d["YMESHNODES"] = np.linspace(0.0, 2.0, ny + 1).round(10)
+    d["DISTANCESCALE"] = distancescale
+    return d
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32", "FLOAT16"])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (9, 1), (3, 5)])
+def test_degenerate_meshes(gpu_lib, oracle_lib, precision, shape):
+    for bcs in (("REFLECT",) * 4, ("VACUUM",) * 4, ("VACUUM", "REFLECT", "REFLECT", "VACUUM")):
+        inputs = degenerate_2d(precision, shape[0], shape[1], bcs)
+        a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=3, precision=precision)
+        assert_step_parity(a, b, out, precision)
+        esc = sum(r[0]["transport"]["n_escaped"] for r in out)
+        assert (esc > 0) == ("VACUUM" in bcs)
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32"])
+@pytest.mark.parametrize("distancescale", ["4.0", "3.0"])
+def test_distance_scale_and_both_time_divisors(gpu_lib, oracle_lib, precision, distancescale):
+    """(dist / ds) / c with ds != 1 and c != 1 (imc_transport.jl:617): both divisions run, one of them by a cached
+    reciprocal in Float32."""
+    inputs = degenerate_2d(precision, 6, 4, ("REFLECT", "VACUUM", "REFLECT", "REFLECT"), n_input=1500, distancescale=distancescale)
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=3, precision=precision)
+    assert_step_parity(a, b, out, precision)
+    inputs = decks.suolson(precision=precision, n_input=1500, n_max=20000)
+    inputs["DISTANCESCALE"] = distancescale
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=4, precision=precision)
+    assert_step_parity(a, b, out, precision)
+
+
+def test_empty_population(gpu_lib, oracle_lib):
+    """transport / clean / tally / energycheck on an engine that holds no particle."""
+    for inputs in (decks.suolson(precision="FLOAT32", n_input=100, n_max=1000), decks.small_2d(precision="FLOAT32", n_input=100)):
+        for library in (gpu_lib, oracle_lib):
+            sim = driver.setup(inputs, library)
+            eng = sim.engine
+            eng.update(float(sim.simvars.dt))
+            eng.set_particles(np.zeros((0, eng.nslots)))
+            tr = eng.transport(float(sim.simvars.dt), 0)
+            assert tr["segments"] == 0 and tr["histories"] == 0 and tr["n_census"] == 0
+            assert eng.clean() == 0 and eng.num_particles() == 0
+            st = eng.tally(0.0, float(sim.simvars.dt))
+            assert np.all(eng.field("radenergydens") == 0) and st["totalenergydep"] == 0
+            slots, ids = eng.particles()
+            assert slots.shape == (0, eng.nslots) and ids.shape == (0,)
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 255, 257, 1000])
+@pytest.mark.parametrize("track", [lib.TRACK_HISTORY, lib.TRACK_REFILL])
+def test_ragged_population_sizes(gpu_lib, oracle_lib, n, track):
+    """Populations that do not fill a warp / a block, under both history schedules: same particles as the oracle."""
+    inputs = decks.crooked_pipe(precision="FLOAT32", n_input=3000, n_max=60000, cellmin=1, pairwise="FALSE")
+    a = driver.setup(inputs, gpu_lib, track_mode=track)
+    b = driver.setup(inputs, oracle_lib)
+    a.advance(); b.advance()
+    slots, ids = b.engine.particles()
+    keep = np.linspace(0, len(ids) - 1, n).astype(int)
+    for s in (a, b):
+        s.engine.set_particles(slots[keep], ids[keep])
+    ta = a.engine.transport(float(a.simvars.dt), 1)
+    tb = b.engine.transport(float(b.simvars.dt), 1)
+    for k in ("segments", "histories", "n_census", "n_absorbed", "n_escaped"):
+        assert ta[k] == tb[k], (k, ta, tb)
+    assert a.engine.clean() == b.engine.clean()
+    pa, ia = a.engine.particles(); pb, ib = b.engine.particles()
+    assert np.array_equal(ia, ib) and np.array_equal(pa, pb)
+
+
+def test_full_size_crooked_pipe_properties(gpu_lib):
+    """BASELINE config 5 at its per-GPU size (4096 x 4096 cells, NMAX 1.25e8, Float32): properties that do not need the
+    oracle — every history ends in exactly one outcome, the census count is the population after clean, the energy
+    balance of imc_energycheck.jl:34 closes to Float32 accuracy, and with FIXED tallies the static and the warp-refill
+    schedules give bit-identical fields and segment counts."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs 40 GB of device memory")
+    inputs = decks.crooked_pipe(precision="FLOAT32", n_input=62_500_000, n_max=125_000_000, cellmin=1, mesh_cells=(4096, 4096), pairwise="FALSE")
+    fields = {}
+    for track in (lib.TRACK_REFILL, lib.TRACK_HISTORY):
+        sim = driver.setup(inputs, gpu_lib, tally_mode=lib.TALLY_FIXED, track_mode=track)
+        sim.save_history = False
+        segs = []
+        for _ in range(2):
+            r = sim.advance()
+            tr = r["transport"]
+            assert tr["histories"] == tr["n_census"] + tr["n_absorbed"] + tr["n_escaped"] and tr["n_errors"] == 0
+            assert sim.engine.num_particles() == tr["n_census"]
+            assert tr["histories"] > 60_000_000 and tr["segments"] > 10 * tr["histories"]
+            assert abs(r["energy"]["energy_error"]) < 2e-3, r["energy"]
+            segs.append(tr["segments"])
+        fields[track] = (segs, sim.engine.field_native("temp"), sim.engine.field_native("radenergydens"), sim.engine.field_native("energydep"))
+        del sim
+    a, b = fields[lib.TRACK_REFILL], fields[lib.TRACK_HISTORY]
+    assert a[0] == b[0]
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(x, y)

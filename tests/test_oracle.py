@@ -242,3 +242,34 @@ def test_engine_side_history_matches_per_step_downloads(oracle_lib, deck):
     eng.history_enable(0)
     sim.advance()
     assert eng.history_count() == (0, 0)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (9, 1), (3, 5)])
+def test_degenerate_2d_meshes_conserve_energy(oracle_lib, shape):
+    """1 x 1, 1 x N, N x 1 meshes with every boundary REFLECT / VACUUM: the step runs, every history ends in exactly one
+    outcome and the Float64 energy balance closes (imc_energycheck.jl:34)."""
+    for bcs in (("REFLECT",) * 4, ("VACUUM",) * 4):
+        d = decks.small_2d(precision="FLOAT64", n_input=400, bcs=bcs)
+        d["XMESHNODES"] = np.linspace(0.0, 1.0, shape[0] + 1).round(10)
+        d["YMESHNODES"] = np.linspace(0.0, 2.0, shape[1] + 1).round(10)
+        d["RADSOURCE_VALS"] = ["0.0"]   # with a radiation source the reference's 2-D emission loop breaks conservation (Q6)
+        sim = driver.setup(d, oracle_lib)
+        sim.save_history = False
+        for _ in range(3):
+            r = sim.advance()
+            tr = r["transport"]
+            assert tr["histories"] == tr["n_census"] + tr["n_absorbed"] + tr["n_escaped"] and tr["n_errors"] == 0
+            assert abs(r["energy"]["energy_error"]) < 1e-10
+            assert (tr["n_escaped"] > 0) == (bcs[0] == "VACUUM")
+
+
+def test_empty_population_on_the_oracle(oracle_lib):
+    sim = driver.setup(decks.small_2d(precision="FLOAT32", n_input=100), oracle_lib)
+    eng = sim.engine
+    eng.update(float(sim.simvars.dt))
+    eng.set_particles(np.zeros((0, eng.nslots)))
+    tr = eng.transport(float(sim.simvars.dt), 0)
+    assert tr["segments"] == 0 and tr["histories"] == 0
+    assert eng.clean() == 0
+    eng.tally(0.0, float(sim.simvars.dt))
+    assert np.all(eng.field("radenergydens") == 0)
