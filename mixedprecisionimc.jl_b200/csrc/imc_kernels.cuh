@@ -1250,7 +1250,11 @@ __global__ void k_compact(Parts<P> src, Parts<P> dst, long long n, int geom, con
 // ======================================================================================
 // Tally.tally
 // ======================================================================================
-// census radiation energy density: E / (dx [*dy] * scale) per surviving particle (imc_tally.jl:92, :106)
+// census radiation energy density: E / (dx [*dy] * scale) per surviving particle (imc_tally.jl:92, :106).
+// The particle list is close to cell order (new particles are emitted cell by cell, compaction is stable), so the
+// lanes of a warp mostly hold the same cell: runs of consecutive lanes with equal cells are summed with a segmented
+// shuffle scan and the last lane of each run issues the one atomic (Float64 sums in ATOMIC mode, exact integer sums in
+// FIXED mode — both order-free to the tolerance / exactly, like the per-lane atomics they replace).
 template <class P>
 __global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Parts<P> p, long long n, TallyArgs ta) {
   using N = Num<P>;
@@ -1258,12 +1262,54 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Pa
   Tally<P> tal(ta, smem);
   tal.zero();
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    if (!particle_alive(p, i, m.geom)) { if (ta.mode == IMC_TALLY_EXACT) { ta.rec_key[i] = 0x7fffffffu; ta.rec_val[i] = 0.0; } continue; }
-    N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
-    int cx = p.cx[i];
-    if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale), i);
-    else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale), i); }
+  const long long n_round = (n + 31) & ~31ll;
+  const int lane = threadIdx.x & 31;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool alive = i < n && particle_alive(p, i, m.geom);
+    if (ta.mode == IMC_TALLY_EXACT) {   // one record per particle, in particle order (Q19)
+      if (i < n) {
+        if (!alive) { ta.rec_key[i] = 0x7fffffffu; ta.rec_val[i] = 0.0; }
+        else {
+          N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
+          int cx = p.cx[i];
+          if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale), i);
+          else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale), i); }
+        }
+      }
+      continue;
+    }
+    int cell = -1;
+    double v = 0.0; long long q = 0;
+    if (alive) {
+      N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
+      int cx = p.cx[i];
+      N d;
+      if (m.geom == 1) { cell = cx; d = E / (N::load(m.dx, cx) * scale); }
+      else { int cy = p.cy[i]; cell = cx + m.nx * cy; d = E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale); }
+      v = d.d();
+      if (ta.mode == IMC_TALLY_FIXED) q = __double2ll_rn(v * ta.fx_mul);
+    }
+    // runs of equal cells: head = first lane of a run; segmented inclusive scan from the head
+    const int prev = __shfl_up_sync(IMC_FULL_MASK, cell, 1);
+    const unsigned heads = __ballot_sync(IMC_FULL_MASK, lane == 0 || prev != cell);
+    const int head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    if (ta.mode == IMC_TALLY_FIXED) {
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) { const long long tq = __shfl_up_sync(IMC_FULL_MASK, q, dlt); if (lane - dlt >= head) q += tq; }
+    } else {
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) { const double tv = __shfl_up_sync(IMC_FULL_MASK, v, dlt); if (lane - dlt >= head) v += tv; }
+    }
+    if (tail && cell >= 0) {
+      if (ta.mode == IMC_TALLY_FIXED) {
+        if (ta.use_smem) atomicAdd(&tal.s_fx[cell], (unsigned long long)q);
+        else atomicAdd(reinterpret_cast<unsigned long long*>(ta.g_fx) + cell, (unsigned long long)q);
+      } else {
+        if (ta.use_smem) atomicAdd(&tal.s_acc[cell], (typename AccType<P>::type)v);
+        else atomicAdd(ta.g_acc + cell, v);
+      }
+    }
   }
   tal.flush();
 }
