@@ -25,6 +25,12 @@ namespace imc {
 #ifndef IMC_EARLY_NEXT_CELL
 #define IMC_EARLY_NEXT_CELL 1   // MC2D: request the next cell's constants as soon as the event is known (0: in the face branch)
 #endif
+#ifndef IMC_CELL_GATHER_CG
+#define IMC_CELL_GATHER_CG 1    // MC2D: gather the per-cell constants through L2 only (0: default caching in L1)
+#endif
+#ifndef IMC_DEBUG_TALLY
+#define IMC_DEBUG_TALLY 0
+#endif
 #ifndef IMC_TRACK_MIN_BLOCKS
 #define IMC_TRACK_MIN_BLOCKS 4
 #endif
@@ -46,11 +52,15 @@ template <class P> struct alignas(2 * sizeof(typename P::store_t)) AxisProp { ty
 // so that the gathers do not evict the small per-axis tables and the particle stream from L1.
 template <class P>
 __device__ __forceinline__ CellProp2<P> load_cell2(const CellProp2<P>* tab, int c) {
+#if IMC_CELL_GATHER_CG
   CellProp2<P> r;
   if constexpr (P::id == 0) { const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(tab) + c); r.sig_col = (uint16_t)(v & 0xffffu); r.neg_saf = (uint16_t)(v >> 16); }
   else if constexpr (P::id == 1) { const float2 v = __ldcg(reinterpret_cast<const float2*>(tab) + c); r.sig_col = v.x; r.neg_saf = v.y; }
   else { const double2 v = __ldcg(reinterpret_cast<const double2*>(tab) + c); r.sig_col = v.x; r.neg_saf = v.y; }
   return r;
+#else
+  return tab[c];
+#endif
 }
 
 // a / b for a divisor whose refined reciprocal r is cached (imc_fastdiv.cuh): Float16 / Float32 only — Float16 divides in
@@ -546,7 +556,13 @@ struct Tally {
       else atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + idx, (unsigned long long)q);
     } else {
       if (K::smem(a)) atomicAdd(&s_acc[idx], (A)v.v);
+#if IMC_DEBUG_TALLY == 1      /* measurement only: no deposit */
+      else if (v.v == (typename P::comp_t)123456.0f) atomicAdd(a.g_acc + idx, v.d());
+#elif IMC_DEBUG_TALLY == 2    /* measurement only: Float32 atomics on the same buffer */
+      else atomicAdd(reinterpret_cast<float*>(a.g_acc) + 2 * idx, (float)v.v);
+#else
       else atomicAdd(a.g_acc + idx, v.d());
+#endif
     }
   }
   __device__ __forceinline__ void flush() {
