@@ -125,6 +125,28 @@ def traffic_from_profile(workload, mesh, particles):
     return None
 
 
+def tally_rel_err(w, mesh, sample_particles: int, glib, tally_mode, device: int):
+    """BASELINE.json's second metric, "tally rel. err vs reference": one time step of the same bounded sample on the
+    engine (the bench's tally mode) and on the oracle, from identical state and with identical draws — the particles
+    are then bit-identical, so the difference of the tallied fields is the engine's summation order (atomics) and its
+    reciprocal-form deposits.  Relative L2 error per field, and the Float64 energy-balance residual of each side."""
+    import __graft_entry__ as entry
+    from mpimc_b200 import driver, lib
+    olib = lib.ImcLib(entry.ORACLE_LIB)
+    inputs = make_inputs(w, sample_particles, mesh)
+    a = driver.setup(inputs, glib, device=device, tally_mode=tally_mode)
+    b = driver.setup(inputs, olib)
+    a.save_history = b.save_history = False
+    ra, rb = a.advance(), b.advance()
+    out = {"sample": f"1 step, {sample_particles} particles (NMAX), mesh {'x'.join(map(str, mesh))}, same seed on both sides",
+           "segments_equal": ra["transport"]["segments"] == rb["transport"]["segments"]}
+    for name in ("energydep", "radenergydens", "matenergydens", "temp"):
+        fa, fb = a.engine.field(name).astype(np.float64), b.engine.field(name).astype(np.float64)
+        out[name] = float(np.linalg.norm(fa - fb) / max(np.linalg.norm(fb), 1e-300))
+    out["energy_error_engine"], out["energy_error_reference_port"] = ra["energy"]["energy_error"], rb["energy"]["energy_error"]
+    return out
+
+
 def cpu_port_run(w, mesh, sample_particles: int, steps: int, warmup: int):
     """Time the oracle (1 thread, like the reference) on a bounded sample of the workload."""
     import __graft_entry__ as entry
@@ -326,6 +348,10 @@ def main():
             line["cpu_baseline"] = {"value": seg_s, "unit": "segments/s", "cores": 1, "kind": "port",
                                     "sample": f"oracle (C++ restatement of the Julia reference, single-threaded like it) on {sample} particles, "
                                               f"mesh {'x'.join(map(str, cmesh))}, 2 steps after 1 warm-up: {cseg} segments in {dt:.1f} s"}
+            try:
+                line["tally_rel_err"] = tally_rel_err(w, cmesh, min(sample, 2_000_000), glib, tally_mode, local_rank)
+            except Exception as e:  # a reported metric, never a reason to lose the bench line
+                line["tally_rel_err"] = {"error": str(e)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
