@@ -260,6 +260,7 @@ struct SrcArrays {
   int* cnt;           // loop count per entry
   S* nrg;             // energy per particle of the entry
   S* q_em;            // emittedenergy ./ escale, [Nc x Ns], for the print at :75
+  int* big;           // [SRC_BIG_CAP] entries with more than SRC_BIG_COUNT particles, in no particular order
 };
 
 struct SrcScalars {   // written by k_src_total, read by k_src_counts and by the host
@@ -267,7 +268,10 @@ struct SrcScalars {   // written by k_src_total, read by k_src_counts and by the
   double nsrc;        // n_source as a T value
   double sums[8];
   int bad;
+  int n_big;         // entries that emit more than SRC_BIG_COUNT particles (listed in SrcArrays::big)
 };
+constexpr int SRC_BIG_COUNT = 16;
+constexpr int SRC_BIG_CAP = 1 << 20;
 
 template <class P>
 __global__ void k_src_energies(MeshDev<P> m, SrcArrays<P> s, SrcLayout L, typename P::comp_t dt_) {
@@ -357,6 +361,7 @@ __global__ void k_src_total(SrcArrays<P> s, SrcLayout L, const typename P::comp_
   }
   out->nsrc = nsrc;
   out->bad = 0;
+  out->n_big = 0;
 }
 
 template <class P>
@@ -414,15 +419,86 @@ __global__ void k_src_counts(MeshDev<P> m, SrcArrays<P> s, SrcLayout L, SrcScala
   }
   if (ks < 0) bad = 1;
   s.cnt[e] = (int)loops;
+  if (loops > SRC_BIG_COUNT) { const int k = atomicAdd(&sc->n_big, 1); if (k < SRC_BIG_CAP) s.big[k] = (int)e; }   // e < 2^31: nc < 2^30 (set_mesh)
   (cnt > 0 ? div_count(en, cnt) : N()).store(s.nrg, e);
   if (bad) atomicOr(&sc->bad, 1);
 }
 
+// One new particle: entry e of the source list (surfaces, body cells, radiation-source cells), global ordinal j in the
+// reference's emission order (particle id and Philox counter), slot o of the particle list.  Cell indices are 32-bit.
+template <class P>
+__device__ __forceinline__ void emit_one(const MeshDev<P>& m, const Parts<P>& p, const SrcArrays<P>& s, const SrcLayout& L, long long e,
+                                         long long j, long long o, typename P::comp_t dt_, const RngArgs& rng, unsigned long long* over_flag) {
+  using N = Num<P>;
+  N dt(dt_), ds(m.ds), one = N::from_d(1.0), two = N::from_i(2);
+  const double PI = 3.141592653589793;
+  unsigned long long id = ((unsigned long long)rng.step << 40) | (unsigned long long)j;
+  Draw<P> d; d.init(rng, id, STREAM_SOURCE, j);
+  N t, x, y, mu, nrg = N::load(s.nrg, e);
+  int cx = 0, cy = 0;
+  const int nsurf = (int)L.n_surf(), nc = (int)L.nc;
+  if (L.geom == 1) {
+    if (e < 2) {                                                                   // :161-189
+      bool left = e == 0;
+      cx = left ? 0 : nc - 1;
+      x = N::from_d(((left ? 0.01 : 0.99) * N::load(m.dx, cx).d()) * ds.d());
+      mu = MathDet::sqrt<P>(d.uniform());
+      if (!left) mu = -mu;
+      while (mu == N()) { mu = MathDet::sqrt<P>(d.uniform()); if (!left) mu = -mu; }
+      t = dt * d.uniform();
+    } else {                                                                       // :193-236
+      const int c = (int)(e - 2);
+      cx = c < nc ? c : c - nc;
+      x = (N::load(m.dx, cx) * d.uniform()) * ds;
+      mu = one - two * d.uniform();
+      while (mu == N()) mu = one - two * d.uniform();
+      t = dt * d.uniform();
+    }
+  } else {
+    if (e < nsurf) {                                                               // :265-323
+      int side; int i = (int)e;
+      if (i < L.nx) side = 0; else if ((i -= L.nx) < L.nx) side = 1; else if ((i -= L.nx) < L.ny) side = 2; else { i -= L.ny; side = 3; }
+      t = dt * d.uniform();
+      if (side == 0) {
+        cx = i; cy = 0;
+        x = (N::load(m.dx, i) * d.uniform()) * ds;
+        y = N::from_d((0.001 * N::load(m.dy, 0).d()) * ds.d());
+        mu = N::from_d(PI) * d.uniform();
+      } else if (side == 1) {
+        cx = i; cy = L.ny - 1;
+        x = (N::load(m.dx, i) * d.uniform()) * ds;
+        y = N::from_d((0.999 * N::load(m.dy, L.ny - 1).d()) * ds.d());
+        mu = N::from_d((-PI) * d.uniform().d());
+      } else {
+        cx = side == 2 ? 0 : L.nx - 1; cy = i;
+        x = N::from_d(((side == 2 ? 0.001 : 0.999) * N::load(m.dx, cx).d()) * ds.d());
+        N dq7 = i < L.nx ? N::load(m.dx, i) : N::load(m.dy, i);                    // Q7: mesh.dx[j]
+        y = (dq7 * d.uniform()) * ds;
+        double u = d.uniform().d();
+        mu = N::from_d(PI * (side == 2 ? 0.5 - u : 0.5 + u));
+      }
+    } else {                                                                       // :326-366
+      int c = (int)(e - nsurf);
+      if (c >= nc) c -= nc;
+      cy = c / L.nx; cx = c - cy * L.nx;
+      x = (N::load(m.dx, cx) * d.uniform()) * ds;
+      y = (N::load(m.dy, cy) * d.uniform()) * ds;
+      mu = N::from_d((2.0 * PI) * d.uniform().d());
+      t = dt * d.uniform();
+    }
+  }
+  t.store(p.t, o); x.store(p.x, o); mu.store(p.mu, o); nrg.store(p.E, o); nrg.store(p.E0, o);
+  p.cx[o] = cx; p.ks[o] = (unsigned char)(s.ks[e] < 0 ? 0 : s.ks[e]); p.id[o] = id;
+  if (L.geom == 2) { y.store(p.y, o); p.cy[o] = cy; } else p.origin[o] = cx;
+  if (d.over()) atomicAdd(over_flag, 1ull);
+}
+
+// thread per new particle: the entry is found by binary search in the scan of the counts (any count distribution,
+// e.g. the 1-D decks where one surface entry emits most of the particles)
 template <class P>
 __global__ void k_src_emit(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
                            long long base, long long n_local, int rank, int world, typename P::comp_t dt_,
                            RngArgs rng, unsigned long long* over_flag) {
-  using N = Num<P>;
   long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n_local) return;
   long long j = rank + l * (long long)world;  // global ordinal in the reference's emission order
@@ -432,66 +508,31 @@ __global__ void k_src_emit(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L
     long long mid = (lo + hi + 1) >> 1;
     if (offs[mid] <= j) lo = mid; else hi = mid - 1;
   }
-  long long e = lo;
-  N dt(dt_), ds(m.ds), one = N::from_d(1.0), two = N::from_i(2);
-  const double PI = 3.141592653589793;
-  unsigned long long id = ((unsigned long long)rng.step << 40) | (unsigned long long)j;
-  Draw<P> d; d.init(rng, id, STREAM_SOURCE, j);
-  N t, x, y, mu, nrg = N::load(s.nrg, e);
-  int cx = 0, cy = 0;
-  if (L.geom == 1) {
-    if (e < 2) {                                                                   // :161-189
-      bool left = e == 0;
-      cx = left ? 0 : (int)L.nc - 1;
-      x = N::from_d(((left ? 0.01 : 0.99) * N::load(m.dx, cx).d()) * ds.d());
-      mu = MathDet::sqrt<P>(d.uniform());
-      if (!left) mu = -mu;
-      while (mu == N()) { mu = MathDet::sqrt<P>(d.uniform()); if (!left) mu = -mu; }
-      t = dt * d.uniform();
-    } else {                                                                       // :193-236
-      cx = (int)((e - 2) % L.nc);
-      x = (N::load(m.dx, cx) * d.uniform()) * ds;
-      mu = one - two * d.uniform();
-      while (mu == N()) mu = one - two * d.uniform();
-      t = dt * d.uniform();
-    }
-  } else {
-    if (e < L.n_surf()) {                                                          // :265-323
-      int side; long long i = e;
-      if (i < L.nx) side = 0; else if ((i -= L.nx) < L.nx) side = 1; else if ((i -= L.nx) < L.ny) side = 2; else { i -= L.ny; side = 3; }
-      t = dt * d.uniform();
-      if (side == 0) {
-        cx = (int)i; cy = 0;
-        x = (N::load(m.dx, i) * d.uniform()) * ds;
-        y = N::from_d((0.001 * N::load(m.dy, 0).d()) * ds.d());
-        mu = N::from_d(PI) * d.uniform();
-      } else if (side == 1) {
-        cx = (int)i; cy = L.ny - 1;
-        x = (N::load(m.dx, i) * d.uniform()) * ds;
-        y = N::from_d((0.999 * N::load(m.dy, L.ny - 1).d()) * ds.d());
-        mu = N::from_d((-PI) * d.uniform().d());
-      } else {
-        cx = side == 2 ? 0 : L.nx - 1; cy = (int)i;
-        x = N::from_d(((side == 2 ? 0.001 : 0.999) * N::load(m.dx, cx).d()) * ds.d());
-        N dq7 = i < L.nx ? N::load(m.dx, i) : N::load(m.dy, i);                    // Q7: mesh.dx[j]
-        y = (dq7 * d.uniform()) * ds;
-        double u = d.uniform().d();
-        mu = N::from_d(PI * (side == 2 ? 0.5 - u : 0.5 + u));
-      }
-    } else {                                                                       // :326-366
-      long long c = (e - L.n_surf()) % L.nc;
-      cx = (int)(c % L.nx); cy = (int)(c / L.nx);
-      x = (N::load(m.dx, cx) * d.uniform()) * ds;
-      y = (N::load(m.dy, cy) * d.uniform()) * ds;
-      mu = N::from_d((2.0 * PI) * d.uniform().d());
-      t = dt * d.uniform();
-    }
-  }
-  long long o = base + l;
-  t.store(p.t, o); x.store(p.x, o); mu.store(p.mu, o); nrg.store(p.E, o); nrg.store(p.E0, o);
-  p.cx[o] = cx; p.ks[o] = (unsigned char)(s.ks[e] < 0 ? 0 : s.ks[e]); p.id[o] = id;
-  if (L.geom == 2) { y.store(p.y, o); p.cy[o] = cy; } else p.origin[o] = cx;
-  if (d.over()) atomicAdd(over_flag, 1ull);
+  emit_one(m, p, s, L, lo, j, base + l, dt_, rng, over_flag);
+}
+
+// thread per entry, looping over its few particles: no search, and the runs of adjacent entries are adjacent in the
+// particle list.  Entries with more than SRC_BIG_COUNT particles (hot cells, the surface entries of the 1-D decks) are
+// left to k_src_emit_big, one block per listed entry.  Rank r of `world` emits the ordinals j = r (mod world).
+template <class P>
+__global__ void k_src_emit_entries(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
+                                   long long total, long long base, int rank, int world, typename P::comp_t dt_, RngArgs rng,
+                                   unsigned long long* over_flag) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= L.total()) return;
+  const long long j0 = offs[e], j1 = e + 1 < L.total() ? offs[e + 1] : total;   // offs is the exclusive scan of the counts
+  if (j1 <= j0 || j1 - j0 > SRC_BIG_COUNT) return;
+  long long j = j0 + ((rank - j0 % world) + world) % world;   // first ordinal of this rank in [j0, j1)
+  for (; j < j1; j += world) emit_one(m, p, s, L, e, j, base + (j - rank) / world, dt_, rng, over_flag);
+}
+template <class P>
+__global__ void k_src_emit_big(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
+                               long long total, long long base, int rank, int world, typename P::comp_t dt_, RngArgs rng,
+                               unsigned long long* over_flag) {
+  const long long e = s.big[blockIdx.x];
+  const long long j0 = offs[e], j1 = e + 1 < L.total() ? offs[e + 1] : total;
+  long long j = j0 + ((rank - j0 % world) + world) % world + (long long)threadIdx.x * world;
+  for (; j < j1; j += (long long)blockDim.x * world) emit_one(m, p, s, L, e, j, base + (j - rank) / world, dt_, rng, over_flag);
 }
 
 // ======================================================================================
