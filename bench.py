@@ -337,7 +337,8 @@ def main():
                     "path": "imc_set_state_native (pinned Array{T} -> device) + the step + imc_get_field_native x3 (device -> pinned Array{T})"},
             "gpu_launches": launches, "schedule_per_step": variants,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_from_profile(args.workload, mesh, particles),
-                         "kernel": "k_track2d" if w["geom"] == 2 else ("k_track1d_rw" if w["deck"] == "marshak" else "k_track1d"),
+                         "kernel": ("k_track1d_rw" if w["deck"] == "marshak" else
+                                    {"refill": f"k_track_refill<{w['geom']}-D>", "static": f"k_track{w['geom']}d", "event": "k_track_event"}.get(variants[-1], "?")),
                          "bytes_per_segment": bps, "peak_source": peak_src},
             "clocks": sampler.summary(),
         }

@@ -597,7 +597,11 @@ struct EngineT : EngineBase {
       // IMC_AUTO_PROBE_EVENT=1: measured on B200 it is 17x (Su-Olson) to 40x (crooked pipe) slower, because the
       // last few long histories need thousands of nearly empty launches.
       static const bool probe_event = getenv("IMC_AUTO_PROBE_EVENT") && atoi(getenv("IMC_AUTO_PROBE_EVENT")) != 0;
-      long long phase = n_transport_calls % 32;
+      // the losing schedule is re-measured every 32 calls while it is within 30 % of the winner, every 256 calls otherwise
+      // (a lost probe costs one slow step: static is 1.7-2x slower than refill on the crooked pipe)
+      const bool close = rate_static > 0 && rate_refill > 0 && std::min(rate_static, rate_refill) > 0.7 * std::max(rate_static, rate_refill);
+      const long long period = (n_transport_calls < 2 || close) ? 32 : 256;
+      long long phase = n_transport_calls % period;
       if (phase == 0) variant = IMC_TRACK_HISTORY;
       else if (phase == 1) variant = IMC_TRACK_REFILL;
       else if (n_transport_calls == 2 && event_ok && probe_event) variant = IMC_TRACK_EVENT;
