@@ -11,7 +11,9 @@ the workload's particle population.  Workloads (synthetic decks from mixedprecis
                     quoted on (1e9 particles over 8 GPUs).
   crookedpipe_f64   BASELINE config 3 (1024 x 1024, Float64, 1e8 particles).
   marshak_f32_rw    BASELINE config 2 (Marshak 1-D Float32, 2048 graded cells, RANDOMWALK, 1e7 particles).
-  suolson_f32       Su-Olson 1-D Float32 scaled to 1e8 particles (config 4 family).
+  suolson_f32       Su-Olson 1-D Float32 scaled to 1e8 particles (config 4 family); suolson_f16 / suolson_f64: its
+                    Float16 (ENERGYSCALES 32768, counts kept as integers: Q10) and Float64 members.
+  crookedpipe_f16   CrookedPipe 2-D Float16 (ENERGYSCALES 1024) on the 1024 x 1024 mesh.
 
 `value`  = whole-job segments/s with everything resident in HBM (all stages of the step timed).
 `e2e`    = the same through the host-buffer path a stateless drop-in shim uses: every step uploads the
@@ -44,6 +46,9 @@ WORKLOADS = {
     "crookedpipe_f64": dict(deck="crooked_pipe", precision="FLOAT64", mesh=(1024, 1024), particles=100_000_000, geom=2, s=8),
     "marshak_f32_rw": dict(deck="marshak", precision="FLOAT32", mesh=(2048,), particles=10_000_000, geom=1, s=4),
     "suolson_f32": dict(deck="suolson", precision="FLOAT32", mesh=(1000,), particles=100_000_000, geom=1, s=4),
+    "suolson_f16": dict(deck="suolson", precision="FLOAT16", mesh=(1000,), particles=100_000_000, geom=1, s=2),
+    "suolson_f64": dict(deck="suolson", precision="FLOAT64", mesh=(1000,), particles=100_000_000, geom=1, s=8),
+    "crookedpipe_f16": dict(deck="crooked_pipe", precision="FLOAT16", mesh=(1024, 1024), particles=100_000_000, geom=2, s=2),
 }
 
 
@@ -54,8 +59,9 @@ def make_inputs(w: dict, particles: int, mesh, world: int = 1):
     if w["deck"] == "crooked_pipe":
         # CELLMIN (every cell emits at least that many particles per step, Q9) grows with the GPU count so that the
         # per-GPU work stays fixed under weak scaling
+        es = dict(energyscales=(1024.0,)) if w["precision"] == "FLOAT16" else {}
         return decks.crooked_pipe(precision=w["precision"], n_input=n_input, n_max=n_max, cellmin=max(1, world),
-                                  mesh_cells=mesh, pairwise="FALSE")
+                                  mesh_cells=mesh, pairwise="FALSE", **es)
     if w["deck"] == "marshak":
         return decks.marshak(precision=w["precision"], n_cells=mesh[0], nonuniform=True, randomwalk="TRUE", n_input=n_input,
                              n_max=n_max, cellmin=5, pairwise="FALSE")

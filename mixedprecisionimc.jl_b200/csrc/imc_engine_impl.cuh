@@ -113,7 +113,8 @@ struct EngineT : EngineBase {
   DBuf<int> rec_cnt;
   DBuf<long long> rec_off, rec_start;
   DBuf<unsigned> rec_key[2];
-  DBuf<double> rec_val[2], lost_val, lost_scratch;
+  DBuf<double> rec_val[2], lost_val, lost_scratch, lost_cval;
+  DBuf<unsigned char> lost_cks;
   DBuf<unsigned char> sort_temp;
   int last_mode = IMC_TALLY_ATOMIC;
   // event-based schedule
@@ -493,6 +494,14 @@ struct EngineT : EngineBase {
     }
     k_exact_bounds<<<grid_for(nacc + 1, 256), 256, 0, stream>>>(rec_key[1].p, R, nacc, rec_start.p); ++n_launch;
     k_exact_reduce<P><<<grid_for(nacc, 128), 128, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, pairwise, out); ++n_launch;
+    if (R >= EXACT_WARP_MIN) {   // cells with many records: a warp per cell, same order of additions
+      unsigned grid = (unsigned)std::min<long long>((nacc * 32 + 255) / 256, (long long)sm_count * 8);
+      k_exact_reduce_warp<P><<<grid, 256, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, pairwise, out); ++n_launch;
+    }
+    if (pairwise && R >= EXACT_BLOCK_MIN) {   // very long pairwise segments: a block per cell, leaves in parallel
+      unsigned grid = (unsigned)std::min<long long>(nacc, (long long)sm_count * 2);
+      k_exact_reduce_block<P><<<grid, EXACT_BLOCK_THREADS, 0, stream>>>(rec_val[1].p, rec_start.p, nacc, out); ++n_launch;
+    }
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
@@ -630,7 +639,6 @@ struct EngineT : EngineBase {
       if (mode == IMC_TALLY_EXACT) {
         // pass 1: count the deposits of every particle (no side effects), scan -> record offsets
         IMC_CK(rec_cnt.ensure((size_t)n_part)); IMC_CK(rec_off.ensure((size_t)n_part + 1)); IMC_CK(lost_val.ensure((size_t)n_part));
-        IMC_CK(lost_scratch.ensure((size_t)n_part));
         a.tally.pass = 1; a.tally.rec_cnt = rec_cnt.p;
         IMC_RC(launch_track(a, variant, grid, smem));
         IMC_RC(scan_counts(rec_cnt.p, rec_off.p, n_part));
@@ -652,7 +660,17 @@ struct EngineT : EngineBase {
           a.tally.pass = 2; a.tally.rec_off = rec_off.p; a.tally.rec_key = rec_key[0].p; a.tally.rec_val = rec_val[0].p; a.tally.lost_val = lost_val.p;
           IMC_RC(launch_track(a, variant, grid, smem));
           IMC_RC(exact_reduce_records(R, nc * ns, cfg.pairwise, red.p + rb_dep0()));
-          k_exact_lost<P><<<1, 1, 0, stream>>>(lost_val.p, pb[cur].view().ks, n_part, m, cfg.pairwise, lost_scratch.p, red.p + rb_sc0() + RB_LOST); ++n_launch;
+          // vacuum losses: compact the per-particle slots in order, then add them as the reference's loop does
+          k_lost_flags<<<grid_for(n_part, 256), 256, 0, stream>>>(lost_val.p, n_part, rec_cnt.p); ++n_launch;
+          IMC_RC(scan_counts(rec_cnt.p, rec_off.p, n_part));
+          long long n_lost = 0;
+          IMC_CK(cudaMemcpyAsync(&n_lost, scan_total.p, sizeof n_lost, cudaMemcpyDeviceToHost, stream));
+          IMC_CK(cudaStreamSynchronize(stream));
+          if (n_lost > 0) {
+            IMC_CK(lost_cval.ensure((size_t)n_lost)); IMC_CK(lost_cks.ensure((size_t)n_lost)); IMC_CK(lost_scratch.ensure((size_t)n_lost));
+            k_lost_gather<<<grid_for(n_part, 256), 256, 0, stream>>>(lost_val.p, pb[cur].view().ks, rec_off.p, n_part, lost_cval.p, lost_cks.p); ++n_launch;
+            k_exact_lost<P><<<1, 1, 0, stream>>>(lost_cval.p, lost_cks.p, n_lost, m, cfg.pairwise, lost_scratch.p, red.p + rb_sc0() + RB_LOST); ++n_launch;
+          }
           IMC_CK(cudaGetLastError());
         }
       } else {

@@ -1413,6 +1413,127 @@ __device__ Num<P> jl_sum_serial(const double* __restrict__ vals, long long first
   }
   return ret;
 }
+// ---- the same two reductions by a whole warp, for cells with many records (1-D decks at scale: 10^4-10^5 deposits per
+// cell).  The additions keep the reference's order — they are a dependent chain — but the records are read 32 at a time,
+// coalesced, and handed to the chain by shuffles; every lane carries the same accumulator.
+constexpr int EXACT_WARP_MIN = 64;   // segments at least this long go to k_exact_reduce_warp
+__device__ __forceinline__ bool exact_block_segment(long long len, int pairwise);   // ... or, pairwise and very long, to k_exact_reduce_block
+// v (op)= vals[first..last] in order; `started` = v already holds a value (else v = vals[first] first).  wide records (bit 31 of
+// the key, MC_RW) are Float64 values added in Float64 and rounded; keys == nullptr: no wide records (census, pairwise leaves)
+template <class P>
+__device__ __forceinline__ Num<P> warp_seq_add(Num<P> v, bool started, const unsigned* __restrict__ keys, const double* __restrict__ vals,
+                                               long long first, long long last, int lane) {
+  using N = Num<P>;
+  for (long long base = first; base <= last; base += 32) {
+    const long long i = base + lane;
+    double x = 0.0; unsigned k = 0u;
+    if (i <= last) { x = vals[i]; if (keys) k = keys[i]; }
+    const int cnt = (int)(last - base + 1 < 32 ? last - base + 1 : 32);
+#pragma unroll 8
+    for (int j = 0; j < cnt; ++j) {
+      const double xj = __shfl_sync(IMC_FULL_MASK, x, j);
+      const unsigned kj = keys ? __shfl_sync(IMC_FULL_MASK, k, j) : 0u;
+      if (!started) { v = (kj & 0x80000000u) ? N::from_d(N().d() + xj) : N() + N::from_d(xj); started = true; }
+      else v = (kj & 0x80000000u) ? N::from_d(v.d() + xj) : v + N::from_d(xj);
+    }
+  }
+  return v;
+}
+// Julia Base.sum of vals[first..last] (jl_sum_serial's recursion, leaves summed by warp_seq_add); all lanes return the value
+template <class P>
+__device__ Num<P> warp_jl_sum(const double* __restrict__ vals, long long first, long long last, int lane) {
+  using N = Num<P>;
+  struct Frame { long long first, last; int state; N v1; };
+  Frame st[48];
+  int sp = 0;
+  st[sp++] = {first, last, 0, N()};
+  N ret;
+  while (sp > 0) {
+    Frame& f = st[sp - 1];
+    if (f.state == 0) {
+      if (f.last - f.first < 1024) {   // one element, or a sequential leaf: v = A[first] + A[first+1]; v += A[i] ...
+        const double x0 = vals[f.first];
+        ret = f.first == f.last ? N::from_d(x0) : warp_seq_add<P>(N::from_d(x0), true, nullptr, vals, f.first + 1, f.last, lane);
+        --sp;
+      } else {
+        long long mid = f.first + ((f.last - f.first) >> 1);
+        f.state = 1;
+        st[sp++] = {f.first, mid, 0, N()};
+      }
+    } else if (f.state == 1) {
+      f.v1 = ret; f.state = 2;
+      long long mid = f.first + ((f.last - f.first) >> 1);
+      st[sp++] = {mid + 1, f.last, 0, N()};
+    } else { ret = f.v1 + ret; --sp; }
+  }
+  return ret;
+}
+template <class P>
+__global__ void k_exact_reduce_warp(const unsigned* __restrict__ keys, const double* __restrict__ vals, const long long* __restrict__ start,
+                                    long long nacc, int pairwise, double* __restrict__ out) {
+  using N = Num<P>;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nacc; c += nwarps) {
+    const long long b = start[c], e = start[c + 1];
+    if (e - b < EXACT_WARP_MIN || exact_block_segment(e - b, pairwise)) continue;
+    N v;
+    if (pairwise) v = warp_jl_sum<P>(vals, b, e - 1, lane);
+    else v = warp_seq_add<P>(N(), true, keys, vals, b, e - 1, lane);   // v = zero(T); v += record ... (imc_transport.jl:101, :120)
+    if (lane == 0) out[c] = v.d();
+  }
+}
+// Julia's pairwise sum of a very long segment by a whole block: the recursion's leaves (< 1024 elements each, all on two
+// adjacent depths: see k_jlsum_leaves) are independent, so the warps of the block sum them concurrently, each leaf in
+// order (warp_seq_add); the tree is then folded bottom-up in shared memory exactly as the recursion combines it.
+constexpr int EXACT_BLOCK_MIN = 8192;        // pairwise segments at least this long go to k_exact_reduce_block ...
+constexpr int EXACT_BLOCK_MAX_DEPTH = 12;    // ... while their tree has at most 2^12 leaf slots (4 Mi records)
+constexpr int EXACT_BLOCK_THREADS = 1024;
+__device__ __forceinline__ int jl_sum_depth_dev(long long n) { int d = 0; while (n > 1024) { n = (n + 1) / 2; ++d; } return d; }
+__device__ __forceinline__ bool exact_block_segment(long long len, int pairwise) {
+  return pairwise && len >= EXACT_BLOCK_MIN && jl_sum_depth_dev(len) <= EXACT_BLOCK_MAX_DEPTH;
+}
+template <class P>
+__global__ void __launch_bounds__(EXACT_BLOCK_THREADS) k_exact_reduce_block(const double* __restrict__ vals, const long long* __restrict__ start,
+                                                                           long long nacc, double* __restrict__ out) {
+  using N = Num<P>;
+  __shared__ typename P::comp_t part[1 << EXACT_BLOCK_MAX_DEPTH];
+  __shared__ unsigned char valid[1 << EXACT_BLOCK_MAX_DEPTH];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (long long c = blockIdx.x; c < nacc; c += gridDim.x) {
+    const long long b = start[c], len = start[c + 1] - b;
+    if (!exact_block_segment(len, 1)) continue;
+    const int depth = jl_sum_depth_dev(len);
+    const int slots = 1 << depth;
+    for (int slot = wid; slot < slots; slot += nw) {     // walk from the root to this slot's leaf (uniform in the warp)
+      long long first = 0, last = len - 1;
+      int d = 0; bool mine = true;
+      while (last - first >= 1024) {
+        const long long mid = first + ((last - first) >> 1);
+        if ((slot >> (depth - 1 - d)) & 1) first = mid + 1; else last = mid;
+        ++d;
+      }
+      if (d < depth && (slot & ((1 << (depth - d)) - 1)) != 0) mine = false;   // a shallower leaf belongs to its leftmost slot
+      if (mine) {
+        const double x0 = vals[b + first];
+        const N v = first == last ? N::from_d(x0) : warp_seq_add<P>(N::from_d(x0), true, nullptr, vals, b + first + 1, b + last, lane);
+        if (lane == 0) part[slot] = v.v;
+      }
+      if (lane == 0) valid[slot] = mine ? 1 : 0;
+    }
+    __syncthreads();
+    for (int level = depth; level >= 1; --level) {         // k_jlsum_fold
+      const int nodes = 1 << (level - 1), sh = depth - level;
+      for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
+        const int ls = (2 * i) << sh, rs = (2 * i + 1) << sh;
+        if (valid[rs]) part[ls] = (N(part[ls]) + N(part[rs])).v;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = (double)part[0];
+    __syncthreads();
+  }
+}
 // one thread per tally cell: PAIRWISE = FALSE -> `+=` in record order (imc_transport.jl:101,120); TRUE -> sum(vector) (:202)
 template <class P>
 __global__ void k_exact_reduce(const unsigned* __restrict__ keys, const double* __restrict__ vals, const long long* __restrict__ start,
@@ -1421,6 +1542,7 @@ __global__ void k_exact_reduce(const unsigned* __restrict__ keys, const double* 
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nacc) return;
   long long b = start[c], e = start[c + 1];
+  if (e - b >= EXACT_WARP_MIN) return;   // long segments: k_exact_reduce_warp
   N v;
   if (e > b) {
     if (pairwise) v = jl_sum_serial<P>(vals, b, e - 1);
@@ -1431,7 +1553,20 @@ __global__ void k_exact_reduce(const unsigned* __restrict__ keys, const double* 
   }
   out[c] = v.d();
 }
-// lost energy in particle order (imc_transport.jl:141 / :200), one thread
+// lost energy in particle order (imc_transport.jl:141 / :200).  The per-particle slots (NaN = no loss) are first
+// compacted in order (k_lost_flags, scan, k_lost_gather) — escapes are few next to the population — and one thread
+// then adds the compacted values exactly as the reference's loop does.
+static __global__ void k_lost_flags(const double* __restrict__ lost_val, long long n, int* __restrict__ flag) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const double e = lost_val[i]; flag[i] = e == e ? 1 : 0; }
+}
+static __global__ void k_lost_gather(const double* __restrict__ lost_val, const unsigned char* __restrict__ ks, const long long* __restrict__ offs,
+                                     long long n, double* __restrict__ cval, unsigned char* __restrict__ cks) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double e = lost_val[i];
+  if (e == e) { cval[offs[i]] = e; cks[offs[i]] = ks[i]; }
+}
 template <class P>
 __global__ void k_exact_lost(const double* __restrict__ lost_val, const unsigned char* __restrict__ ks, long long n, MeshDev<P> m,
                              int pairwise, double* __restrict__ scratch, double* __restrict__ lost_io) {

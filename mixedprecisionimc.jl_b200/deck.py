@@ -28,7 +28,8 @@ def parse_T(T, s) -> Any:
     if isinstance(s, (bytes, str)):
         s = s.strip()
     if T is np.float16:
-        return np.float16(np.float32(s))
+        with np.errstate(over="ignore"):   # parse(Float16, "100000") is Inf16 in Julia too
+            return np.float16(np.float32(s))
     return T(s)
 
 

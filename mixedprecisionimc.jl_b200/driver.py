@@ -20,6 +20,20 @@ from . import lib as _lib
 from .deck import MeshStruct, parse_T, tointeger
 
 
+def parse_count(T, text) -> int:
+    """NINPUT / NMAX.  The reference parses them through the deck precision (MixedPrecisionIMC.jl:107-110), so a Float16
+    deck cannot say more than 65504 (Q10).  The engine keeps counts as integers; a count a Float16 deck cannot represent
+    is therefore taken as the integer written in the deck — the intentional divergence BASELINE configs 4-5 need
+     — while every representable count goes through T exactly like the reference."""
+    v = parse_T(T, text)
+    if np.dtype(T) == np.dtype(np.float16) and not np.isfinite(float(v)):
+        x = float(text)
+        if x != int(x):
+            raise ValueError(f"InexactError: {text!r} is not an integer")
+        return int(x)
+    return tointeger(v)
+
+
 @dataclass
 class SimVars:
     """``SimVars`` (MixedPrecisionIMC.jl:35-51)."""
@@ -77,7 +91,7 @@ def make_config(inputs, mesh: MeshStruct, **overrides) -> _lib.Config:
         if s not in _BC:
             raise ValueError(f"{nm} = {s}: the transport loop only handles REFLECT and VACUUM")
         bc[i] = _BC[s]
-    n_max = tointeger(parse_T(T, inputs["NMAX"]))
+    n_max = parse_count(T, inputs["NMAX"])
     cfg = _lib.Config(
         precision=_lib.PRECISION_IDS[np.dtype(T)], geometry=geom, nx=mesh.nx, ny=mesh.ny, bc=bc,
         linearized=str(inputs["LINEARIZED"]).upper() == "TRUE",
@@ -224,8 +238,8 @@ def make_simvars(inputs, mesh: MeshStruct) -> SimVars:
         t_end = parse_T(T, inputs["ENDTIME"]); dt = dt0
     else:
         raise ValueError(f"TIMESTEPPING = {ts}")
-    n_input = tointeger(parse_T(T, inputs["NINPUT"]))
-    n_max = tointeger(parse_T(T, inputs["NMAX"]))
+    n_input = parse_count(T, inputs["NINPUT"])
+    n_max = parse_count(T, inputs["NMAX"])
     cellmin = parse_T(T, inputs["CELLMIN"])
     if mesh.geometry == "1D":
         BC = (str(inputs["LEFTBC"]).upper(), str(inputs["RIGHTBC"]).upper())

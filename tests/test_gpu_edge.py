@@ -113,3 +113,16 @@ def test_full_size_crooked_pipe_properties(gpu_lib):
     assert a[0] == b[0]
     for x, y in zip(a[1:], b[1:]):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("deck", ["suolson", "crooked"])
+def test_float16_deck_with_counts_beyond_float16(gpu_lib, oracle_lib, deck):
+    """Q10: NINPUT / NMAX above 65504 in a Float16 deck (BASELINE config 4): counts are integers in the engine and the
+    per-cell count arithmetic runs in Float32; the engine and the oracle still agree particle for particle."""
+    if deck == "suolson":
+        inputs = decks.suolson(precision="FLOAT16", n_input=100000, n_max=200000)
+    else:
+        inputs = decks.crooked_pipe(precision="FLOAT16", n_input=100000, n_max=200000, cellmin=1, energyscales=(1024.0,))
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=3, precision="FLOAT16")
+    assert_step_parity(a, b, out, "FLOAT16")
+    assert out[-1][0]["source"]["n_particles"] > 65504

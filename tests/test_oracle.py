@@ -273,3 +273,15 @@ def test_empty_population_on_the_oracle(oracle_lib):
     assert eng.clean() == 0
     eng.tally(0.0, float(sim.simvars.dt))
     assert np.all(eng.field("radenergydens") == 0)
+
+
+def test_float16_counts_beyond_float16_range(oracle_lib):
+    """Q10: a Float16 deck may ask for more particles than Float16 can count; counts below that go through T exactly
+    like the reference (2049 -> 2048), counts above are the integers written in the deck."""
+    assert driver.parse_count(np.float16, "2049") == 2048
+    assert driver.parse_count(np.float16, "100000") == 100000
+    assert driver.parse_count(np.float32, "16777217") == 16777216
+    sim = driver.setup(decks.suolson(precision="FLOAT16", n_input=100000, n_max=200000), oracle_lib)
+    sim.save_history = False
+    r = sim.advance()
+    assert r["source"]["n_particles"] > 65504 and r["transport"]["n_errors"] == 0
