@@ -36,7 +36,9 @@ struct DBuf {
     n = count;
     return zero ? cudaMemset(p, 0, count * sizeof(T)) : cudaSuccess;
   }
-  cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count, false); }
+  // scratch that follows the population (records, flags, scans): grow by at least a quarter, so that a population creeping
+  // upward does not pay a cudaFree + cudaMalloc (and its device synchronisation) every time step
+  cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count > n + n / 4 ? count : n + n / 4, false); }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   ~DBuf() { release(); }
   DBuf() = default;
