@@ -13,7 +13,6 @@ the workload's particle population.  Workloads (synthetic decks from mixedprecis
   marshak_f32_rw    BASELINE config 2 (Marshak 1-D Float32, 2048 graded cells, RANDOMWALK, 1e7 particles).
   suolson_f32       Su-Olson 1-D Float32 scaled to 1e8 particles (config 4 family); suolson_f16 / suolson_f64: its
                     Float16 (ENERGYSCALES 32768, counts kept as integers: Q10) and Float64 members.
-  crookedpipe_f16   CrookedPipe 2-D Float16 (ENERGYSCALES 1024) on the 1024 x 1024 mesh.
 
 `value`  = whole-job segments/s with everything resident in HBM (all stages of the step timed).
 `e2e`    = the same through the host-buffer path a stateless drop-in shim uses: every step uploads the
@@ -48,7 +47,6 @@ WORKLOADS = {
     "suolson_f32": dict(deck="suolson", precision="FLOAT32", mesh=(1000,), particles=100_000_000, geom=1, s=4),
     "suolson_f16": dict(deck="suolson", precision="FLOAT16", mesh=(1000,), particles=100_000_000, geom=1, s=2),
     "suolson_f64": dict(deck="suolson", precision="FLOAT64", mesh=(1000,), particles=100_000_000, geom=1, s=8),
-    "crookedpipe_f16": dict(deck="crooked_pipe", precision="FLOAT16", mesh=(1024, 1024), particles=100_000_000, geom=2, s=2),
 }
 
 

@@ -98,7 +98,7 @@ struct EngineT : EngineBase {
   SrcLayout L;
   DBuf<S> src_e, src_q, src_nrg, src_qem;
   DBuf<signed char> src_ks;
-  DBuf<int> src_cnt, src_big;
+  DBuf<int> src_cnt;
   DBuf<long long> src_offs, scan_tiles, scan_tiles2, scan_total;
   DBuf<SrcScalars> src_sc;
   DBuf<Cc> sums;  // device slots for jl_sum results
@@ -292,7 +292,7 @@ struct EngineT : EngineBase {
     IMC_CK(red.alloc(red_n));
     // sourcing / tally scratch
     long long M = L.total();
-    IMC_CK(src_e.alloc(M)); IMC_CK(src_q.alloc(M)); IMC_CK(src_nrg.alloc(M)); IMC_CK(src_ks.alloc(M)); IMC_CK(src_cnt.alloc(M)); IMC_CK(src_big.alloc(SRC_BIG_CAP));
+    IMC_CK(src_e.alloc(M)); IMC_CK(src_q.alloc(M)); IMC_CK(src_nrg.alloc(M)); IMC_CK(src_ks.alloc(M)); IMC_CK(src_cnt.alloc(M));
     IMC_CK(src_offs.alloc(M + 1)); IMC_CK(src_qem.alloc(nc * ns)); IMC_CK(src_sc.alloc(1)); IMC_CK(sums.alloc(16));
     IMC_CK(q_dep.alloc(nc * ns)); IMC_CK(q_tot.alloc(nc)); IMC_CK(q_rad.alloc(nc));
     IMC_CK(d_max.alloc(2)); IMC_CK(d_flag.alloc(2)); IMC_CK(over_flag.alloc(2));
@@ -369,7 +369,7 @@ struct EngineT : EngineBase {
     if (!have_mesh) { err = "source before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     Cc dt = P::from_d(dt_), cellmin = P::from_d(cellmin_);
-    SrcArrays<P> s; s.e = src_e.p; s.q = src_q.p; s.ks = src_ks.p; s.cnt = src_cnt.p; s.nrg = src_nrg.p; s.q_em = src_qem.p; s.big = src_big.p;
+    SrcArrays<P> s; s.e = src_e.p; s.q = src_q.p; s.ks = src_ks.p; s.cnt = src_cnt.p; s.nrg = src_nrg.p; s.q_em = src_qem.p;
     k_src_energies<P><<<grid_for(L.n_surf() + nc, 128), 128, 0, stream>>>(m, s, L, dt); ++n_launch;
     IMC_CK(cudaGetLastError());
     // totalenergy sums in the reference's association order
@@ -403,13 +403,7 @@ struct EngineT : EngineBase {
     IMC_RC(ensure_capacity(n_part + n_local));
     if (n_local > 0) {
       IMC_CK(cudaMemsetAsync(over_flag.p, 0, sizeof(unsigned long long), stream));
-      // thread per entry for the entries that emit a handful of particles, block per entry for the listed big ones;
-      // thread per particle with a binary search when the list of big entries overflowed or entries are mostly empty
-      if (hsc.n_big <= SRC_BIG_CAP && L.total() <= 8 * total) {
-        k_src_emit_entries<P><<<grid_for(L.total(), 256), 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, total, n_part, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p);
-        if (hsc.n_big > 0) { k_src_emit_big<P><<<(unsigned)hsc.n_big, 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, total, n_part, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p); ++n_launch; }
-      } else
-        k_src_emit<P><<<grid_for(n_local, 256), 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, n_part, n_local, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p);
+      k_src_emit<P><<<grid_for(n_local, 256), 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, n_part, n_local, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p);
       ++n_launch;
       IMC_CK(cudaGetLastError());
       unsigned long long over = 0;

@@ -260,7 +260,6 @@ struct SrcArrays {
   int* cnt;           // loop count per entry
   S* nrg;             // energy per particle of the entry
   S* q_em;            // emittedenergy ./ escale, [Nc x Ns], for the print at :75
-  int* big;           // [SRC_BIG_CAP] entries with more than SRC_BIG_COUNT particles, in no particular order
 };
 
 struct SrcScalars {   // written by k_src_total, read by k_src_counts and by the host
@@ -268,10 +267,7 @@ struct SrcScalars {   // written by k_src_total, read by k_src_counts and by the
   double nsrc;        // n_source as a T value
   double sums[8];
   int bad;
-  int n_big;         // entries that emit more than SRC_BIG_COUNT particles (listed in SrcArrays::big)
 };
-constexpr int SRC_BIG_COUNT = 16;
-constexpr int SRC_BIG_CAP = 1 << 20;
 
 template <class P>
 __global__ void k_src_energies(MeshDev<P> m, SrcArrays<P> s, SrcLayout L, typename P::comp_t dt_) {
@@ -361,7 +357,6 @@ __global__ void k_src_total(SrcArrays<P> s, SrcLayout L, const typename P::comp_
   }
   out->nsrc = nsrc;
   out->bad = 0;
-  out->n_big = 0;
 }
 
 template <class P>
@@ -419,7 +414,6 @@ __global__ void k_src_counts(MeshDev<P> m, SrcArrays<P> s, SrcLayout L, SrcScala
   }
   if (ks < 0) bad = 1;
   s.cnt[e] = (int)loops;
-  if (loops > SRC_BIG_COUNT) { const int k = atomicAdd(&sc->n_big, 1); if (k < SRC_BIG_CAP) s.big[k] = (int)e; }   // e < 2^31: nc < 2^30 (set_mesh)
   (cnt > 0 ? div_count(en, cnt) : N()).store(s.nrg, e);
   if (bad) atomicOr(&sc->bad, 1);
 }
@@ -493,8 +487,9 @@ __device__ __forceinline__ void emit_one(const MeshDev<P>& m, const Parts<P>& p,
   if (d.over()) atomicAdd(over_flag, 1ull);
 }
 
-// thread per new particle: the entry is found by binary search in the scan of the counts (any count distribution,
-// e.g. the 1-D decks where one surface entry emits most of the particles)
+// thread per new particle: the entry is found by binary search in the scan of the counts — robust for any count
+// distribution (one surface entry of a 1-D deck emits millions of particles, a cold body cell emits CELLMIN); a
+// thread-per-entry variant was measured: no gain on the crooked pipe (hot cells emit thousands), 16x slower on Marshak
 template <class P>
 __global__ void k_src_emit(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
                            long long base, long long n_local, int rank, int world, typename P::comp_t dt_,
@@ -509,30 +504,6 @@ __global__ void k_src_emit(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L
     if (offs[mid] <= j) lo = mid; else hi = mid - 1;
   }
   emit_one(m, p, s, L, lo, j, base + l, dt_, rng, over_flag);
-}
-
-// thread per entry, looping over its few particles: no search, and the runs of adjacent entries are adjacent in the
-// particle list.  Entries with more than SRC_BIG_COUNT particles (hot cells, the surface entries of the 1-D decks) are
-// left to k_src_emit_big, one block per listed entry.  Rank r of `world` emits the ordinals j = r (mod world).
-template <class P>
-__global__ void k_src_emit_entries(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
-                                   long long total, long long base, int rank, int world, typename P::comp_t dt_, RngArgs rng,
-                                   unsigned long long* over_flag) {
-  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= L.total()) return;
-  const long long j0 = offs[e], j1 = e + 1 < L.total() ? offs[e + 1] : total;   // offs is the exclusive scan of the counts
-  if (j1 <= j0 || j1 - j0 > SRC_BIG_COUNT) return;
-  long long j = j0 + ((rank - j0 % world) + world) % world;   // first ordinal of this rank in [j0, j1)
-  for (; j < j1; j += world) emit_one(m, p, s, L, e, j, base + (j - rank) / world, dt_, rng, over_flag);
-}
-template <class P>
-__global__ void k_src_emit_big(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
-                               long long total, long long base, int rank, int world, typename P::comp_t dt_, RngArgs rng,
-                               unsigned long long* over_flag) {
-  const long long e = s.big[blockIdx.x];
-  const long long j0 = offs[e], j1 = e + 1 < L.total() ? offs[e + 1] : total;
-  long long j = j0 + ((rank - j0 % world) + world) % world + (long long)threadIdx.x * world;
-  for (; j < j1; j += (long long)blockDim.x * world) emit_one(m, p, s, L, e, j, base + (j - rank) / world, dt_, rng, over_flag);
 }
 
 // ======================================================================================
