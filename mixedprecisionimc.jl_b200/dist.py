@@ -2,8 +2,9 @@
 
 The transport step shards by particle: every rank holds the whole mesh, emits the
 new-particle ordinals j with j % world == rank, tracks and cleans its own slice, and the per-cell tallies
-are combined by ONE all-reduce per time step over the engine's reduce buffer
-[energydep | radenergydens | lostenergy | counters]; the per-cell update that follows is replicated, so
+are combined by an all-reduce of the engine's reduce buffer [energydep | radenergydens | lostenergy | counters] per
+time step (issued in two parts so that the large one overlaps compaction and the census tally); the per-cell update
+that follows is replicated, so
 every rank ends the step with identical temperature / Fleck fields.  The census count needed by the NMAX
 cap (imc_sourcing.jl:133-136) is a second, scalar all-reduce.
 
@@ -50,12 +51,23 @@ def advance_sharded(sim: _driver.Simulation, group=None) -> dict:
     dist.all_reduce(cnt, group=group)
     rec["source"] = _driver.Sourcing.sourcing(mesh, sv, parts, n_census_global=int(cnt.item()))
     rec["transport"] = eng.transport(float(sv.dt), sv.step)
-    _driver.Clean.clean(parts)
-    eng.tally_local()
-    buf = reduce_buffer_tensor(eng)
-    dist.all_reduce(buf, group=group)
+    # The deposits [energydep Nc*Ns] are final once the tracking kernel has returned: their all-reduce starts now, on the
+    # collective's stream, and overlaps the compaction and the census tally (which only write the particle list and the
+    # [radenergydens | scalars] tail of the buffer); the tail is reduced afterwards.  Two collectives per step, same bytes.
+    # (The oracle fills its host-side buffer only in tally_local, so there the whole buffer is reduced afterwards.)
     if on_gpu:
+        buf = reduce_buffer_tensor(eng)
+        n_dep = eng.nc * eng.ns
+        work = dist.all_reduce(buf[:n_dep], group=group, async_op=True)
+        _driver.Clean.clean(parts)
+        eng.tally_local()
+        dist.all_reduce(buf[n_dep:], group=group)
+        work.wait()
         torch.cuda.current_stream().synchronize()
+    else:
+        _driver.Clean.clean(parts)
+        eng.tally_local()
+        dist.all_reduce(reduce_buffer_tensor(eng), group=group)
     rec["tally"] = eng.tally_finish(float(sv.t), float(sv.dt))
     rec["energy"] = eng.energycheck()
     _driver.timestep(str(inputs["TIMESTEPPING"]).upper(), sv)
