@@ -488,8 +488,9 @@ __device__ __forceinline__ void emit_one(const MeshDev<P>& m, const Parts<P>& p,
 }
 
 // thread per new particle: the entry is found by binary search in the scan of the counts — robust for any count
-// distribution (one surface entry of a 1-D deck emits millions of particles, a cold body cell emits CELLMIN); a
-// thread-per-entry variant was measured: no gain on the crooked pipe (hot cells emit thousands), 16x slower on Marshak
+// distribution (one surface entry of a 1-D deck emits millions of particles, a cold body cell emits CELLMIN).  Measured
+// alternatives, all slower or equal (the search is a chain of ~25 dependent loads, hidden by 32 warps per SM): thread per
+// entry (16x slower on Marshak), one search per warp + shuffle window (3.2 vs 3.06 ms), one search per block (3.5 ms)
 template <class P>
 __global__ void k_src_emit(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
                            long long base, long long n_local, int rank, int world, typename P::comp_t dt_,
