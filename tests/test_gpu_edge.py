@@ -126,3 +126,30 @@ def test_float16_deck_with_counts_beyond_float16(gpu_lib, oracle_lib, deck):
     a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=3, precision="FLOAT16")
     assert_step_parity(a, b, out, "FLOAT16")
     assert out[-1][0]["source"]["n_particles"] > 65504
+
+
+@pytest.mark.parametrize("deck", ["suolson", "crooked"])
+def test_fused_step_equals_staged_calls(gpu_lib, oracle_lib, deck):
+    """imc_step (update -> source -> transport -> clean -> tally -> energycheck in one ABI call) gives exactly the
+    particles, fields and statistics of the stage-by-stage calls, on the engine and against the oracle."""
+    inputs = (decks.suolson(precision="FLOAT32", n_input=2000, n_max=20000) if deck == "suolson"
+              else decks.crooked_pipe(precision="FLOAT32", n_input=3000, n_max=60000, cellmin=1, pairwise="TRUE"))
+    sims = []
+    for library, fused in ((gpu_lib, True), (gpu_lib, False), (oracle_lib, True)):
+        sim = driver.setup(inputs, library, **({"tally_mode": lib.TALLY_EXACT} if library is gpu_lib else {}))
+        sim.save_history = False
+        sim.fused = fused
+        recs = [sim.advance() for _ in range(3)]
+        sims.append((sim, recs))
+    (a, ra), (b, rb), (c, rc) = sims
+    for x, y in ((ra, rb), (ra, rc)):
+        for r1, r2 in zip(x, y):
+            for stage in ("source", "tally", "energy"):
+                assert r1[stage] == r2[stage], (stage, r1[stage], r2[stage])
+            for k in ("segments", "histories", "n_census", "n_absorbed", "n_escaped", "lostenergy"):
+                assert r1["transport"][k] == r2["transport"][k], k
+    for other in (b, c):
+        pa, ia = a.engine.particles(); pb, ib = other.engine.particles()
+        assert np.array_equal(ia, ib) and np.array_equal(pa, pb)
+        for name in ("temp", "matenergydens", "radenergydens", "energydep", "fleck"):
+            assert np.array_equal(a.engine.field(name), other.engine.field(name)), name

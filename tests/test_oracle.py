@@ -285,3 +285,19 @@ def test_float16_counts_beyond_float16_range(oracle_lib):
     sim.save_history = False
     r = sim.advance()
     assert r["source"]["n_particles"] > 65504 and r["transport"]["n_errors"] == 0
+
+
+def test_fused_step_equals_staged_calls_on_the_oracle(oracle_lib):
+    inputs = decks.suolson(precision="FLOAT64", n_input=1000, n_max=10000)
+    out = []
+    for fused in (True, False):
+        sim = driver.setup(inputs, oracle_lib)
+        sim.save_history = False
+        sim.fused = fused
+        recs = [sim.advance() for _ in range(3)]
+        out.append((sim, recs))
+    (a, ra), (b, rb) = out
+    for r1, r2 in zip(ra, rb):
+        assert r1["source"] == r2["source"] and r1["tally"] == r2["tally"] and r1["energy"] == r2["energy"]
+    assert np.array_equal(a.engine.particles()[0], b.engine.particles()[0])
+    assert np.array_equal(a.engine.field("temp"), b.engine.field("temp"))
