@@ -31,6 +31,9 @@ namespace imc {
 #ifndef IMC_DEBUG_TALLY
 #define IMC_DEBUG_TALLY 0
 #endif
+#ifndef IMC_FASTDIV_DIR
+#define IMC_FASTDIV_DIR 1       // MC2D: divide by the direction cosines with cached reciprocals (imc_fastdiv.cuh)
+#endif
 #ifndef IMC_TRACK_MIN_BLOCKS
 #define IMC_TRACK_MIN_BLOCKS 4
 #endif
@@ -52,6 +55,9 @@ template <class P> struct alignas(2 * sizeof(typename P::store_t)) AxisProp { ty
 // so that the gathers do not evict the small per-axis tables and the particle stream from L1.
 template <class P>
 __device__ __forceinline__ CellProp2<P> load_cell2(const CellProp2<P>* tab, int c) {
+#if IMC_DEBUG_TALLY == 3 || IMC_DEBUG_TALLY == 4      /* measurement only: no gather (every cell reads entry c & 1023) */
+  c &= 1023;
+#endif
 #if IMC_CELL_GATHER_CG
   CellProp2<P> r;
   if constexpr (P::id == 0) { const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(tab) + c); r.sig_col = (uint16_t)(v & 0xffffu); r.neg_saf = (uint16_t)(v >> 16); }
@@ -66,11 +72,23 @@ __device__ __forceinline__ CellProp2<P> load_cell2(const CellProp2<P>* tab, int 
 // a / b for a divisor whose refined reciprocal r is cached (imc_fastdiv.cuh): Float16 / Float32 only — Float16 divides in
 // Float32 and rounds, as Julia does; Float64 keeps the plain division
 template <class P> __device__ __forceinline__ typename P::comp_t recip_of(Num<P> b) {
+#if IMC_FASTDIV_DIR
   if constexpr (P::id == 2) return 0.0; else return FastDivisor::recip(b.v);
+#else
+  return 0;
+#endif
 }
 template <class P> __device__ __forceinline__ Num<P> div_cached(Num<P> a, Num<P> b, typename P::comp_t r) {
   if constexpr (P::id == 2) return a / b;
   else { FastDivisor d; d.b = b.v; d.r = r; return Num<P>(P::rnd(d.divide(a.v))); }
+}
+// division by a direction cosine (reciprocal cached in the history registers) — IMC_FASTDIV_DIR=0: plain division
+template <class P> __device__ __forceinline__ Num<P> div_dir(Num<P> a, Num<P> b, typename P::comp_t r) {
+#if IMC_FASTDIV_DIR
+  return div_cached(a, b, r);
+#else
+  return a / b;
+#endif
 }
 
 template <class P>
@@ -569,7 +587,7 @@ struct Tally {
       else atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + idx, (unsigned long long)q);
     } else {
       if (K::smem(a)) atomicAdd(&s_acc[idx], (A)v.v);
-#if IMC_DEBUG_TALLY == 1      /* measurement only: no deposit */
+#if IMC_DEBUG_TALLY == 1 || IMC_DEBUG_TALLY == 4      /* measurement only: no deposit */
       else if (v.v == (typename P::comp_t)123456.0f) atomicAdd(a.g_acc + idx, v.d());
 #elif IMC_DEBUG_TALLY == 2    /* measurement only: Float32 atomics on the same buffer */
       else atomicAdd(reinterpret_cast<float*>(a.g_acc) + 2 * idx, (float)v.v);
@@ -848,8 +866,8 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   // the cell's {sigma_a (1 - f) + sigma_s, -sigma_a f} stay in registers and are re-read when the particle enters
   // another cell
   const N sig_col = h.sig_col, neg_saf = h.neg_saf;
-  const N dist_bx = nabs(div_cached(h.vx > zero ? h.wxc - h.x : h.x, h.vx, h.rvx)); // :538-542
-  const N dist_by = nabs(div_cached(h.vy > zero ? h.wyc - h.y : h.y, h.vy, h.rvy)); // :544-548
+  const N dist_bx = nabs(div_dir(h.vx > zero ? h.wxc - h.x : h.x, h.vx, h.rvx));    // :538-542
+  const N dist_by = nabs(div_dir(h.vy > zero ? h.wyc - h.y : h.y, h.vy, h.rvy));    // :544-548
   const N dist_b = min_nonnan(dist_bx, dist_by);                                    // :551-557
   const N dist_col = d.randexp(seg) / sig_col;                                      // :561
   const N dist_cen = (c_light * (dt - h.t)) * ds;                                   // :569
