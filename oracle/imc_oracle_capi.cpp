@@ -92,7 +92,8 @@ int imc_set_source_tape(imc_handle h, const double* u, int32_t nu, int64_t slots
 int imc_get_outcomes(imc_handle h, int32_t* ev, int32_t* nseg, int64_t cap) { GUARD(h->e->get_outcomes(ev, nseg, cap)); }
 
 // ---- test hooks (oracle only): evaluate the shared math / number helpers on arrays -------------
-// fn: 0 exp 1 expm1 2 log 3 sin 4 cos 5 atan2(x,y) 6 pow(x,y) 7 round-to-precision 8 sqrt ; prec: imc_precision
+// fn: 0 exp 1 expm1 2 log 3 sin 4 cos 5 atan2(x,y) 6 pow(x,y) 7 round-to-precision 8 sqrt 9 mul 10 add 11 div
+//     12 -log(u) sampler (Float32) 13 / 14 fused exp|expm1 in Float64 / Float32 (y != 0 selects expm1); prec: imc_precision
 int imc_oracle_math_eval(int32_t fn, int32_t prec, const double* x, const double* y, double* out, int64_t n) {
   auto run = [&](auto tag) {
     using P = decltype(tag); using N = Num<P>;
@@ -111,6 +112,9 @@ int imc_oracle_math_eval(int32_t fn, int32_t prec, const double* x, const double
         case 9: out[i] = (a * b).d(); break;
         case 10: out[i] = (a + b).d(); break;
         case 11: out[i] = (a / b).d(); break;
+        case 12: out[i] = (double)dm::neglog_unit_f((float)x[i]); break;                       // the Float16 / Float32 exponential sampler
+        case 13: { double e, m; dm::exp_expm1_d(x[i], &e, &m); out[i] = y ? (y[i] != 0 ? m : e) : e; break; }   // fused exp / expm1 (Float64)
+        case 14: { float e, m; dm::exp_expm1_f((float)x[i], &e, &m); out[i] = y ? (y[i] != 0 ? (double)m : (double)e) : (double)e; break; }
         default: return (int)IMC_ERR_ARG;
       }
     }

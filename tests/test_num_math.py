@@ -149,3 +149,46 @@ def test_julia_pairwise_sum(oracle_lib, n):
         a = (rng.random(n) * 10.0 ** rng.integers(-4, 4, size=n)).astype(T)
         got = f(prec, a.astype(np.float64).ctypes.data_as(DP), n)
         assert got == float(julia_sum(a))
+
+
+def _eval(oracle_lib, fn, prec, x, y=None):
+    f = oracle_lib.dll.imc_oracle_math_eval
+    f.restype = C.c_int
+    f.argtypes = [C.c_int32, C.c_int32, DP, DP, DP, C.c_int64]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    yp = None if y is None else np.ascontiguousarray(y, dtype=np.float64).ctypes.data_as(DP)
+    assert f(fn, prec, x.ctypes.data_as(DP), yp, out.ctypes.data_as(DP), x.size) == 0
+    return out
+
+
+def test_exponential_sampler_transform(oracle_lib):
+    """dm::neglog_unit_f, the division-free -log(u) behind randexp(Float16 / Float32): within 2 ulp of -log(u) for every
+    kind of uniform the generator can produce, exactly 0 at u = 1, finite at the smallest u, never negative."""
+    rng = np.random.default_rng(5)
+    w = np.concatenate([rng.integers(0, 2 ** 32, 400000, dtype=np.uint64), [0, 1, 2, 2 ** 31, 2 ** 32 - 2, 2 ** 32 - 1],
+                        2 ** 32 - 1 - rng.integers(0, 4096, 2000, dtype=np.uint64)]).astype(np.float64)
+    u = np.minimum((w.astype(np.float32) * np.float32(2.3283064365386963e-10) + np.float32(1.1641532182693481e-10)).astype(np.float32), np.float32(1.0))
+    got = _eval(oracle_lib, 12, lib.F32, u.astype(np.float64))
+    want = -np.log(u.astype(np.float64))
+    assert np.all(got >= 0) and np.all(np.isfinite(got))
+    assert got[u == 1.0].max() == 0.0
+    nz = want > 0
+    ulp = np.spacing(want[nz].astype(np.float32)).astype(np.float64)
+    assert np.max(np.abs(got[nz] - want[nz]) / ulp) <= 2.0
+    assert 22.0 < got.max() < 23.0       # u = 2^-33
+
+
+@pytest.mark.parametrize("prec,fn", [(lib.F64, 13), (lib.F32, 14)])
+def test_fused_exp_expm1_equals_the_separate_functions(oracle_lib, prec, fn):
+    """exp_expm1 (one range reduction, and none at all when |x| < ln2/2 — the tracking loop's usual argument) returns
+    bit for bit what exp and expm1 return separately."""
+    rng = np.random.default_rng(6)
+    x = np.concatenate([-rng.uniform(0, 0.5, 200000), -rng.uniform(0, 1e-3, 100000), rng.uniform(-40, 40, 100000), -10.0 ** rng.uniform(-45, 1, 50000),
+                        [0.0, -0.0, 0.34657, -0.34657, 0.3466, -0.3466, 1e-300, -1e-300, 88.0, -17.0, -37.0, 709.0, -745.0]])
+    if prec == lib.F32:
+        x = x.astype(np.float32).astype(np.float64)
+    e = _eval(oracle_lib, fn, prec, x, np.zeros_like(x))
+    m = _eval(oracle_lib, fn, prec, x, np.ones_like(x))
+    assert np.array_equal(e, _eval(oracle_lib, 0, prec, x), equal_nan=True)
+    assert np.array_equal(m, _eval(oracle_lib, 1, prec, x), equal_nan=True)
