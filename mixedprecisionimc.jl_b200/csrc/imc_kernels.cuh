@@ -596,6 +596,32 @@ struct Tally {
 #endif
     }
   }
+  // 1-D decks: the lanes of a warp mostly deposit into the same one or two cells, and a shared-memory Float32 / 64-bit
+  // atomic add is a compare-and-swap loop (27 % of k_track1d's instructions on Su-Olson were its retries).  Runs of
+  // adjacent active lanes with the same accumulator are therefore summed first with a segmented shuffle scan and the last
+  // lane of each run issues the one atomic.  Float32 partial sums in ATOMIC mode (order-free to the tolerance, like the
+  // per-lane atomics), exact integer sums in FIXED mode.  Only for the shared-memory kinds; everything else -> add().
+  __device__ __forceinline__ void add_runs(int idx, Num<P> v, long long rec = 0) {
+    if (!K::smem(a) || K::exact(a)) { add(idx, v, rec); return; }
+    const unsigned act = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int prev = __shfl_up_sync(act, idx, 1);
+    const bool head = lane == 0 || !((act >> (lane - 1)) & 1u) || prev != idx;
+    const unsigned heads = __ballot_sync(act, head);
+    const int headlane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    const bool tail = lane == 31 || !((act >> (lane + 1)) & 1u) || ((heads >> (lane + 1)) & 1u);
+    if (K::fixed(a)) {
+      long long q = __double2ll_rn(v.d() * a.fx_mul);
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) { const long long t = __shfl_up_sync(act, q, dlt); if (lane - dlt >= headlane) q += t; }
+      if (tail) atomicAdd(&s_fx[idx], (unsigned long long)q);
+    } else {
+      A x = (A)v.v;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) { const A t = __shfl_up_sync(act, x, dlt); if (lane - dlt >= headlane) x += t; }
+      if (tail) atomicAdd(&s_acc[idx], x);
+    }
+  }
   __device__ __forceinline__ void flush() {
     if (!K::smem(a) || K::exact(a)) return;
     __syncthreads();
@@ -751,11 +777,11 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   // (EXACT), else E * (1/dx) (<= 1.5 ulp from it; sums in these modes are order-dependent anyway)
   const N idx = exact ? N() : N(P::unpack(a.m.ax_inv[h.cell].q));
   if (newE <= h.minE) {                                                             // :97-106
-    tal.add(acc, exact ? h.E / dx : h.E * idx, h.rec_base + h.nseg - 1);
+    tal.add_runs((int)acc, exact ? h.E / dx : h.E * idx, h.rec_base + h.nseg - 1);
     h.E0 = N::from_d(-1.0);
     return 1;
   }
-  tal.add(acc, exact ? (-(h.E / dx)) * em1 : ((-h.E) * idx) * em1, h.rec_base + h.nseg - 1);                                   // :110 / :120
+  tal.add_runs((int)acc, exact ? (-(h.E / dx)) * em1 : ((-h.E) * idx) * em1, h.rec_base + h.nseg - 1);                        // :110 / :120
   h.x = h.x + h.mu * dist;                                                          // :124
   { N dd = dist;                                                                    // :125 (dist / ds) / c; x / 1 == x exactly
 #pragma unroll 1
