@@ -561,6 +561,16 @@ struct TKind {
   static __device__ __forceinline__ bool smem(const TallyArgs& a) { if constexpr (TK == TK_RUNTIME) return a.use_smem != 0; else return TK == TK_ATOMIC_S || TK == TK_FIXED_S; }
 };
 
+// 64-bit shared-memory accumulator += 64-bit value by native 32-bit atomics (low word, carry, high word): a 64-bit shared
+// atomicAdd is a compare-and-swap loop on sm_100.  Two's-complement, so negative addends work; readers synchronise first.
+__device__ __forceinline__ void smem_add64(unsigned long long* acc, unsigned long long q) {
+  unsigned* w = reinterpret_cast<unsigned*>(acc);
+  const unsigned lo = (unsigned)q, hi = (unsigned)(q >> 32);
+  const unsigned old = atomicAdd(w, lo);
+  const unsigned carry = old > 0xffffffffu - lo ? 1u : 0u;
+  if (hi + carry) atomicAdd(w + 1, hi + carry);
+}
+
 template <class P, int TK = TK_RUNTIME>
 struct Tally {
   using A = typename AccType<P>::type;
@@ -583,7 +593,7 @@ struct Tally {
     }
     if (K::fixed(a)) {
       long long q = __double2ll_rn(v.d() * a.fx_mul);
-      if (K::smem(a)) atomicAdd(&s_fx[idx], (unsigned long long)q);
+      if (K::smem(a)) smem_add64(&s_fx[idx], (unsigned long long)q);
       else atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + idx, (unsigned long long)q);
     } else {
       if (K::smem(a)) atomicAdd(&s_acc[idx], (A)v.v);
@@ -614,7 +624,7 @@ struct Tally {
       long long q = __double2ll_rn(v.d() * a.fx_mul);
 #pragma unroll
       for (int dlt = 1; dlt < 32; dlt <<= 1) { const long long t = __shfl_up_sync(act, q, dlt); if (lane - dlt >= headlane) q += t; }
-      if (tail) atomicAdd(&s_fx[idx], (unsigned long long)q);
+      if (tail) smem_add64(&s_fx[idx], (unsigned long long)q);
     } else {
       A x = (A)v.v;
 #pragma unroll
@@ -650,16 +660,23 @@ struct Counters {
     const unsigned segs = __reduce_add_sync(m, (unsigned)nseg);
     const unsigned c0 = __ballot_sync(m, ev == 0), c2 = __ballot_sync(m, ev == 2);
     if (lane == leader) {
-      atomicAdd(&s[RB_SEG], (unsigned long long)segs);
-      atomicAdd(&s[RB_HIST], (unsigned long long)__popc(m));
-      if (c0) atomicAdd(&s[RB_CENSUS], (unsigned long long)__popc(c0));
-      if (c2) atomicAdd(&s[RB_ESCAPED], (unsigned long long)__popc(c2));
+      add64(RB_SEG, segs);
+      add64(RB_HIST, (unsigned)__popc(m));
+      if (c0) add64(RB_CENSUS, (unsigned)__popc(c0));
+      if (c2) add64(RB_ESCAPED, (unsigned)__popc(c2));
       const int nabs = __popc(m) - __popc(c0) - __popc(c2);
-      if (nabs) atomicAdd(&s[RB_ABSORBED], (unsigned long long)nabs);
+      if (nabs) add64(RB_ABSORBED, (unsigned)nabs);
     }
   }
-  __device__ __forceinline__ void error() { atomicAdd(&s[RB_ERRORS], 1ull); }
-  __device__ __forceinline__ void rw() { atomicAdd(&s[RB_RW], 1ull); }
+  // 64-bit counter += 32-bit value with native 32-bit shared-memory atomics (a 64-bit shared atomicAdd is a compare-and-swap
+  // loop on sm_100): low word, then the carry into the high word.  The counters are read only after a __syncthreads().
+  __device__ __forceinline__ void add64(int k, unsigned v) {
+    unsigned* w = reinterpret_cast<unsigned*>(&s[k]);
+    const unsigned old = atomicAdd(w, v);
+    if (old > 0xffffffffu - v) atomicAdd(w + 1, 1u);
+  }
+  __device__ __forceinline__ void error() { add64(RB_ERRORS, 1u); }
+  __device__ __forceinline__ void rw() { add64(RB_RW, 1u); }
   template <int TK = TK_RUNTIME>
   __device__ __forceinline__ void lose_value(const TallyArgs& a, double e_over_scale) {
     if (TKind<TK>::fixed(a)) atomicAdd(&s[RB_LOST], (unsigned long long)__double2ll_rn(e_over_scale * a.fx_mul_lost));
@@ -925,11 +942,11 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   // the deposit only feeds the tally: the reference's expression when the tally is reduced in reference order
   // (EXACT), else E * ((1/dx) * (1/dy)) (<= 3 ulp from it; sums in these modes are order-dependent anyway)
   if (newE <= h.minE) {                                                             // :586-595
-    tal.add(acc, exact ? (h.E / h.qx) / h.qy : h.E * (h.qx * h.qy), h.rec_base + h.nseg - 1);
+    tal.add_runs((int)acc, exact ? (h.E / h.qx) / h.qy : h.E * (h.qx * h.qy), h.rec_base + h.nseg - 1);
     h.E = N::from_d(-1.0);
     return 1;
   }
-  tal.add(acc, exact ? ((-(h.E / h.qx)) / h.qy) * em1 : ((-h.E) * (h.qx * h.qy)) * em1, h.rec_base + h.nseg - 1);  // :599 / :607
+  tal.add_runs((int)acc, exact ? ((-(h.E / h.qx)) / h.qy) * em1 : ((-h.E) * (h.qx * h.qy)) * em1, h.rec_base + h.nseg - 1);  // :599 / :607
   h.x = h.x + dist * h.vx;                                                          // :615
   h.y = h.y + dist * h.vy;                                                          // :616
   { N dd = dist;                                                                    // :617 (dist / ds) / c; x / 1 == x exactly
@@ -1376,7 +1393,7 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Pa
     }
     if (tail && cell >= 0) {
       if (ta.mode == IMC_TALLY_FIXED) {
-        if (ta.use_smem) atomicAdd(&tal.s_fx[cell], (unsigned long long)q);
+        if (ta.use_smem) smem_add64(&tal.s_fx[cell], (unsigned long long)q);
         else atomicAdd(reinterpret_cast<unsigned long long*>(ta.g_fx) + cell, (unsigned long long)q);
       } else {
         if (ta.use_smem) atomicAdd(&tal.s_acc[cell], (typename AccType<P>::type)v);
