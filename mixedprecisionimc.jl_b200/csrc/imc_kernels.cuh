@@ -1245,7 +1245,8 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
         N ex, em1; MathDet::exp_expm1<P>(expo, &ex, &em1);
         D newE = dyn_mul(E, D(ex));
         D depv = dyn_mul(dyn_mul(D(-one), dyn_div(E, D(dx))), D(em1));              // :317-320 / :352-356
-        tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);  // Float64 deposits: converted on push! / added in Float64 on setindex!
+        if (a.tally.mode == IMC_TALLY_EXACT) tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);  // Float64 deposits: converted on push! / added in Float64 on setindex!
+        else tal.add_runs((int)(kbase + cell), N::from_d(depv.v));
         if (newE.v != newE.v) cn.error();
         E0 = N::from_d(-1.0); ev = 3;
         break;
@@ -1253,7 +1254,8 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
       D newE = dyn_mul(E, D::w(dm::exp_d(neg_saf.d() * dist.v)));                   // :376 (Float64)
       if (newE.v <= minE.d()) newE = D(zero);                                       // :377-379
       D depv = dyn_sub(E, newE);                                                    // :383 / :385 (not / dx, Q2)
-      tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);
+      if (a.tally.mode == IMC_TALLY_EXACT) tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);
+      else tal.add_runs((int)(kbase + cell), N::from_d(depv.v));
       if (newE.v == 0.0) { E0 = N::from_d(-1.0); ev = 1; break; }    // :390-394
       x = dyn_add(x, dyn_mul(D(mu), dist));                                         // :397
       t = dyn_add(t, dyn_div(dist, D(c_light)));                                    // :398
