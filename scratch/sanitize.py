@@ -16,6 +16,9 @@ cases = [
     ("crooked f32 big mesh global tally", decks.crooked_pipe(precision="FLOAT32", n_input=20000, n_max=200000, cellmin=1, mesh_cells=(160, 160), pairwise="FALSE"), dict()),
     ("marshak rw f32", decks.marshak(precision="FLOAT32", n_cells=64, nonuniform=True, randomwalk="TRUE", n_input=2000, n_max=30000, dx_min=2e-4), dict()),
     ("nonuniform multiscale f64", decks.nonuniform_1d(precision="FLOAT64", n_input=2000), dict()),
+    ("marshak rw f32 atomic", decks.marshak(precision="FLOAT32", n_cells=64, nonuniform=True, randomwalk="TRUE", n_input=2000, n_max=30000, dx_min=2e-4, pairwise="FALSE"), dict(tally_mode=lib.TALLY_ATOMIC)),
+    ("suolson f32 fixed refill", decks.suolson(precision="FLOAT32", n_input=1500, n_max=20000), dict(tally_mode=lib.TALLY_FIXED, track_mode=lib.TRACK_REFILL)),
+    ("nonuniform multiscale f32 atomic", decks.nonuniform_1d(precision="FLOAT32", n_input=2000, pairwise="FALSE"), dict(tally_mode=lib.TALLY_ATOMIC)),
 ]
 for name, inputs, cfg in cases:
     sim = driver.setup(inputs, g, **cfg)
