@@ -726,11 +726,13 @@ struct EngineT : EngineBase {
     Parts<P> src = pb[cur].view(), dst = pb[cur ^ 1].view();
     k_alive_count<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, n_part, geom, blk_cnt.p); ++n_launch;
     k_scan_small<<<1, 1024, 0, stream>>>(blk_cnt.p, blocks, scan_total.p); ++n_launch;
-    k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, dst, n_part, geom, blk_cnt.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     long long total = 0;
     IMC_CK(cudaMemcpyAsync(&total, scan_total.p, sizeof total, cudaMemcpyDeviceToHost, stream));
     IMC_CK(cudaStreamSynchronize(stream));
+    if (total == n_part) { if (n_alive) *n_alive = n_part; return IMC_OK; }   // nobody died (Su-Olson: most steps): the list is already compact
+    k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, dst, n_part, geom, blk_cnt.p); ++n_launch;
+    IMC_CK(cudaGetLastError());
     n_part = total;
     cur ^= 1;
     if (n_alive) *n_alive = n_part;
