@@ -480,6 +480,12 @@ struct EngineT : EngineBase {
     size_t per = mode == IMC_TALLY_FIXED ? 8 : sizeof(typename AccType<P>::type);
     return (size_t)nacc * per;
   }
+  // accumulator sets per block: as many as fit in 48 KB, at most one per warp of the block (a power of two)
+  static int smem_copies(size_t one_set) {
+    int c = 1;
+    while (c < TRACK_THREADS / 32 && one_set * (size_t)(2 * c) <= 48 * 1024) c *= 2;
+    return c;
+  }
 
 
   // EXACT mode: records (key = tally cell, val) in reference order -> out[c] = reduction of cell c's records
@@ -584,7 +590,8 @@ struct EngineT : EngineBase {
     if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
     size_t smem = smem_for(mode, nc * ns);
     a.tally.use_smem = (smem <= 48 * 1024 && mode != IMC_TALLY_EXACT) ? 1 : 0;
-    if (!a.tally.use_smem) smem = 0;
+    a.tally.copies = a.tally.use_smem ? smem_copies(smem) : 1;
+    smem = a.tally.use_smem ? smem * a.tally.copies : 0;
     // outcome records for replay checks (small populations only)
     bool record = n_part <= (1ll << 22);
     if (record) {
@@ -652,7 +659,8 @@ struct EngineT : EngineBase {
           if (mode == IMC_TALLY_FIXED && !red_fixed) { IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream)); red_fixed = true; }
           a.tally.mode = mode; a.tally.pass = 0;
           if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
-          smem = smem_for(mode, nc * ns); a.tally.use_smem = smem <= 48 * 1024 ? 1 : 0; if (!a.tally.use_smem) smem = 0;
+          smem = smem_for(mode, nc * ns); a.tally.use_smem = smem <= 48 * 1024 ? 1 : 0;
+          a.tally.copies = a.tally.use_smem ? smem_copies(smem) : 1; smem = a.tally.use_smem ? smem * a.tally.copies : 0;
           IMC_RC(launch_track(a, variant, grid, smem));
         } else {
           for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)std::max<long long>(R, 1))); IMC_CK(rec_val[b].ensure((size_t)std::max<long long>(R, 1))); }
@@ -751,7 +759,7 @@ struct EngineT : EngineBase {
     ta.pass = 0; ta.rec_cnt = nullptr; ta.rec_off = nullptr; ta.rec_key = nullptr; ta.rec_val = nullptr; ta.lost_val = nullptr;
     if (mode == IMC_TALLY_EXACT) {  // per-cell vectors + Julia sum, in particle order (imc_tally.jl:84-113, Q19)
       for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)n_part)); IMC_CK(rec_val[b].ensure((size_t)n_part)); }
-      ta.mode = mode; ta.nacc = (int)nc; ta.use_smem = 0; ta.g_acc = nullptr; ta.g_fx = nullptr; ta.fx_mul = 1; ta.fx_mul_lost = 1; ta.sc0 = 0;
+      ta.mode = mode; ta.nacc = (int)nc; ta.use_smem = 0; ta.copies = 1; ta.g_acc = nullptr; ta.g_fx = nullptr; ta.fx_mul = 1; ta.fx_mul_lost = 1; ta.sc0 = 0;
       ta.pass = 2; ta.rec_key = rec_key[0].p; ta.rec_val = rec_val[0].p;
       k_census_tally<P><<<grid_for(n_part, TRACK_THREADS), TRACK_THREADS, 0, stream>>>(m, pb[cur].view(), n_part, ta); ++n_launch;
       IMC_CK(cudaGetLastError());
@@ -762,7 +770,8 @@ struct EngineT : EngineBase {
     ta.fx_mul = fx_mul_rad; ta.fx_mul_lost = fx_mul_lost; ta.sc0 = 0;
     size_t smem = smem_for(mode, nc);
     ta.use_smem = smem <= 48 * 1024 ? 1 : 0;
-    if (!ta.use_smem) smem = 0;
+    ta.copies = ta.use_smem ? smem_copies(smem) : 1;
+    smem = ta.use_smem ? smem * ta.copies : 0;
     int blocks_per_sm = 2048 / TRACK_THREADS;
     unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
     k_census_tally<P><<<grid, TRACK_THREADS, smem, stream>>>(m, pb[cur].view(), n_part, ta); ++n_launch;

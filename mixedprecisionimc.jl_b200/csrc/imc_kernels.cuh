@@ -534,6 +534,8 @@ template <> struct AccType<F64> { using type = double; };
 struct TallyArgs {
   int mode;          // IMC_TALLY_ATOMIC or IMC_TALLY_FIXED (EXACT uses the record path)
   int use_smem;      // block-private accumulators in shared memory (nacc of them)
+  int copies;        // shared-memory accumulator sets per block (a power of two): warp w deposits into set w % copies, so that
+                     // the compare-and-swap loops of different warps do not collide
   int nacc;          // Nc * Ns
   double* g_acc;     // reduce buffer viewed as Float64 (ATOMIC)
   long long* g_fx;   // reduce buffer viewed as int64 (FIXED)
@@ -577,13 +579,17 @@ struct Tally {
   using K = TKind<TK>;
   const TallyArgs& a;
   A* s_acc; unsigned long long* s_fx;
+  A* s_acc0; unsigned long long* s_fx0;   // set 0 (zero / flush walk all sets from here)
   __device__ __forceinline__ Tally(const TallyArgs& a_, unsigned char* smem) : a(a_) {
-    s_acc = reinterpret_cast<A*>(smem); s_fx = reinterpret_cast<unsigned long long*>(smem);
+    s_acc0 = reinterpret_cast<A*>(smem); s_fx0 = reinterpret_cast<unsigned long long*>(smem);
+    const int set = K::smem(a_) ? (int)((threadIdx.x >> 5) & (unsigned)(a_.copies - 1)) : 0;
+    s_acc = s_acc0 + (size_t)set * a_.nacc; s_fx = s_fx0 + (size_t)set * a_.nacc;
   }
   __device__ __forceinline__ void zero() {
     if (!K::smem(a) || K::exact(a)) return;
-    if (K::fixed(a)) { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_fx[i] = 0ull; }
-    else { for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) s_acc[i] = (A)0; }
+    const int n = a.nacc * a.copies;
+    if (K::fixed(a)) { for (int i = threadIdx.x; i < n; i += blockDim.x) s_fx0[i] = 0ull; }
+    else { for (int i = threadIdx.x; i < n; i += blockDim.x) s_acc0[i] = (A)0; }
     __syncthreads();
   }
   __device__ __forceinline__ void add(long long idx, Num<P> v, long long rec = 0, bool wide = false, double wide_v = 0.0) {
@@ -636,9 +642,17 @@ struct Tally {
     if (!K::smem(a) || K::exact(a)) return;
     __syncthreads();
     if (K::fixed(a)) {
-      for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) { unsigned long long q = s_fx[i]; if (q) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + i, q); }
+      for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) {
+        unsigned long long q = 0ull;
+        for (int c = 0; c < a.copies; ++c) q += s_fx0[(size_t)c * a.nacc + i];
+        if (q) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + i, q);
+      }
     } else {
-      for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) { A q = s_acc[i]; if (q != (A)0) atomicAdd(a.g_acc + i, (double)q); }
+      for (int i = threadIdx.x; i < a.nacc; i += blockDim.x) {
+        double q = 0.0;
+        for (int c = 0; c < a.copies; ++c) q += (double)s_acc0[(size_t)c * a.nacc + i];
+        if (q != 0.0) atomicAdd(a.g_acc + i, q);
+      }
     }
   }
 };
