@@ -346,7 +346,7 @@ def main():
                          "bytes_per_segment": bps, "peak_source": peak_src},
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU legs run on rank 0 at N = 1 only
             sample = args.cpu_sample or 10_000_000
             cmesh = mesh if w["geom"] == 1 else (min(mesh[0], 256), min(mesh[1], 256))
             seg_s, dt, cseg, chist = cpu_port_run(w, cmesh, sample, 2, 1)
