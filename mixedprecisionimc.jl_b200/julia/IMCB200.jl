@@ -32,6 +32,7 @@ mutable struct EnergyStats; radenergy::Float64; radenergy_change::Float64; loste
 
 const ENGINES = IdDict{Any,Ptr{Cvoid}}()   # mesh => imc_handle
 const STEP = Ref(0)                        # time-step ordinal (Philox counter word)
+const PENDING_RW = Ref{Any}(nothing)       # (aVals, prVals, ptVals) of Transport.randomwalk_table, until the engine exists
 
 check(h, rc) = rc == 0 || error("imc error $rc: " * unsafe_string(ccall((:imc_last_error, libimc), Cstring, (Ptr{Cvoid},), h)))
 f64(a) = Float64.(vec(collect(a)))         # column-major linear order, as the ABI expects
@@ -45,7 +46,7 @@ function attach!(inputs, mesh, simvars)
     scales = sort(Float64.(collect(mesh.energyscales)), rev=true)
     bc = geom == 1 ? (bcid(simvars.BC[1]), bcid(simvars.BC[2]), Int32(1), Int32(1)) :
                      (bcid(simvars.BC[1]), bcid(simvars.BC[2]), bcid(simvars.BC[3]), bcid(simvars.BC[4]))
-    C = Main.MixedPrecisionIMC.Constants
+    C = parentmodule(@__MODULE__).Constants     # the module that included this file (MixedPrecisionIMC)
     cfg = ImcConfig(sizeof(ImcConfig), precid(simvars.precision), geom, nx, ny, bc,
         inputs["LINEARIZED"] == "TRUE", simvars.pairwise == "TRUE",
         geom == 1 && uppercase(string(get(inputs, "RANDOMWALK", "FALSE"))) == "TRUE",
@@ -63,8 +64,21 @@ function attach!(inputs, mesh, simvars)
          f64(mesh.sigma[:, 1]), f64(mesh.bee), f64(mesh.radsource), f64(mesh.temp), Float64[], Float64[], [Float64(ts[1])], [Float64(ts[2])]) :
         (f64(mesh.dx), f64(mesh.dy), f64(sel(mesh.sigma_a, 2)), f64(sel(mesh.sigma_a, 3)), f64(sel(mesh.sigma_s, 2)), f64(sel(mesh.sigma_s, 3)),
          f64(mesh.sigma[:, :, 1]), f64(mesh.bee), f64(mesh.radsource), f64(mesh.temp), f64(ts[1]), f64(ts[2]), f64(ts[3]), f64(ts[4]))
-    GC.@preserve args check(h[], ccall((:imc_set_mesh, libimc), Cint, (Ptr{Cvoid}, ntuple(_ -> Ptr{Float64}, 14)...), h[], map(pointer, args)...))
+    # ccall takes a literal tuple of argument types and no splatting, hence the fourteen names
+    (a_dx, a_dy, a_sac, a_sap, a_ssc, a_ssp, a_sig, a_bee, a_rad, a_temp, a_tsb, a_tst, a_tsl, a_tsr) = args
+    PF = Ptr{Float64}
+    check(h[], ccall((:imc_set_mesh, libimc), Cint, (Ptr{Cvoid}, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF),
+                     h[], a_dx, a_dy, a_sac, a_sap, a_ssc, a_ssp, a_sig, a_bee, a_rad, a_temp, a_tsb, a_tst, a_tsl, a_tsr))
+    if PENDING_RW[] !== nothing                # random-walk tables: built by the engine, copied into the host's arrays
+        aVals, prVals, ptVals = PENDING_RW[]
+        a = Vector{Float64}(undef, length(aVals)); pr = similar(a); pt = similar(a)
+        check(h[], ccall((:imc_rw_table, libimc), Cint, (Ptr{Cvoid}, Float64, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                         h[], Float64(first(aVals)), Float64(last(aVals)), length(aVals), a, pr, pt))
+        prVals .= pr; ptVals .= pt
+        PENDING_RW[] = nothing
+    end
     ENGINES[mesh] = h[]
+    STEP[] = 0
     return h[]
 end
 engine(inputs, mesh, simvars) = get!(() -> attach!(inputs, mesh, simvars), ENGINES, mesh)
@@ -107,7 +121,7 @@ module Sourcing
 end
 
 module Transport
-    import ..IMCB200: engine, check, libimc, TransportStats, STEP
+    import ..IMCB200: engine, check, libimc, TransportStats, STEP, PENDING_RW
     function run(mesh, simvars)
         st = TransportStats()
         check(engine(mesh), ccall((:imc_transport, libimc), Cint, (Ptr{Cvoid}, Float64, Int64, Ref{TransportStats}), engine(mesh), Float64(simvars.dt), STEP[], st))
@@ -118,11 +132,10 @@ module Transport
     MC(mesh, simvars, particles) = run(mesh, simvars)                         # imc_transport.jl:13
     MC_RW(mesh, simvars, rwvars, particles) = run(mesh, simvars)              # imc_transport.jl:212
     MC2D(mesh, simvars, particles) = run(mesh, simvars)                       # imc_transport.jl:483
-    function randomwalk_table(aVals, prVals, ptVals, simvars; mesh)           # imc_transport.jl:786
-        a = Vector{Float64}(undef, length(aVals)); pr = similar(a); pt = similar(a)
-        check(engine(mesh), ccall((:imc_rw_table, libimc), Cint, (Ptr{Cvoid}, Float64, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-              engine(mesh), Float64(first(aVals)), Float64(last(aVals)), length(aVals), a, pr, pt))
-        prVals .= pr; ptVals .= pt
+    # imc_transport.jl:786.  `main` calls this before the first Update.update (MixedPrecisionIMC.jl:132), i.e. before the
+    # engine exists: the request is parked and `attach!` fills prVals / ptVals in place (RWVars holds these same arrays).
+    function randomwalk_table(aVals, prVals, ptVals, simvars)
+        PENDING_RW[] = (aVals, prVals, ptVals)
         return prVals, ptVals
     end
 end
@@ -145,6 +158,9 @@ module Tally
         print("Energy increase: ", st.energy_increase, "\n")
         print("Maximum mesh temperature is ", st.max_temp, "\n")
         print("Final total energy density ", st.total_energy_density, "\n")
+        nrg_inc = similar(mesh.matenergydens)                                 # imc_tally.jl:58
+        GC.@preserve nrg_inc check(engine(mesh), ccall((:imc_get_field_native, libimc), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64), engine(mesh), 10, pointer(nrg_inc), sizeof(nrg_inc)))
+        push!(mesh.energyincrease_saved, nrg_inc)
         push!(mesh.temp_saved, copy(mesh.temp)); push!(mesh.matenergy_saved, copy(mesh.matenergydens)); push!(mesh.radenergy_saved, copy(mesh.radenergydens))
     end
 end
