@@ -110,6 +110,18 @@ class JuliaMath:
         return self._eval(6, T, T(x), T(y))
 
 
+class ReferenceThrows(Exception):
+    """Base of the exceptions the Julia reference itself would raise at this point."""
+
+
+class BoundsError(ReferenceThrows, IndexError):
+    """The reference indexes past the end of an array here and Julia throws (e.g. mesh.dx[j] with j > Nx, Q7)."""
+
+
+class InexactError(ReferenceThrows, ValueError):
+    """Utilities.tointeger / Int(x) on a value that is not an integer (NaN, Inf, a fraction): Julia throws."""
+
+
 class Tape:
     """Pre-drawn random numbers of one particle: rand(T) values and Float64 randexp() values, consumed in call order."""
 
@@ -233,7 +245,8 @@ def update(S):
 def _count(S, e, esc, n_source):
     """tointeger(max(round((e/escale)*n_source/totalenergy), cellmin)) stored into a zeros(T) array."""
     v = jmax(np.round(((e / esc) * n_source) / S.totalenergy), S.cellmin)
-    assert float(v) == int(v)
+    if not np.isfinite(v) or float(v) != int(v):
+        raise InexactError(f"tointeger({v!r})")
     return S.T(int(v))
 
 
@@ -256,6 +269,8 @@ def sourcing(S, tapes):
             e_body[c], esc_body[c] = T(e_body[c]), T(esc_body[c])                                               # stored into zeros(T) / ones(T)
             e_rad[c], esc_rad[c], _ = sorter([S.radsource[c], dx, dt], S.scales, T)                             # (:68)
             em, emitted_scale[c], k = sorter([f, sa, a_, c_, t, t, t, t, dt, ds], S.scales, T)                  # (:69)
+            if k == 0:
+                raise BoundsError("mesh.emittedenergy[i, 0]: no scale gives a finite product (imc_sourcing.jl:70)")
             S.emittedenergy[(c, k)] = T(em)
     else:
         eb, et, el, er = {}, {}, {}, {}
@@ -277,6 +292,8 @@ def sourcing(S, tapes):
             e_body[c], esc_body[c] = T(e_body[c]), T(esc_body[c])
             e_rad[c], esc_rad[c], _ = sorter([S.radsource[c], dx, dy, dt], S.scales, T)                         # (:100)
             em, _, k = sorter([f, sa, a_, c_, t, t, t, t, dt, ds], S.scales, T)                                 # (:101)
+            if k == 0:
+                raise BoundsError("mesh.emittedenergy[x, y, 0]: no scale gives a finite product (imc_sourcing.jl:102)")
             S.emittedenergy[(c, k)] = T(em)
     S.totalenergy = (jl_sum([e_body[c] / esc_body[c] for c in S.cells]) + jl_sum([e_rad[c] / esc_rad[c] for c in S.cells])) + e_surface   # (:121)
 
@@ -295,10 +312,15 @@ def sourcing(S, tapes):
     if S.geometry == "1D":
         N = S.N
         n_left = n_right = 0
+        def surf_count(e, esc):
+            v = np.round(T(((e / esc) * n_source) / S.totalenergy))                                             # round(precision, x)
+            if not np.isfinite(v):
+                raise InexactError(f"tointeger({v!r})")
+            return int(v)
         if e_left > 0:
-            n_left = int(np.round(T(((e_left / esc_left) * n_source) / S.totalenergy)))                         # round(precision, x)  (:152)
+            n_left = surf_count(e_left, esc_left)                                                               # (:152)
         if e_right > 0:
-            n_right = int(np.round(T(((e_right / esc_right) * n_source) / S.totalenergy)))                      # (:156)
+            n_right = surf_count(e_right, esc_right)                                                            # (:156)
         for _ in range(n_left):                                                                                 # (:159-174)
             tp = next(tapes)
             xpos = T((F64(0.01) * S.w(1)) * ds)
@@ -358,6 +380,8 @@ def sourcing(S, tapes):
                 tp = next(tapes)
                 spawn = dt * tp.rand(T)
                 xpos = T((F64(0.001) * S.dx[0]) * ds)
+                if j > Nx:
+                    raise BoundsError("mesh.dx[j] with j > Nx (imc_sourcing.jl:301)")
                 ypos = (S.dx[j - 1] * tp.rand(T)) * ds                                                          # dx indexed by j (Q7)
                 mu = T(pi64 * (F64(0.5) - tp.rand(T)))
                 nrg = T(el[j]) / nl[j]
@@ -367,6 +391,8 @@ def sourcing(S, tapes):
                 tp = next(tapes)
                 spawn = dt * tp.rand(T)
                 xpos = T((F64(0.999) * S.dx[Nx - 1]) * ds)
+                if j > Nx:
+                    raise BoundsError("mesh.dx[j] with j > Nx (imc_sourcing.jl:316)")
                 ypos = (S.dx[j - 1] * tp.rand(T)) * ds
                 mu = T(pi64 * (F64(0.5) + tp.rand(T)))
                 nrg = T(er[j]) / nr[j]

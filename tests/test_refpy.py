@@ -70,8 +70,17 @@ def run_both(inputs, oracle_lib, steps, seed=0, n_batch=0):
         n_before = eng.num_particles()
         uni, _ = make_tapes(rng, T, 6000, n_exp=1)
         eng.set_source_tape(uni[:16])
-        src = eng.source(dt, sv.n_input, float(sv.cellmin), step)
-        refpy.sourcing(S, (refpy.Tape(uni[:16, j]) for j in range(uni.shape[1])))
+        source_tapes = (refpy.Tape(uni[:16, j]) for j in range(uni.shape[1]))
+        try:
+            src = eng.source(dt, sv.n_input, float(sv.cellmin), step)
+        except lib.ImcError as e:
+            if e.code != -6:
+                raise
+            with pytest.raises(refpy.ReferenceThrows):   # NaN / Inf particle count (tointeger) or no representable scale (emittedenergy[i, 0])
+                refpy.sourcing(S, source_tapes)
+            stats["reference_throws"] = step
+            return stats
+        refpy.sourcing(S, source_tapes)
         assert src["n_particles"] == len(S.particles), f"step {step}: {src['n_particles']} vs {len(S.particles)} particles after sourcing"
         assert src["totalenergy"] == float(S.totalenergy), f"step {step} totalenergy {src['totalenergy']!r} vs {float(S.totalenergy)!r}"
         same(eng.field("emittedenergy"), S.field_scaled(S.emittedenergy), f"step {step} emittedenergy")
@@ -224,3 +233,34 @@ def test_distance_scale(oracle_lib, precision, distancescale):
     d["PHYS_C"] = "2.7"
     st = run_both(d, oracle_lib, steps=3, seed=9, n_batch=60)
     assert st["events"][2] > 0
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_random_decks(oracle_lib, seed):
+    """The randomised decks of tests/test_gpu_fuzz.py (mesh shape and grading, boundary conditions, opacities and powers,
+    scattering, sources, energy scales, distance scale, c, dt, precision, PAIRWISE) at a small particle count."""
+    import test_gpu_fuzz as fuzz
+    global N_UNI, N_EXP
+    rng = np.random.default_rng(5000 + seed)
+    precision = ["FLOAT64", "FLOAT32", "FLOAT16"][seed % 3]
+    d = fuzz.random_2d(rng, precision) if seed % 4 != 3 else fuzz.random_1d(rng, precision)
+    d["NINPUT"] = str(int(rng.integers(40, 160)))
+    if d["GEOMETRY"] == "2D" and len(d["YMESHNODES"]) > len(d["XMESHNODES"]):
+        # left / right surface sources read mesh.dx[j] for j up to Ny (Q7): with Ny > Nx the reference throws BoundsError
+        # (imc_refpy raises it too; the engine and the C++ oracle read dy[j] there instead, DESIGN.md §2) — keep Ny <= Nx
+        d["XMESHNODES"], d["YMESHNODES"] = d["YMESHNODES"], d["XMESHNODES"]
+        (x1, x2, y1, y2), = d["T_SURFACE_REGS"]
+        d["T_SURFACE_REGS"] = [(y1, y2, x1, x2)]
+    if d["GEOMETRY"] == "1D":
+        d["CELLMIN"] = "0"                               # the 1-D decks have 100-1000 cells: no particle floor per cell
+    keep = N_UNI, N_EXP
+    N_UNI = N_EXP = 1536                                 # scattering-dominated decks make long histories
+    try:
+        st = run_both(d, oracle_lib, steps=2, seed=seed, n_batch=24)
+    except lib.ImcError as e:
+        if e.code != -5:
+            raise
+        pytest.skip("a history needs more draws than the tape holds")
+    finally:
+        N_UNI, N_EXP = keep
+    assert st["segments"] > 0 or "reference_throws" in st
