@@ -8,7 +8,9 @@
 //   - the one reference KAT that touches the path (clean: test/runtests.jl:78-87),
 //   - the deck-embedded Su-Olson benchmark curve (src/inputs/SuOlson.txt:71-72),
 //   - the analytic infinite-medium equilibrium and energy conservation (imc_energycheck.jl:34),
-// and by line-by-line reading of the Julia source, cited at each function.
+// and by line-by-line reading of the Julia source, cited at each function.  That reading is cross-checked
+// by a second restatement written separately in plain Python (oracle/imc_refpy.py; tests/test_refpy.py
+// requires the two to agree bit for bit, stage by stage, on replay tapes).
 // Julia's RNG stream and libm are not reproducible here: random numbers come from a tape
 // (replay) or from Philox (csrc/imc_rng.h); elementary functions come from a Math policy:
 // MathDet (csrc/imc_math.h, bit-identical to the GPU) or MathLibm (glibc, independent check).

@@ -144,7 +144,7 @@ class Tape:
 def sorter(vals, scales, T):
     """Utilities.sorter (imc_utilities.jl:23-54): pair the smallest with the largest factor, round every pair product to T."""
     for j, sc in enumerate(scales, start=1):
-        E = jtype(*vals, sc) if jtype(*vals, sc) is not None else None   # eltype of vcat(vals, scales[j])
+        E = jtype(*vals, sc)                          # eltype of vcat(vals, scales[j]); Int scales do not widen it
         s = sorted(E(v) for v in list(vals) + [sc])
         n = len(s)
         product = T(1.0)
