@@ -257,6 +257,15 @@ int imc_set_transport_tape(imc_handle h, const double* uniforms, int32_t n_uni,
                            const double* exponentials, int32_t n_exp, int64_t n_slots);
 int imc_set_source_tape(imc_handle h, const double* uniforms, int32_t n_uni, int64_t n_slots);
 
+/* Sourcing.sample_planck (imc_sourcing.jl:372-399): n frequencies h nu / k T drawn from the Planck spectrum with the
+ * Fleck-Cummings series method, in the deck precision.  The reference defines the function but every call site is
+ * commented out (grey transport, particle slot `frq` = 1.0: imc_sourcing.jl:171, :209, :342 ...), so nothing in the
+ * step uses it; it is exported for hosts that switch the frequency sampling on.  Sample i draws from its own Philox
+ * stream (seed, id = i, step) or, in replay mode, from slot i of the source tape.  The reference's loop does not
+ * terminate when the first draw exceeds the largest value 90 nsum / pi^4 can reach in the deck precision (Float32:
+ * 0.9999989); such a sample is returned as NaN after 100000 terms. */
+int imc_sample_planck(imc_handle h, int64_t n, int64_t step, double* out);
+
 /* per-particle outcome of the last imc_transport call, for replay checks:
  * event[i] = 0 census, 1 absorbed (energy cut-off), 2 escaped (VACUUM), 3 random-walk kill;
  * nseg[i] = segments tracked.  Indexed like the particle list before imc_clean. */

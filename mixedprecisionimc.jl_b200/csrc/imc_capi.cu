@@ -89,5 +89,6 @@ int imc_set_particles(imc_handle h, const double* s, const uint64_t* ids, int64_
 int imc_set_transport_tape(imc_handle h, const double* u, int32_t nu, const double* e, int32_t ne, int64_t slots) { GUARD(h->e->set_transport_tape(u, nu, e, ne, slots)); }
 int imc_set_source_tape(imc_handle h, const double* u, int32_t nu, int64_t slots) { GUARD(h->e->set_source_tape(u, nu, slots)); }
 int imc_get_outcomes(imc_handle h, int32_t* ev, int32_t* nseg, int64_t cap) { GUARD(h->e->get_outcomes(ev, nseg, cap)); }
+int imc_sample_planck(imc_handle h, int64_t n, int64_t step, double* out) { GUARD(h->e->sample_planck(n, step, out)); }
 
 }  // extern "C"

@@ -1065,6 +1065,24 @@ struct EngineT : EngineBase {
     st_nuni = nu; st_slots = slots;
     return IMC_OK;
   }
+  // ---- Sourcing.sample_planck (imc_sourcing.jl:372-399) --------------------------------------------------
+  int sample_planck(int64_t n, int64_t step, double* out) override {
+    IMC_RC(use_device());
+    if (n < 0 || (n > 0 && !out)) { err = "sample_planck: bad arguments"; return IMC_ERR_ARG; }
+    if (n == 0) return IMC_OK;
+    if (cfg.rng_mode == IMC_RNG_TAPE && n > st_slots) { err = "source tape has fewer slots than samples"; return IMC_ERR_TAPE; }
+    IMC_CK(stage.ensure((size_t)n));
+    IMC_CK(over_flag.ensure(2));
+    IMC_CK(cudaMemsetAsync(over_flag.p, 0, sizeof(unsigned long long), stream));
+    k_sample_planck<P><<<grid_for(n, 128), 128, 0, stream>>>(rng_args(step, true), n, stage.p, over_flag.p); ++n_launch;
+    IMC_CK(cudaGetLastError());
+    unsigned long long over = 0;
+    IMC_CK(cudaMemcpyAsync(out, stage.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaMemcpyAsync(&over, over_flag.p, sizeof over, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    if (over) { err = "source tape exhausted"; return IMC_ERR_TAPE; }
+    return IMC_OK;
+  }
   int get_outcomes(int32_t* ev, int32_t* nseg, int64_t capacity) override {
     IMC_RC(use_device());
     if (out_n == 0) { err = "no outcome record (population above 2^22 or no transport call yet)"; return IMC_ERR_STATE; }

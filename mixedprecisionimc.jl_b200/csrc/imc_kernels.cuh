@@ -1311,6 +1311,39 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
 }
 
 // ======================================================================================
+// Sourcing.sample_planck (imc_sourcing.jl:372-399) — thread per sample.  Unused by the reference's step (every call
+// site is commented out); exported through imc_sample_planck.
+// ======================================================================================
+constexpr int PLANCK_MAX_TERMS = 100000;   // the reference's loop has no exit when rn1 > max(90 nsum / pi^4): NaN by convention
+template <class P>
+__global__ void k_sample_planck(RngArgs r, long long n, double* __restrict__ out, unsigned long long* over_flag) {
+  using N = Num<P>;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Draw<P> d; d.init(r, (unsigned long long)i, STREAM_PLANCK, i);
+  const N one = N::from_d(1.0);
+  const double pi2 = 3.141592653589793 * 3.141592653589793, pi4 = pi2 * pi2;        // pi^4: power by squaring in Float64
+  N nn = one, nsum = one;                                                           // :382, :384
+  N rn1 = d.uniform();                                                              // :383
+  double res = nan("");
+  for (int it = 0; it < PLANCK_MAX_TERMS; ++it) {
+    if (rn1.d() <= (90.0 * nsum.d()) / pi4) {                                       // :388 (Float64 comparison)
+      rn1 = d.uniform();                                                            // :389-392
+      const N rn2 = d.uniform(), rn3 = d.uniform(), rn4 = d.uniform();
+      const N lg = MathDet::log<P>(((rn1 * rn2) * rn3) * rn4);
+      res = N::from_d((-1.0 * lg.d()) / nn.d()).d();                                // :393
+      break;
+    }
+    nn = nn + one;                                                                  // :396
+    // n^4: Float16 computes Float32(n)^4 and rounds once; n is a small integer, so every algorithm is exact in Float32 / Float64
+    const double n4 = P::id == 0 ? N::from_d((double)nn.v * nn.v * nn.v * nn.v).d() : ((nn * nn) * (nn * nn)).d();
+    nsum = nsum + N::from_d(1.0 / n4);                                              // :397
+  }
+  out[i] = res;
+  if (d.over()) atomicAdd(over_flag, 1ull);
+}
+
+// ======================================================================================
 // Clean.clean — stable compaction
 // ======================================================================================
 constexpr int COMPACT_THREADS = 512;

@@ -65,7 +65,7 @@ struct Philox {
   }
 };
 
-enum : uint32_t { STREAM_SOURCE = 0u, STREAM_TRACK = 1u, STREAM_TRACK_EXTRA = 2u };
+enum : uint32_t { STREAM_SOURCE = 0u, STREAM_TRACK = 1u, STREAM_TRACK_EXTRA = 2u, STREAM_PLANCK = 3u };
 
 // One particle's draw stream for one time step.  Words are consumed in order; a new Philox
 // block is generated every 4 words.  counter = (id_lo, id_hi, step, stream<<28 | block).

@@ -120,6 +120,14 @@ module Sourcing
     end
 end
 
+"""`Sourcing.sample_planck` (imc_sourcing.jl:372-399; every call site in the reference is commented out): n Planck-spectrum
+frequencies drawn by the engine in the deck precision."""
+function sample_planck(mesh, n::Integer)
+    out = Vector{Float64}(undef, n)
+    check(engine(mesh), ccall((:imc_sample_planck, libimc), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), engine(mesh), n, STEP[], out))
+    return eltype(mesh.matenergydens).(out)
+end
+
 module Transport
     import ..IMCB200: engine, check, libimc, TransportStats, STEP, PENDING_RW
     function run(mesh, simvars)

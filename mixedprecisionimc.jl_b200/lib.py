@@ -123,6 +123,7 @@ ABI = [
     ("imc_set_transport_tape", C.c_int, [C.c_void_p, _DP, C.c_int32, _DP, C.c_int32, C.c_int64]),
     ("imc_set_source_tape", C.c_int, [C.c_void_p, _DP, C.c_int32, C.c_int64]),
     ("imc_get_outcomes", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64]),
+    ("imc_sample_planck", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_double)]),
 ]
 
 
@@ -421,6 +422,12 @@ class Engine:
     def set_source_tape(self, uniforms: np.ndarray):
         u = np.ascontiguousarray(uniforms, dtype=np.float64)
         self._check(self.lib.dll.imc_set_source_tape(self._h, _dp(u), u.shape[0], u.shape[1]))
+
+    def sample_planck(self, n: int, step: int = 0) -> np.ndarray:
+        """``Sourcing.sample_planck`` (imc_sourcing.jl:372-399): n Planck-spectrum frequencies in the deck precision."""
+        out = np.empty(n, dtype=np.float64)
+        self._check(self.lib.dll.imc_sample_planck(self._h, n, step, _dp(out)))
+        return out
 
     def outcomes(self, n: int):
         ev = np.empty(n, dtype=np.int32); ns = np.empty(n, dtype=np.int32)

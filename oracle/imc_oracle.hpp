@@ -162,6 +162,7 @@ struct EngineBase {
   virtual int set_transport_tape(const double*, int, const double*, int, int64_t) = 0;
   virtual int set_source_tape(const double*, int, int64_t) = 0;
   virtual int get_outcomes(int32_t*, int32_t*, int64_t) = 0;
+  virtual int sample_planck(int64_t, int64_t, double*) = 0;
 };
 
 template <class P, class M>
@@ -1109,6 +1110,47 @@ struct Oracle : EngineBase {
   }
   int set_source_tape(const double* u, int nu, int64_t slots) override {
     st_uni.assign(u, u + (size_t)nu * slots); st_nuni = nu; st_slots = slots;
+    return IMC_OK;
+  }
+  // ---- Sourcing.sample_planck (imc_sourcing.jl:372-399): Fleck-Cummings series method.  Never called by the reference's
+  // step (call sites commented out at :171, :186, :209, :232, :342, :362).  Sample i draws from Philox stream
+  // (seed, id = i, step, STREAM_PLANCK) or from slot i of the source tape.
+  int sample_planck(int64_t n_samples, int64_t step, double* out) override {
+    if (n_samples < 0 || (n_samples > 0 && !out)) { err = "sample_planck: bad arguments"; return IMC_ERR_ARG; }
+    const bool tape = cfg.rng_mode == IMC_RNG_TAPE;
+    if (tape && n_samples > st_slots) { err = "source tape has fewer slots than samples"; return IMC_ERR_TAPE; }
+    bool over = false;
+    for (int64_t i = 0; i < n_samples; ++i) {
+      PhiloxDraw<P> ph; TapeDraw<P> tp;
+      if (tape) tp.init(st_uni.data(), st_nuni, nullptr, 0, (size_t)st_slots, (size_t)i);
+      else ph.init((uint64_t)cfg.seed, (uint64_t)i, (uint32_t)step, STREAM_PLANCK);
+      auto rnd = [&]() { return tape ? tp.uniform() : ph.uniform(); };
+      N n = N::from_d(1.0);                                   // :382
+      N rn1 = rnd();                                          // :383
+      N nsum = N::from_d(1.0);                                // :384
+      const double pi = 3.141592653589793;
+      const double pi_4 = (pi * pi) * (pi * pi);              // pi^4 -> Float64 power by squaring
+      double freq = std::nan("");
+      for (int terms = 0; terms < 100000; ++terms) {          // `while true` in the reference: see include/imc.h for the cap
+        if (rn1.d() <= 90.0 * nsum.d() / pi_4) {              // :388
+          rn1 = rnd();                                        // :389
+          N rn2 = rnd();                                      // :390
+          N rn3 = rnd();                                      // :391
+          N rn4 = rnd();                                      // :392
+          N l = M::template log<P>(rn1 * rn2 * rn3 * rn4);
+          freq = N::from_d(-1.0 * l.d() / n.d()).d();         // :393
+          break;
+        }
+        n = n + N::from_d(1.0);                               // :396
+        double n4;                                            // n^4 in T (Float16: through Float32, rounded once)
+        if constexpr (P::id == 0) { float f = (float)n.d(); n4 = N::from_d((double)(f * f * f * f)).d(); }
+        else { N sq = n * n; n4 = (sq * sq).d(); }
+        nsum = nsum + N::from_d(1.0 / n4);                    // :397
+      }
+      out[i] = freq;
+      if (tape && tp.exhausted()) over = true;
+    }
+    if (over) { err = "source tape exhausted"; return IMC_ERR_TAPE; }
     return IMC_OK;
   }
   int get_outcomes(int32_t* ev, int32_t* nseg, int64_t cap) override {

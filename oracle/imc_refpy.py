@@ -20,6 +20,7 @@ operation order, promotions, quirks Q1-Q32 of SURVEY.md §9.
 Reference functions restated (file:line of /root/reference/src):
   sorter            imc_utilities.jl:23-54        update   imc_update.jl:12-70      clean  imc_clean.jl:6-19
   sourcing          imc_sourcing.jl:12-370        tally    imc_tally.jl:11-149      energychecker imc_energycheck.jl:10-37
+  sample_planck     imc_sourcing.jl:372-399
   MC                imc_transport.jl:13-210       MC_RW    imc_transport.jl:212-479 MC2D   imc_transport.jl:483-732
   P_r / bisection / randomwalk_table              imc_transport.jl:734-797
 """
@@ -410,6 +411,24 @@ def sourcing(S, tapes):
                     mu = T((2 * pi64) * tp.rand(T))
                     spawn = dt * tp.rand(T)
                     new.append([spawn, T(i), T(j), xpos, ypos, mu, T(1.0), nrg, nrg, T(esc[c])])
+
+
+def sample_planck(T, tp, m, max_terms=100000):
+    """Sourcing.sample_planck (imc_sourcing.jl:372-399).  `while true` in the reference; a first draw above the largest
+    value 90 nsum / pi^4 reaches in T never leaves it — NaN after max_terms by the convention of include/imc.h."""
+    n = T(1.0)
+    rn1 = tp.rand(T)
+    nsum = T(1.0)
+    pi = F64(math.pi)
+    pi4 = (pi * pi) * (pi * pi)                       # pi^4: Float64 power by squaring
+    for _ in range(max_terms):
+        if rn1 <= F64(90.0) * nsum / pi4:                                                                       # (:388)
+            rn1 = tp.rand(T); rn2 = tp.rand(T); rn3 = tp.rand(T); rn4 = tp.rand(T)
+            return T(F64(-1.0) * m.log(rn1 * rn2 * rn3 * rn4) / n)                                              # (:393)
+        n = n + T(1.0)                                                                                          # (:396)
+        n4 = T(np.float32(n) ** 4) if T is np.float16 else (n * n) * (n * n)                                    # Float16: Float32(n)^4, rounded once
+        nsum = nsum + T(F64(1.0) / n4)                                                                          # (:397)
+    return T(np.nan)
 
 
 # ------------------------------------------------------------------------------------------------- imc_transport.jl

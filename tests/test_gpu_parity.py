@@ -336,3 +336,29 @@ def test_exact_tally_mode_with_many_records_per_cell(gpu_lib, oracle_lib, case, 
         assert ra["energy"] == rb["energy"]
     for name in FIELDS_EXACT + FIELDS_TALLIED + ("bee",):
         assert np.array_equal(a.engine.field(name), b.engine.field(name)), name
+
+
+@pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32", "FLOAT16"])
+def test_sample_planck_bit_exact(gpu_lib, oracle_lib, precision):
+    """Sourcing.sample_planck (imc_sourcing.jl:372-399; dormant in the reference): the device kernel
+    against the oracle on Philox draws and on a replay tape, including samples that need many series terms."""
+    T = {"FLOAT64": np.float64, "FLOAT32": np.float32, "FLOAT16": np.float16}[precision]
+    bits = {np.float16: 11, np.float32: 24, np.float64: 53}[T]
+    mk = lambda l, **kw: lib.Engine(lib.Config(precision=lib.PRECISION_IDS[np.dtype(T)], geometry=1, nx=4, seed=2024, **kw), l)
+    a, b = mk(gpu_lib), mk(oracle_lib)
+    ga, gb = a.sample_planck(200_000, step=5), b.sample_planck(200_000, step=5)
+    assert np.array_equal(ga, gb, equal_nan=True)
+    assert abs(ga[np.isfinite(ga)].mean() - 3.83223) < 0.05
+    rng = np.random.default_rng(3)
+    n = 3000
+    uni = rng.integers(0, 2 ** bits, size=(5, n)).astype(np.float64) * 2.0 ** -bits
+    uni[0, :64] = 1.0 - rng.integers(1, 200, size=64) * 2.0 ** -bits
+    uni[3, 100] = 0.0
+    a, b = mk(gpu_lib, rng_mode=lib.RNG_TAPE), mk(oracle_lib, rng_mode=lib.RNG_TAPE)
+    a.set_source_tape(uni); b.set_source_tape(uni)
+    ta, tb = a.sample_planck(n), b.sample_planck(n)
+    assert np.array_equal(ta, tb, equal_nan=True) and np.isinf(ta[100])
+    a.set_source_tape(uni[:2])
+    with pytest.raises(lib.ImcError) as e:
+        a.sample_planck(n)
+    assert e.value.code == -5

@@ -264,3 +264,54 @@ def test_random_decks(oracle_lib, seed):
     finally:
         N_UNI, N_EXP = keep
     assert st["segments"] > 0 or "reference_throws" in st
+
+
+# ---------------------------------------------------------------------------------------------- Sourcing.sample_planck
+def _planck_engine(oracle_lib, precision, **kw):
+    return lib.Engine(lib.Config(precision=lib.PRECISION_IDS[np.dtype(precision)], geometry=1, nx=4, seed=77, **kw), oracle_lib)
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32, np.float16])
+def test_sample_planck_on_a_tape(oracle_lib, T):
+    """Sourcing.sample_planck (imc_sourcing.jl:372-399), unused by the reference's step: both restatements on pre-drawn
+    numbers, including first draws so close to 1 that the series runs for many terms, zeros (log(0) -> Inf) and, in
+    Float32, a first draw the series can never reach (the reference would loop for ever: NaN by convention)."""
+    rng = np.random.default_rng(11)
+    n = 400
+    uni = rng.integers(0, 2 ** BITS[T], size=(5, n)).astype(np.float64) * 2.0 ** -BITS[T]
+    uni[0, :40] = 1.0 - rng.integers(1, 60, size=40) * 2.0 ** -BITS[T]      # largest rand(T) values
+    uni[2, 50] = 0.0
+    if T is np.float32:
+        uni[0, 0] = 1.0 - 2.0 ** -24
+    eng = _planck_engine(oracle_lib, T, rng_mode=lib.RNG_TAPE)
+    eng.set_source_tape(uni)
+    got = eng.sample_planck(n)
+    m = refpy.JuliaMath(oracle_lib.dll)
+    want = np.array([float(refpy.sample_planck(T, refpy.Tape(uni[:, i]), m)) for i in range(n)])
+    same(got, want, "sample_planck")
+    assert np.isinf(got[50]) and not np.isnan(got[40:]).any()       # Float16 products of four draws underflow to 0 now and then: Inf
+    if T is np.float32:
+        assert np.isnan(got[0])                                          # 1 - 2^-24 > 0.9999989 = the largest 90 nsum / pi^4 in Float32
+    with pytest.raises(lib.ImcError) as e:                                # the accepting branch needs four more draws
+        eng.set_source_tape(uni[:3]); eng.sample_planck(n)
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32, np.float16])
+def test_sample_planck_philox_and_spectrum(oracle_lib, T):
+    """Philox draws (stream 3 of sample i): the restatements agree, and the sample mean is the Planck mean
+    360 zeta(5) / pi^4 = 3.83223 (Fleck-Cummings series method)."""
+    eng = _planck_engine(oracle_lib, T)
+    n = 40000
+    got = eng.sample_planck(n, step=3)
+    f = oracle_lib.dll.imc_oracle_draws
+    f.restype = None
+    f.argtypes = [refpy.C.c_int32, refpy.C.c_int64, refpy.C.c_uint64, refpy.C.c_uint32, refpy.C.c_uint32, refpy.C.c_int32, refpy._DP, refpy.C.c_int64]
+    m = refpy.JuliaMath(oracle_lib.dll)
+    draws = np.empty(64)
+    for i in range(300):
+        f(lib.PRECISION_IDS[np.dtype(T)], 77, i, 3, 3, 0, draws.ctypes.data_as(refpy._DP), 64)
+        assert got[i] == float(refpy.sample_planck(T, refpy.Tape(draws), m, max_terms=50)) or np.isnan(got[i])
+    ok = np.isfinite(got)
+    assert ok.mean() > (0.999 if T is not np.float16 else 0.99)       # Float16: a product of four 11-bit draws underflows to 0 (-> Inf) in ~0.2 %
+    assert abs(got[ok].mean() - 3.83223) < (0.05 if T is not np.float16 else 0.08)
