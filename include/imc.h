@@ -204,7 +204,10 @@ int imc_step(imc_handle h, double t, double dt, int64_t n_input, double cellmin,
 /* The buffer a multi-GPU host must sum over ranks between imc_tally_local and imc_tally_finish:
  * [energydep Nc*Ns | radenergydens Nc | lostenergy | counters...], n elements of 8 bytes,
  * *is_int64 != 0 when the engine accumulates in fixed point (sum as int64), else Float64.
- * *ptr is a device pointer for the CUDA library, a host pointer for the oracle. */
+ * *ptr is a device pointer for the CUDA library, a host pointer for the oracle.
+ * The call waits for the engine's stream, i.e. for everything issued before it (the tracking kernel, imc_tally_local's
+ * census tally): a host that runs its collective on another stream calls it immediately before reducing each part —
+ * [energydep] may be reduced as soon as imc_transport has returned, the rest after imc_tally_local. */
 int imc_reduce_buffer(imc_handle h, void** ptr, int64_t* n, int32_t* is_int64);
 
 int imc_get_field(imc_handle h, int32_t field, double* dst, int64_t n);

@@ -61,6 +61,9 @@ def advance_sharded(sim: _driver.Simulation, group=None) -> dict:
         work = dist.all_reduce(buf[:n_dep], group=group, async_op=True)
         _driver.Clean.clean(parts)
         eng.tally_local()
+        # tally_local only enqueues the census tally on the engine's own stream, which the collective's stream does not
+        # know about: imc_reduce_buffer waits for that stream, so the tail is complete before it is reduced
+        eng.reduce_buffer()
         dist.all_reduce(buf[n_dep:], group=group)
         work.wait()
         torch.cuda.current_stream().synchronize()
