@@ -163,6 +163,7 @@ struct EngineT : EngineBase {
     }
     if (cfg.device < 0 || cfg.device >= ndev) { err = "bad device ordinal"; return IMC_ERR_ARG; }
     if (nc >= (1ll << 30)) { err = "mesh has 2^30 or more cells (cell and source-entry indices are 32-bit)"; return IMC_ERR_ARG; }
+    if (nc * ns >= (1ll << 31)) { err = "cells x energy scales reaches 2^31 (tally accumulator indices are 32-bit)"; return IMC_ERR_ARG; }
     IMC_CK(cudaSetDevice(cfg.device));
     cudaDeviceProp prop;
     IMC_CK(cudaGetDeviceProperties(&prop, cfg.device));
