@@ -86,6 +86,7 @@ def run_both(inputs, oracle_lib, steps, seed=0, n_batch=0):
         same(eng.field("emittedenergy"), S.field_scaled(S.emittedenergy), f"step {step} emittedenergy")
         same(eng.particles()[0], S.slots(), f"step {step} particles after sourcing")
         stats["sourced"] += len(S.particles) - n_before
+        stats.setdefault("scales", set()).update(float(p[-1]) for p in S.particles[n_before:])
         if step == 0 and n_batch:
             extra = edge_batch(rng, T, mesh, n_batch)
             slots = np.vstack([S.slots(), extra])
@@ -189,6 +190,18 @@ def test_marshak_surface_source_multiscale(oracle_lib, precision):
     assert st["sourced"] > 300
     st = run_both(decks.nonuniform_1d(precision=precision, n_input=150, n_max=3000), oracle_lib, steps=3, seed=4)
     assert st["sourced"] > 200
+
+
+@pytest.mark.parametrize("pairwise", ["FALSE", "TRUE"])
+def test_float16_scale_selection(oracle_lib, pairwise):
+    """Float16 with several ENERGYSCALES: sorter takes the largest scale whose product stays finite (Q29), so particles of
+    different scales coexist and every tally has one plane per scale (Q28) — the regime the scales exist for."""
+    d = decks.nonuniform_1d(precision="FLOAT16", n_input=150, n_max=3000, pairwise=pairwise)       # nine scales, 32768 ... 0.5
+    st = run_both(d, oracle_lib, steps=4, seed=21, n_batch=40)
+    assert len(st["scales"]) >= 2 and st["sourced"] > 300
+    d = decks.suolson(precision="FLOAT16", n_input=150, n_max=2000, pairwise=pairwise, energyscales=(32768.0, 1024.0, 32.0, 1.0))
+    st = run_both(d, oracle_lib, steps=4, seed=22, n_batch=40)
+    assert st["events"][0] > 0 and st["events"][1] > 0
 
 
 @pytest.mark.parametrize("precision", ["FLOAT64", "FLOAT32", "FLOAT16"])
