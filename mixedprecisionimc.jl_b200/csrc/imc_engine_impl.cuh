@@ -503,7 +503,8 @@ struct EngineT : EngineBase {
     k_exact_reduce<P><<<grid_for(nacc, 128), 128, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, pairwise, out); ++n_launch;
     if (R >= EXACT_WARP_MIN) {   // cells with many records: a warp per cell, same order of additions
       unsigned grid = (unsigned)std::min<long long>((nacc * 32 + 255) / 256, (long long)sm_count * 8);
-      k_exact_reduce_warp<P><<<grid, 256, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, pairwise, out); ++n_launch;
+      static const int skip_stagnant = getenv("IMC_EXACT_SKIP") ? atoi(getenv("IMC_EXACT_SKIP")) : 0;   // experimental, see warp_seq_add_skip
+      k_exact_reduce_warp<P><<<grid, 256, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, pairwise, skip_stagnant, out); ++n_launch;
     }
     if (pairwise && R >= EXACT_BLOCK_MIN) {   // very long pairwise segments: a block per cell, leaves in parallel
       unsigned grid = (unsigned)std::min<long long>(nacc, (long long)sm_count * 2);

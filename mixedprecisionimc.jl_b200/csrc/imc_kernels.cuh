@@ -1521,6 +1521,35 @@ __device__ __forceinline__ Num<P> warp_seq_add(Num<P> v, bool started, const uns
   }
   return v;
 }
+// The same chain with its stagnant stretches skipped (a Float16 sum stops moving once it dwarfs the deposits: 10^6 records
+// per source cell of the Su-Olson deck, a few thousand of which change the sum).  Every lane adds ITS OWN record to the
+// running value; if no lane's result differs from that value, the sequential chain over the block leaves it unchanged too
+// (each addition would see the same value), so the block is skipped; otherwise the chain jumps to the first record that
+// does change it and the remaining lanes are tested against the new value.  Same bits as warp_seq_add for any input
+// (scratch/f16_chain_shortcut.py checks the idea on the CPU).  EXPERIMENTAL: selected by IMC_EXACT_SKIP=1, off by default
+// until it has been run and timed on a GPU.
+template <class P>
+__device__ __forceinline__ Num<P> warp_seq_add_skip(Num<P> v, const unsigned* __restrict__ keys, const double* __restrict__ vals,
+                                                    long long first, long long last, int lane) {
+  using N = Num<P>;
+  for (long long base = first; base <= last; base += 32) {
+    const long long i = base + lane;
+    const bool have = i <= last;
+    double x = 0.0; bool wide = false;
+    if (have) { x = vals[i]; wide = keys && (keys[i] & 0x80000000u); }
+    int done = 0;                                        // records base .. base + done - 1 are accounted for
+    while (true) {
+      const N t = wide ? N::from_d(v.d() + x) : v + N::from_d(x);
+      const bool same = (t.v == v.v && signbit(t.v) == signbit(v.v)) || (t.v != t.v && v.v != v.v);
+      const unsigned m = __ballot_sync(IMC_FULL_MASK, have && lane >= done && !same);
+      if (m == 0u) break;                                // nothing left in this block moves the sum
+      const int j0 = __ffs(m) - 1;
+      v = N(__shfl_sync(IMC_FULL_MASK, t.v, j0));        // records done .. j0 - 1 leave v as it is, record j0 gives lane j0's t
+      done = j0 + 1;
+    }
+  }
+  return v;
+}
 // Julia Base.sum of vals[first..last] (jl_sum_serial's recursion, leaves summed by warp_seq_add); all lanes return the value
 template <class P>
 __device__ Num<P> warp_jl_sum(const double* __restrict__ vals, long long first, long long last, int lane) {
@@ -1552,7 +1581,7 @@ __device__ Num<P> warp_jl_sum(const double* __restrict__ vals, long long first, 
 }
 template <class P>
 __global__ void k_exact_reduce_warp(const unsigned* __restrict__ keys, const double* __restrict__ vals, const long long* __restrict__ start,
-                                    long long nacc, int pairwise, double* __restrict__ out) {
+                                    long long nacc, int pairwise, int skip_stagnant, double* __restrict__ out) {
   using N = Num<P>;
   const int lane = threadIdx.x & 31;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -1561,6 +1590,7 @@ __global__ void k_exact_reduce_warp(const unsigned* __restrict__ keys, const dou
     if (e - b < EXACT_WARP_MIN || exact_block_segment(e - b, pairwise)) continue;
     N v;
     if (pairwise) v = warp_jl_sum<P>(vals, b, e - 1, lane);
+    else if (skip_stagnant) v = warp_seq_add_skip<P>(N(), keys, vals, b, e - 1, lane);
     else v = warp_seq_add<P>(N(), true, keys, vals, b, e - 1, lane);   // v = zero(T); v += record ... (imc_transport.jl:101, :120)
     if (lane == 0) out[c] = v.d();
   }

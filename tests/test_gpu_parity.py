@@ -8,6 +8,8 @@ to the field's max; after the comparison the oracle's fields are copied into the
 so that the next step again starts from identical inputs and per-particle parity stays bit-exact.
 The EXACT tally mode needs no such synchronisation: see test_exact_tally_mode_*.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -362,3 +364,38 @@ def test_sample_planck_bit_exact(gpu_lib, oracle_lib, precision):
     with pytest.raises(lib.ImcError) as e:
         a.sample_planck(n)
     assert e.value.code == -5
+
+
+_SKIP_REDUCER_SNIPPET = r"""
+import sys
+import os
+
+import numpy as np
+sys.path.insert(0, "tests")
+import __graft_entry__ as entry
+from mpimc_b200 import decks, lib
+from test_gpu_parity import FIELDS_EXACT, FIELDS_TALLIED, assert_step_parity, run_pair
+g, o = lib.ImcLib(entry.LIB), lib.ImcLib(entry.ORACLE_LIB)
+cases = [("FLOAT16", decks.suolson(precision="FLOAT16", n_input=60000, n_max=400000, pairwise="FALSE")),
+         ("FLOAT16", decks.infinite_medium(precision="FLOAT16", n_input=30000, n_max=200000, pairwise="FALSE", randomwalk="TRUE", energyscales=(1024.0,))),
+         ("FLOAT32", decks.suolson(precision="FLOAT32", n_input=60000, n_max=400000, pairwise="FALSE"))]
+for precision, d in cases:
+    a, b, out = run_pair(d, g, o, steps=4, sync=False, tally_mode=lib.TALLY_EXACT)
+    assert_step_parity(a, b, out, precision)
+    for name in FIELDS_EXACT + FIELDS_TALLIED:
+        assert np.array_equal(a.engine.field(name), b.engine.field(name), equal_nan=True), (precision, name)
+print("stagnation-skip reducer: identical")
+"""
+
+
+@pytest.mark.skipif(os.environ.get("IMC_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental reducer (IMC_EXACT_SKIP=1, off by default): run with IMC_TEST_EXPERIMENTAL=1")
+def test_stagnation_skip_reducer_is_bit_exact(built):
+    """warp_seq_add_skip (sequential EXACT sums with their stagnant stretches skipped) against the oracle, in a process
+    that has IMC_EXACT_SKIP=1: Float16 Su-Olson (long stagnant chains), a Float16 random-walk deck (Float64 records mixed
+    in), and a Float32 deck (hardly any stagnation)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", _SKIP_REDUCER_SNIPPET], env=dict(os.environ, IMC_EXACT_SKIP="1"), capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=900)
+    assert r.returncode == 0 and "identical" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
