@@ -328,3 +328,27 @@ def test_sample_planck_philox_and_spectrum(oracle_lib, T):
     ok = np.isfinite(got)
     assert ok.mean() > (0.999 if T is not np.float16 else 0.99)       # Float16: a product of four 11-bit draws underflows to 0 (-> Inf) in ~0.2 %
     assert abs(got[ok].mean() - 3.83223) < (0.05 if T is not np.float16 else 0.08)
+
+
+REF_INPUTS = "/root/reference/src/inputs"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INPUTS), reason="reference decks not present (GPU box)")
+@pytest.mark.parametrize("fname,ninput", [("SuOlson.txt", "1000"), ("InfiniteMedium.txt", "400"), ("MarshakWave.txt", "400"), ("1DNonUniform.txt", "400"),
+                                          ("2DNonUniform.txt", "400"), ("CrookedPipe.txt", "1500")])
+def test_shipped_decks(oracle_lib, fname, ninput):
+    """The reference's own deck files (src/inputs/*.txt: parser, mesh generator and every stage) with the particle count
+    reduced to what Python loops can track; SuOlson.txt runs exactly as shipped (FLOAT16, NINPUT 1000).  Lattice.txt cannot
+    run in the reference either (Q21)."""
+    d = _deck.read_inputs(os.path.join(REF_INPUTS, fname))
+    d["NINPUT"] = ninput
+    if fname != "SuOlson.txt":
+        d["CELLMIN"] = "0" if fname == "CrookedPipe.txt" else d["CELLMIN"]       # 4982 cells x CELLMIN 10 otherwise
+    global N_UNI, N_EXP
+    keep = N_UNI, N_EXP
+    N_UNI = N_EXP = 1024
+    try:
+        st = run_both(d, oracle_lib, steps=3, seed=31)
+    finally:
+        N_UNI, N_EXP = keep
+    assert st["segments"] > 500
