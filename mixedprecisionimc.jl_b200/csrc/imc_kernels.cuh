@@ -16,6 +16,7 @@
 #pragma once
 #include "imc_device.cuh"
 #include "imc_fastdiv.cuh"
+#include "imc_warp_reduce.cuh"
 
 namespace imc {
 
@@ -1500,56 +1501,7 @@ __device__ Num<P> jl_sum_serial(const double* __restrict__ vals, long long first
 // coalesced, and handed to the chain by shuffles; every lane carries the same accumulator.
 constexpr int EXACT_WARP_MIN = 64;   // segments at least this long go to k_exact_reduce_warp
 __device__ __forceinline__ bool exact_block_segment(long long len, int pairwise);   // ... or, pairwise and very long, to k_exact_reduce_block
-// v (op)= vals[first..last] in order; `started` = v already holds a value (else v = vals[first] first).  wide records (bit 31 of
-// the key, MC_RW) are Float64 values added in Float64 and rounded; keys == nullptr: no wide records (census, pairwise leaves)
-template <class P>
-__device__ __forceinline__ Num<P> warp_seq_add(Num<P> v, bool started, const unsigned* __restrict__ keys, const double* __restrict__ vals,
-                                               long long first, long long last, int lane) {
-  using N = Num<P>;
-  for (long long base = first; base <= last; base += 32) {
-    const long long i = base + lane;
-    double x = 0.0; unsigned k = 0u;
-    if (i <= last) { x = vals[i]; if (keys) k = keys[i]; }
-    const int cnt = (int)(last - base + 1 < 32 ? last - base + 1 : 32);
-#pragma unroll 8
-    for (int j = 0; j < cnt; ++j) {
-      const double xj = __shfl_sync(IMC_FULL_MASK, x, j);
-      const unsigned kj = keys ? __shfl_sync(IMC_FULL_MASK, k, j) : 0u;
-      if (!started) { v = (kj & 0x80000000u) ? N::from_d(N().d() + xj) : N() + N::from_d(xj); started = true; }
-      else v = (kj & 0x80000000u) ? N::from_d(v.d() + xj) : v + N::from_d(xj);
-    }
-  }
-  return v;
-}
-// The same chain with its stagnant stretches skipped (a Float16 sum stops moving once it dwarfs the deposits: 10^6 records
-// per source cell of the Su-Olson deck, a few thousand of which change the sum).  Every lane adds ITS OWN record to the
-// running value; if no lane's result differs from that value, the sequential chain over the block leaves it unchanged too
-// (each addition would see the same value), so the block is skipped; otherwise the chain jumps to the first record that
-// does change it and the remaining lanes are tested against the new value.  Same bits as warp_seq_add for any input
-// (scratch/f16_chain_shortcut.py checks the idea on the CPU).  EXPERIMENTAL: selected by IMC_EXACT_SKIP=1, off by default
-// until it has been run and timed on a GPU.
-template <class P>
-__device__ __forceinline__ Num<P> warp_seq_add_skip(Num<P> v, const unsigned* __restrict__ keys, const double* __restrict__ vals,
-                                                    long long first, long long last, int lane) {
-  using N = Num<P>;
-  for (long long base = first; base <= last; base += 32) {
-    const long long i = base + lane;
-    const bool have = i <= last;
-    double x = 0.0; bool wide = false;
-    if (have) { x = vals[i]; wide = keys && (keys[i] & 0x80000000u); }
-    int done = 0;                                        // records base .. base + done - 1 are accounted for
-    while (true) {
-      const N t = wide ? N::from_d(v.d() + x) : v + N::from_d(x);
-      const bool same = (t.v == v.v && signbit(t.v) == signbit(v.v)) || (t.v != t.v && v.v != v.v);
-      const unsigned m = __ballot_sync(IMC_FULL_MASK, have && lane >= done && !same);
-      if (m == 0u) break;                                // nothing left in this block moves the sum
-      const int j0 = __ffs(m) - 1;
-      v = N(__shfl_sync(IMC_FULL_MASK, t.v, j0));        // records done .. j0 - 1 leave v as it is, record j0 gives lane j0's t
-      done = j0 + 1;
-    }
-  }
-  return v;
-}
+// warp_seq_add / warp_seq_add_skip: imc_warp_reduce.cuh
 // Julia Base.sum of vals[first..last] (jl_sum_serial's recursion, leaves summed by warp_seq_add); all lanes return the value
 template <class P>
 __device__ Num<P> warp_jl_sum(const double* __restrict__ vals, long long first, long long last, int lane) {

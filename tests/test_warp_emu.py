@@ -1,0 +1,84 @@
+"""Warp-cooperative device code checked on the CPU: csrc/imc_warp_reduce.cuh (the sequential EXACT-tally chains, among
+them the experimental warp_seq_add_skip) is compiled for the host with __ballot_sync / __shfl_sync / __ffs emulated by 32
+threads in lockstep (tests/warp_emu/warp_emu.h) and must reproduce a plain `v += record` loop bit for bit."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(entry.ROOT, "build", "warp_emu", "libwarp_reduce_host.so")
+SRC = os.path.join(HERE, "warp_emu", "warp_reduce_host.cpp")
+DEPS = [SRC, os.path.join(HERE, "warp_emu", "warp_emu.h"), os.path.join(entry.CSRC, "imc_warp_reduce.cuh"), os.path.join(entry.CSRC, "imc_num.h")]
+T = {0: np.float16, 1: np.float32, 2: np.float64}
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mf16c", "-pthread",
+                        "-I" + entry.CSRC, "-I" + os.path.join(entry.ROOT, "include"), "-I" + os.path.join(HERE, "warp_emu"), "-o", OUT, SRC], check=True)
+    dll = C.CDLL(OUT)
+    up, dp = C.POINTER(C.c_uint32), C.POINTER(C.c_double)
+    dll.warp_reduce_host.restype = C.c_double
+    dll.warp_reduce_host.argtypes = [C.c_int, C.c_int, C.c_double, up, dp, C.c_longlong]
+    dll.plain_chain.restype = C.c_double
+    dll.plain_chain.argtypes = [C.c_int, C.c_double, up, dp, C.c_longlong]
+
+    def run(prec, v0, vals, keys=None):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        kp = None
+        if keys is not None:
+            keys = np.ascontiguousarray(keys, dtype=np.uint32); kp = keys.ctypes.data_as(up)
+        a = [dll.warp_reduce_host(w, prec, v0, kp, vals.ctypes.data_as(dp), len(vals)) for w in (0, 1)]
+        return a[0], a[1], dll.plain_chain(prec, v0, kp, vals.ctypes.data_as(dp), len(vals))
+    return run
+
+
+def bits(x):
+    return np.float64(x).tobytes()
+
+
+@pytest.mark.parametrize("prec", [0, 1, 2])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 64, 100, 257])
+def test_chains_of_every_length(emu, prec, n):
+    rng = np.random.default_rng(100 * prec + n)
+    vals = (rng.normal(size=n) * 10.0 ** rng.integers(-4, 3, size=n)).astype(T[prec]).astype(np.float64)
+    seq, skip, plain = emu(prec, 0.0, vals)
+    assert bits(seq) == bits(plain) and bits(skip) == bits(plain)
+    seq, skip, plain = emu(prec, float(T[prec](3.25)), vals)
+    assert bits(seq) == bits(plain) and bits(skip) == bits(plain)
+
+
+def test_stagnating_float16_sum(emu):
+    """The case the skipping chain exists for: thousands of small deposits into a Float16 sum that soon stops moving."""
+    rng = np.random.default_rng(7)
+    vals = (rng.random(20000) ** 3 * 0.004).astype(np.float16).astype(np.float64)
+    seq, skip, plain = emu(0, 0.0, vals)
+    assert bits(seq) == bits(plain) and bits(skip) == bits(plain)
+    assert 1.0 < plain < vals.sum() * 0.6                    # the Float16 sum has stagnated far below the exact one
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+def test_special_values_and_wide_records(emu, prec):
+    """Signed zeros, negative deposits, Inf / NaN, and MC_RW's Float64 records (bit 31 of the key) mixed in."""
+    rng = np.random.default_rng(9 + prec)
+    n = 300
+    vals = (rng.normal(size=n) * 10.0 ** rng.integers(-6, 2, size=n)).astype(T[prec]).astype(np.float64)
+    keys = np.where(rng.random(n) < 0.3, 0x80000000, 0).astype(np.uint32) | 5
+    wide = (keys & 0x80000000) != 0
+    vals[wide] = rng.normal(size=int(wide.sum())) * 1e-3     # Float64 values that are not representable in T
+    for special in ([], [(10, -0.0)], [(0, -0.0), (1, -0.0)], [(50, np.inf)], [(50, np.inf), (200, -np.inf)], [(120, np.nan)]):
+        v = vals.copy()
+        for i, x in special:
+            v[i] = x
+        seq, skip, plain = emu(prec, 0.0, v, keys)
+        assert bits(seq) == bits(plain) or (np.isnan(seq) and np.isnan(plain)), special
+        assert bits(skip) == bits(plain) or (np.isnan(skip) and np.isnan(plain)), special
+    seq, skip, plain = emu(prec, -0.0, np.array([-0.0, -0.0, 0.0, -0.0]))
+    assert bits(seq) == bits(plain) == bits(skip)
