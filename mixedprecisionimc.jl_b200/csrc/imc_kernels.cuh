@@ -1502,35 +1502,7 @@ __device__ Num<P> jl_sum_serial(const double* __restrict__ vals, long long first
 constexpr int EXACT_WARP_MIN = 64;   // segments at least this long go to k_exact_reduce_warp
 __device__ __forceinline__ bool exact_block_segment(long long len, int pairwise);   // ... or, pairwise and very long, to k_exact_reduce_block
 // warp_seq_add / warp_seq_add_skip: imc_warp_reduce.cuh
-// Julia Base.sum of vals[first..last] (jl_sum_serial's recursion, leaves summed by warp_seq_add); all lanes return the value
-template <class P>
-__device__ Num<P> warp_jl_sum(const double* __restrict__ vals, long long first, long long last, int lane) {
-  using N = Num<P>;
-  struct Frame { long long first, last; int state; N v1; };
-  Frame st[48];
-  int sp = 0;
-  st[sp++] = {first, last, 0, N()};
-  N ret;
-  while (sp > 0) {
-    Frame& f = st[sp - 1];
-    if (f.state == 0) {
-      if (f.last - f.first < 1024) {   // one element, or a sequential leaf: v = A[first] + A[first+1]; v += A[i] ...
-        const double x0 = vals[f.first];
-        ret = f.first == f.last ? N::from_d(x0) : warp_seq_add<P>(N::from_d(x0), true, nullptr, vals, f.first + 1, f.last, lane);
-        --sp;
-      } else {
-        long long mid = f.first + ((f.last - f.first) >> 1);
-        f.state = 1;
-        st[sp++] = {f.first, mid, 0, N()};
-      }
-    } else if (f.state == 1) {
-      f.v1 = ret; f.state = 2;
-      long long mid = f.first + ((f.last - f.first) >> 1);
-      st[sp++] = {mid + 1, f.last, 0, N()};
-    } else { ret = f.v1 + ret; --sp; }
-  }
-  return ret;
-}
+// warp_jl_sum: imc_warp_reduce.cuh
 template <class P>
 __global__ void k_exact_reduce_warp(const unsigned* __restrict__ keys, const double* __restrict__ vals, const long long* __restrict__ start,
                                     long long nacc, int pairwise, int skip_stagnant, double* __restrict__ out) {

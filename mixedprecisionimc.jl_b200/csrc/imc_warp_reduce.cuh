@@ -63,4 +63,34 @@ __device__ __forceinline__ Num<P> warp_seq_add_skip(Num<P> v, const unsigned* __
   return v;
 }
 
+// Julia Base.sum of vals[first..last] (jl_sum_serial's recursion, leaves summed by warp_seq_add); all lanes return the value
+template <class P>
+__device__ inline Num<P> warp_jl_sum(const double* __restrict__ vals, long long first, long long last, int lane) {
+  using N = Num<P>;
+  struct Frame { long long first, last; int state; N v1; };
+  Frame st[48];
+  int sp = 0;
+  st[sp++] = {first, last, 0, N()};
+  N ret;
+  while (sp > 0) {
+    Frame& f = st[sp - 1];
+    if (f.state == 0) {
+      if (f.last - f.first < 1024) {   // one element, or a sequential leaf: v = A[first] + A[first+1]; v += A[i] ...
+        const double x0 = vals[f.first];
+        ret = f.first == f.last ? N::from_d(x0) : warp_seq_add<P>(N::from_d(x0), true, nullptr, vals, f.first + 1, f.last, lane);
+        --sp;
+      } else {
+        long long mid = f.first + ((f.last - f.first) >> 1);
+        f.state = 1;
+        st[sp++] = {f.first, mid, 0, N()};
+      }
+    } else if (f.state == 1) {
+      f.v1 = ret; f.state = 2;
+      long long mid = f.first + ((f.last - f.first) >> 1);
+      st[sp++] = {mid + 1, f.last, 0, N()};
+    } else { ret = f.v1 + ret; --sp; }
+  }
+  return ret;
+}
+
 }  // namespace imc

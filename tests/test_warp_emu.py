@@ -29,6 +29,8 @@ def emu():
     dll.warp_reduce_host.argtypes = [C.c_int, C.c_int, C.c_double, up, dp, C.c_longlong]
     dll.plain_chain.restype = C.c_double
     dll.plain_chain.argtypes = [C.c_int, C.c_double, up, dp, C.c_longlong]
+    dll.plain_jl_sum.restype = C.c_double
+    dll.plain_jl_sum.argtypes = [C.c_int, dp, C.c_longlong]
 
     def run(prec, v0, vals, keys=None):
         vals = np.ascontiguousarray(vals, dtype=np.float64)
@@ -37,6 +39,11 @@ def emu():
             keys = np.ascontiguousarray(keys, dtype=np.uint32); kp = keys.ctypes.data_as(up)
         a = [dll.warp_reduce_host(w, prec, v0, kp, vals.ctypes.data_as(dp), len(vals)) for w in (0, 1)]
         return a[0], a[1], dll.plain_chain(prec, v0, kp, vals.ctypes.data_as(dp), len(vals))
+
+    def pairwise(prec, vals):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        return (dll.warp_reduce_host(2, prec, 0.0, None, vals.ctypes.data_as(dp), len(vals)), dll.plain_jl_sum(prec, vals.ctypes.data_as(dp), len(vals)))
+    run.pairwise = pairwise
     return run
 
 
@@ -82,3 +89,13 @@ def test_special_values_and_wide_records(emu, prec):
         assert bits(skip) == bits(plain) or (np.isnan(skip) and np.isnan(plain)), special
     seq, skip, plain = emu(prec, -0.0, np.array([-0.0, -0.0, 0.0, -0.0]))
     assert bits(seq) == bits(plain) == bits(skip)
+
+
+@pytest.mark.parametrize("prec", [0, 1, 2])
+@pytest.mark.parametrize("n", [1, 2, 33, 1023, 1024, 1025, 2049, 4100])
+def test_pairwise_sum_by_a_warp(emu, prec, n):
+    """warp_jl_sum (PAIRWISE = TRUE: Julia's sum(vector), imc_transport.jl:202) against the plain recursion."""
+    rng = np.random.default_rng(7 * prec + n)
+    vals = (rng.random(n) * 10.0 ** rng.integers(-3, 2, size=n)).astype(T[prec]).astype(np.float64)
+    got, want = emu.pairwise(prec, vals)
+    assert bits(got) == bits(want)

@@ -11,20 +11,36 @@ static double run(int which, double v0, const unsigned* keys, const double* vals
   return warp_emu::run_warp<double>([&](int lane) {
     N v = N::from_d(v0);
     if (which == 0) v = warp_seq_add<P>(v, true, keys, vals, 0, n - 1, lane);
-    else v = warp_seq_add_skip<P>(v, keys, vals, 0, n - 1, lane);
+    else if (which == 1) v = warp_seq_add_skip<P>(v, keys, vals, 0, n - 1, lane);
+    else v = warp_jl_sum<P>(vals, 0, n - 1, lane);          // Julia's pairwise sum(vals); v0 and keys unused
     return v.d();
   });
 }
 
+// Base.sum over a vector (mapreduce_impl: sequential below 1024 elements, else split in halves), written as the recursion it is
+template <class P>
+static Num<P> jl_rec(const double* a, long long first, long long last) {
+  using N = Num<P>;
+  if (first == last) return N::from_d(a[first]);
+  if (last - first < 1024) {
+    N v = N::from_d(a[first]) + N::from_d(a[first + 1]);
+    for (long long i = first + 2; i <= last; ++i) v = v + N::from_d(a[i]);
+    return v;
+  }
+  const long long mid = first + ((last - first) >> 1);
+  return jl_rec<P>(a, first, mid) + jl_rec<P>(a, mid + 1, last);
+}
+
 extern "C" {
-// which: 0 = warp_seq_add (the chain as the kernels have always run it), 1 = warp_seq_add_skip; prec: 0 F16, 1 F32, 2 F64
+// which: 0 = warp_seq_add (the chain as the kernels have always run it), 1 = warp_seq_add_skip, 2 = warp_jl_sum;
+// prec: 0 F16, 1 F32, 2 F64
 double warp_reduce_host(int which, int prec, double v0, const unsigned* keys, const double* vals, long long n) {
   if (n <= 0) return v0;
   if (prec == 0) return run<F16>(which, v0, keys, vals, n);
   if (prec == 1) return run<F32>(which, v0, keys, vals, n);
   return run<F64>(which, v0, keys, vals, n);
 }
-// the plain loop both must reproduce: v += record, in order (wide records are added in Float64 and rounded)
+// the plain loop the two chains must reproduce: v += record, in order (wide records are added in Float64 and rounded)
 double plain_chain(int prec, double v0, const unsigned* keys, const double* vals, long long n) {
   auto go = [&](auto tag) {
     using P = decltype(tag); using N = Num<P>;
@@ -35,5 +51,11 @@ double plain_chain(int prec, double v0, const unsigned* keys, const double* vals
   if (prec == 0) return go(F16{});
   if (prec == 1) return go(F32{});
   return go(F64{});
+}
+// the plain recursion warp_jl_sum must reproduce
+double plain_jl_sum(int prec, const double* vals, long long n) {
+  if (prec == 0) return jl_rec<F16>(vals, 0, n - 1).d();
+  if (prec == 1) return jl_rec<F32>(vals, 0, n - 1).d();
+  return jl_rec<F64>(vals, 0, n - 1).d();
 }
 }
