@@ -335,7 +335,7 @@ REF_INPUTS = "/root/reference/src/inputs"
 
 @pytest.mark.skipif(not os.path.isdir(REF_INPUTS), reason="reference decks not present (GPU box)")
 @pytest.mark.parametrize("fname,ninput", [("SuOlson.txt", "1000"), ("InfiniteMedium.txt", "400"), ("MarshakWave.txt", "400"), ("1DNonUniform.txt", "400"),
-                                          ("2DNonUniform.txt", "400"), ("CrookedPipe.txt", "1500")])
+                                          ("2DNonUniform.txt", "1500"), ("CrookedPipe.txt", "1500")])
 def test_shipped_decks(oracle_lib, fname, ninput):
     """The reference's own deck files (src/inputs/*.txt: parser, mesh generator and every stage) with the particle count
     reduced to what Python loops can track; SuOlson.txt runs exactly as shipped (FLOAT16, NINPUT 1000).  Lattice.txt cannot
@@ -343,7 +343,7 @@ def test_shipped_decks(oracle_lib, fname, ninput):
     d = _deck.read_inputs(os.path.join(REF_INPUTS, fname))
     d["NINPUT"] = ninput
     if fname != "SuOlson.txt":
-        d["CELLMIN"] = "0" if fname == "CrookedPipe.txt" else d["CELLMIN"]       # 4982 cells x CELLMIN 10 otherwise
+        d["CELLMIN"] = "0" if fname in ("CrookedPipe.txt", "2DNonUniform.txt") else d["CELLMIN"]   # thousands of cells x CELLMIN otherwise
     global N_UNI, N_EXP
     keep = N_UNI, N_EXP
     N_UNI = N_EXP = 1024
