@@ -202,13 +202,19 @@ int imc_step(imc_handle h, double t, double dt, int64_t n_input, double cellmin,
              imc_source_stats* src, imc_transport_stats* trk, imc_tally_stats* tal, imc_energy_stats* chk);
 
 /* The buffer a multi-GPU host must sum over ranks between imc_tally_local and imc_tally_finish:
- * [energydep Nc*Ns | radenergydens Nc | lostenergy | counters...], n elements of 8 bytes,
- * *is_int64 != 0 when the engine accumulates in fixed point (sum as int64), else Float64.
- * *ptr is a device pointer for the CUDA library, a host pointer for the oracle.
+ * [energydep Nc*Ns | radenergydens Nc | lostenergy | counters...], n slots of 8 bytes.  *kind says how to sum them:
+ *   0  Float64 throughout;
+ *   1  int64 throughout (the engine accumulates in fixed point: FIXED tallies);
+ *   2  the [energydep] region holds Nc*Ns Float32 accumulators in its first 4*Nc*Ns bytes (Float16 / Float32 decks with
+ *      ATOMIC tallies in global memory: deposits accumulate in Float32, as the reference's `energydep[cell] += dep`
+ *      does in the deck precision, imc_transport.jl:120) — sum those as Float32 — and the tail, at byte offset
+ *      8*Nc*Ns, is Float64.
+ * The kind follows from the deck, the mesh size and the tally mode alone, so it is the same on every rank.
+ * *ptr is a device pointer for the CUDA library, a host pointer for the oracle (always kind 0).
  * The call waits for the engine's stream, i.e. for everything issued before it (the tracking kernel, imc_tally_local's
  * census tally): a host that runs its collective on another stream calls it immediately before reducing each part —
  * [energydep] may be reduced as soon as imc_transport has returned, the rest after imc_tally_local. */
-int imc_reduce_buffer(imc_handle h, void** ptr, int64_t* n, int32_t* is_int64);
+int imc_reduce_buffer(imc_handle h, void** ptr, int64_t* n, int32_t* kind);
 
 int imc_get_field(imc_handle h, int32_t field, double* dst, int64_t n);
 /* overwrite mesh.temp (and optionally matenergydens when non-NULL): lets a host restart from saved fields */

@@ -93,6 +93,9 @@ struct EngineT : EngineBase {
   DBuf<double> red;
   long long red_n = 0;
   bool red_fixed = false;
+  DBuf<float> dep_strided;   // experiment (IMC_DEP_STRIDE > 2)
+  bool dep_f32 = false;   // the [energydep] region holds Float32 accumulators (its first nc*ns 4-byte words): Float16 / Float32 decks,
+                          // ATOMIC tallies in global memory, Philox history kernels (Tally::add)
   double fx_mul_dep = 1, fx_mul_rad = 1, fx_mul_lost = 1;
   // sourcing scratch
   SrcLayout L;
@@ -291,6 +294,7 @@ struct EngineT : EngineBase {
     if (geom == 1) IMC_CK(cp1.alloc(nc)); else IMC_CK(cp2.alloc(nc));
     red_n = nc * ns + nc + RB_NSCALARS;
     IMC_CK(red.alloc(red_n));
+    if (IMC_DEP_STRIDE > 2) IMC_CK(dep_strided.alloc((size_t)nc * ns * IMC_DEP_STRIDE));   // experiment
     // sourcing / tally scratch
     long long M = L.total();
     IMC_CK(src_e.alloc(M)); IMC_CK(src_q.alloc(M)); IMC_CK(src_nrg.alloc(M)); IMC_CK(src_ks.alloc(M)); IMC_CK(src_cnt.alloc(M));
@@ -481,10 +485,14 @@ struct EngineT : EngineBase {
     size_t per = mode == IMC_TALLY_FIXED ? 8 : sizeof(typename AccType<P>::type);
     return (size_t)nacc * per;
   }
-  // accumulator sets per block: as many as fit in 48 KB, at most one per warp of the block (a power of two)
-  static int smem_copies(size_t one_set) {
+  // Dynamic shared memory of a launch stays within the 48 KB every kernel may request without an opt-in: `reserved` bytes
+  // (the tracking kernels' counter slots, COUNTER_SMEM_BYTES) plus the accumulator sets.
+  static constexpr size_t SMEM_LIMIT = 48 * 1024;
+  static bool smem_fits(size_t one_set, size_t reserved) { return one_set + reserved <= SMEM_LIMIT; }
+  // accumulator sets per block: as many as fit, at most one per warp of the block (a power of two)
+  static int smem_copies(size_t one_set, size_t reserved) {
     int c = 1;
-    while (c < TRACK_THREADS / 32 && one_set * (size_t)(2 * c) <= 48 * 1024) c *= 2;
+    while (c < TRACK_THREADS / 32 && one_set * (size_t)(2 * c) + reserved <= SMEM_LIMIT) c *= 2;
     return c;
   }
 
@@ -591,9 +599,14 @@ struct EngineT : EngineBase {
     a.tally.pass = 0; a.tally.rec_cnt = nullptr; a.tally.rec_off = nullptr; a.tally.rec_key = nullptr; a.tally.rec_val = nullptr; a.tally.lost_val = nullptr;
     if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
     size_t smem = smem_for(mode, nc * ns);
-    a.tally.use_smem = (smem <= 48 * 1024 && mode != IMC_TALLY_EXACT) ? 1 : 0;
-    a.tally.copies = a.tally.use_smem ? smem_copies(smem) : 1;
+    a.tally.use_smem = (smem_fits(smem, COUNTER_SMEM_BYTES) && mode != IMC_TALLY_EXACT) ? 1 : 0;
+    a.tally.copies = a.tally.use_smem ? smem_copies(smem, COUNTER_SMEM_BYTES) : 1;
     smem = a.tally.use_smem ? smem * a.tally.copies : 0;
+    // decided from the deck and the mesh alone, so that every rank of a multi-GPU run reduces the same element type
+    dep_f32 = IMC_DEP_F32 && P::id != 2 && mode == IMC_TALLY_ATOMIC && !a.tally.use_smem;
+    a.tally.dep_f32 = dep_f32 ? 1 : 0;
+    a.tally.g_dep32 = IMC_DEP_STRIDE > 2 ? dep_strided.p : reinterpret_cast<float*>(red.p);
+    if (IMC_DEP_STRIDE > 2 && dep_f32) IMC_CK(cudaMemsetAsync(dep_strided.p, 0, (size_t)nc * ns * IMC_DEP_STRIDE * sizeof(float), stream));
     // outcome records for replay checks (small populations only)
     bool record = n_part <= (1ll << 22);
     if (record) {
@@ -642,7 +655,7 @@ struct EngineT : EngineBase {
     a.refill_min = refill_min_env();
     if (n_part > 0) {
       int blocks_per_sm = 2048 / TRACK_THREADS;
-      if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / smem));
+      if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / (smem + COUNTER_SMEM_BYTES)));
       unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
       IMC_CK(cudaEventRecord(ev0, stream));
       if (mode == IMC_TALLY_EXACT) {
@@ -661,8 +674,9 @@ struct EngineT : EngineBase {
           if (mode == IMC_TALLY_FIXED && !red_fixed) { IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream)); red_fixed = true; }
           a.tally.mode = mode; a.tally.pass = 0;
           if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
-          smem = smem_for(mode, nc * ns); a.tally.use_smem = smem <= 48 * 1024 ? 1 : 0;
-          a.tally.copies = a.tally.use_smem ? smem_copies(smem) : 1; smem = a.tally.use_smem ? smem * a.tally.copies : 0;
+          smem = smem_for(mode, nc * ns); a.tally.use_smem = smem_fits(smem, COUNTER_SMEM_BYTES) ? 1 : 0;
+          a.tally.copies = a.tally.use_smem ? smem_copies(smem, COUNTER_SMEM_BYTES) : 1; smem = a.tally.use_smem ? smem * a.tally.copies : 0;
+          dep_f32 = IMC_DEP_F32 && P::id != 2 && mode == IMC_TALLY_ATOMIC && !a.tally.use_smem; a.tally.dep_f32 = dep_f32 ? 1 : 0;
           IMC_RC(launch_track(a, variant, grid, smem));
         } else {
           for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)std::max<long long>(R, 1))); IMC_CK(rec_val[b].ensure((size_t)std::max<long long>(R, 1))); }
@@ -758,7 +772,7 @@ struct EngineT : EngineBase {
     IMC_CK(cudaMemsetAsync(red.p + rb_rad0(), 0, nc * sizeof(double), stream));
     if (n_part == 0) return IMC_OK;
     TallyArgs ta;
-    ta.pass = 0; ta.rec_cnt = nullptr; ta.rec_off = nullptr; ta.rec_key = nullptr; ta.rec_val = nullptr; ta.lost_val = nullptr;
+    ta.pass = 0; ta.rec_cnt = nullptr; ta.rec_off = nullptr; ta.rec_key = nullptr; ta.rec_val = nullptr; ta.lost_val = nullptr; ta.dep_f32 = 0; ta.g_dep32 = nullptr;
     if (mode == IMC_TALLY_EXACT) {  // per-cell vectors + Julia sum, in particle order (imc_tally.jl:84-113, Q19)
       for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)n_part)); IMC_CK(rec_val[b].ensure((size_t)n_part)); }
       ta.mode = mode; ta.nacc = (int)nc; ta.use_smem = 0; ta.copies = 1; ta.g_acc = nullptr; ta.g_fx = nullptr; ta.fx_mul = 1; ta.fx_mul_lost = 1; ta.sc0 = 0;
@@ -771,8 +785,8 @@ struct EngineT : EngineBase {
     if (mode == IMC_TALLY_FIXED && fx_mul_rad == 1) IMC_RC(prepare_fixed(ta));
     ta.fx_mul = fx_mul_rad; ta.fx_mul_lost = fx_mul_lost; ta.sc0 = 0;
     size_t smem = smem_for(mode, nc);
-    ta.use_smem = smem <= 48 * 1024 ? 1 : 0;
-    ta.copies = ta.use_smem ? smem_copies(smem) : 1;
+    ta.use_smem = smem_fits(smem, 0) ? 1 : 0;
+    ta.copies = ta.use_smem ? smem_copies(smem, 0) : 1;
     smem = ta.use_smem ? smem * ta.copies : 0;
     int blocks_per_sm = 2048 / TRACK_THREADS;
     unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
@@ -783,9 +797,8 @@ struct EngineT : EngineBase {
   int tally_finish(double t_, double dt_, imc_tally_stats* out) override {
     if (!have_mesh) { err = "tally before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
-    const long long* fx = reinterpret_cast<const long long*>(red.p);
-    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>(red.p + rb_dep0(), fx + rb_dep0(), red_fixed, fx_mul_dep, nc * ns, energydep.p); ++n_launch;
-    k_acc_to_field<P><<<grid_for(nc, 256), 256, 0, stream>>>(red.p + rb_rad0(), fx + rb_rad0(), red_fixed, fx_mul_rad, nc, radenergydens.p); ++n_launch;
+    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>((IMC_DEP_STRIDE > 2 && dep_f32 && !red_fixed) ? reinterpret_cast<double*>(dep_strided.p) : red.p + rb_dep0(), red_fixed ? 1 : (dep_f32 ? 2 : 0), fx_mul_dep, nc * ns, energydep.p); ++n_launch;
+    k_acc_to_field<P><<<grid_for(nc, 256), 256, 0, stream>>>(red.p + rb_rad0(), red_fixed ? 1 : 0, fx_mul_rad, nc, radenergydens.p); ++n_launch;
     TallyScratch<P> s; s.q_dep = q_dep.p; s.q_tot = q_tot.p; s.q_rad = q_rad.p;
     k_tally_finish<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, s, P::from_d(dt_), t_ == 0.0 ? 1 : 0, cfg.linearized, temp_wide ? 1 : 0); ++n_launch;
     IMC_CK(cudaGetLastError());
@@ -850,7 +863,7 @@ struct EngineT : EngineBase {
     if (!have_mesh) { err = "reduce_buffer before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     IMC_CK(cudaStreamSynchronize(stream));  // the host's collective runs on another stream
-    *ptr = red.p; *n = red_n; *is_int = red_fixed ? 1 : 0;
+    *ptr = red.p; *n = red_n; *is_int = red_fixed ? 1 : (dep_f32 ? 2 : 0);
     return IMC_OK;
   }
 

@@ -29,8 +29,11 @@ namespace imc {
 #ifndef IMC_CELL_GATHER_CG
 #define IMC_CELL_GATHER_CG 1    // MC2D: gather the per-cell constants through L2 only (0: default caching in L1)
 #endif
-#ifndef IMC_DEBUG_TALLY
-#define IMC_DEBUG_TALLY 0
+#ifndef IMC_DEP_F32
+#define IMC_DEP_F32 0           // Float16 / Float32 decks: ATOMIC deposits in global memory accumulate in Float32 (RED.F32)
+#endif
+#ifndef IMC_DEP_STRIDE
+#define IMC_DEP_STRIDE 1        // experiment: Float32 accumulators every IMC_DEP_STRIDE 4-byte words
 #endif
 #ifndef IMC_FASTDIV_DIR
 #define IMC_FASTDIV_DIR 1       // MC2D: divide by the direction cosines with cached reciprocals (imc_fastdiv.cuh)
@@ -56,9 +59,6 @@ template <class P> struct alignas(2 * sizeof(typename P::store_t)) AxisProp { ty
 // so that the gathers do not evict the small per-axis tables and the particle stream from L1.
 template <class P>
 __device__ __forceinline__ CellProp2<P> load_cell2(const CellProp2<P>* tab, int c) {
-#if IMC_DEBUG_TALLY == 3 || IMC_DEBUG_TALLY == 4      /* measurement only: no gather (every cell reads entry c & 1023) */
-  c &= 1023;
-#endif
 #if IMC_CELL_GATHER_CG
   CellProp2<P> r;
   if constexpr (P::id == 0) { const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(tab) + c); r.sig_col = (uint16_t)(v & 0xffffu); r.neg_saf = (uint16_t)(v >> 16); }
@@ -82,6 +82,31 @@ template <class P> __device__ __forceinline__ typename P::comp_t recip_of(Num<P>
 template <class P> __device__ __forceinline__ Num<P> div_cached(Num<P> a, Num<P> b, typename P::comp_t r) {
   if constexpr (P::id == 2) return a / b;
   else { FastDivisor d; d.b = b.v; d.r = r; return Num<P>(P::rnd(d.divide(a.v))); }
+}
+// The two face distances of a 2-D segment, ax / vx and ay / vy, by the cached reciprocals with ONE shared range test
+// (a slow-path region per division cost a BSSY / BRA / BSYNC triple and its call set-up each): both quotients are
+// recomputed by the plain division when either numerator leaves [2^-40, 2^40] or the direction was marked slow
+// (rvx == 0: load2d / the collision and reflection branches zero BOTH reciprocals when either cosine is out of range).
+template <class P>
+__device__ __forceinline__ void div_dir2(Num<P> ax, Num<P> vx, typename P::comp_t rvx, Num<P> ay, Num<P> vy, typename P::comp_t rvy, Num<P>& qx, Num<P>& qy) {
+#if IMC_FASTDIV_DIR
+  if constexpr (P::id != 2) {
+    float q0 = __fmul_rn(ax.v, rvx), q1 = __fmul_rn(ay.v, rvy);
+    q0 = __fmaf_rn(rvx, __fmaf_rn(-vx.v, q0, ax.v), q0);
+    q1 = __fmaf_rn(rvy, __fmaf_rn(-vy.v, q1, ay.v), q1);
+    const unsigned tx = (__float_as_uint(ax.v) & 0x7fffffffu) - 0x2b800000u, ty = (__float_as_uint(ay.v) & 0x7fffffffu) - 0x2b800000u;
+    if (__builtin_expect(!(max(tx, ty) < (0x53ffffffu - 0x2b800000u) && rvx != 0.0f), 0)) { q0 = fastdiv_slow(ax.v, vx.v); q1 = fastdiv_slow(ay.v, vy.v); }
+    qx = Num<P>(P::rnd(q0)); qy = Num<P>(P::rnd(q1));
+    return;
+  }
+#endif
+  qx = ax / vx; qy = ay / vy;
+}
+// both-or-none: the reciprocals of a direction (vx, vy) for div_dir2
+template <class P>
+__device__ __forceinline__ void recip_dir(Num<P> vx, Num<P> vy, typename P::comp_t& rvx, typename P::comp_t& rvy) {
+  rvx = recip_of(vx); rvy = recip_of(vy);
+  if constexpr (P::id != 2) { if (rvx == 0.0f || rvy == 0.0f) rvx = rvy = 0.0f; }
 }
 // division by a direction cosine (reciprocal cached in the history registers) — IMC_FASTDIV_DIR=0: plain division
 template <class P> __device__ __forceinline__ Num<P> div_dir(Num<P> a, Num<P> b, typename P::comp_t r) {
@@ -155,32 +180,33 @@ struct Draw {
 // (SegDraw) or the replay tape.  Only the needed state lives in registers.
 // `seg` is the 0-based segment index of the history (the caller's counter).
 template <class P, bool TAPE, bool LEAN = false> struct HistDraw;
+// PAR: parity of the segment index when the caller's loop is unrolled by two segments (-1: read it from `seg`)
 template <class P>
 struct HistDraw<P, false, false> {
   SegDraw<P> sg;
   __device__ __forceinline__ void init(const RngArgs&, unsigned long long id, long long) { sg.init(id); }
   __device__ __forceinline__ void resume(unsigned long long id, unsigned next, unsigned extra) { sg.resume(id, next, extra); }
-  __device__ __forceinline__ void next_segment(const RngArgs& r, unsigned) { sg.next_segment_rk(r.rk, r.step); }
-  __device__ __forceinline__ Num<P> uniform(const RngArgs& r, unsigned) { return sg.uniform(r.seed, r.step); }
-  __device__ __forceinline__ Num<P> randexp(unsigned) { return sg.randexp(); }
+  template <int PAR = -1> __device__ __forceinline__ void next_segment(const RngArgs& r, unsigned) { sg.next_segment_rk(r.rk, r.step); }
+  template <int PAR = -1> __device__ __forceinline__ Num<P> uniform(const RngArgs& r, unsigned) { return sg.uniform(r.seed, r.step); }
+  template <int PAR = -1> __device__ __forceinline__ Num<P> randexp(unsigned) { return sg.randexp(); }
   __device__ __forceinline__ bool over() const { return false; }
 };
 template <class P>
 struct HistDraw<P, false, true> {   // MC2D history kernels
   SegDrawLean<P> sg;
   __device__ __forceinline__ void init(const RngArgs&, unsigned long long id, long long) { sg.init(id); }
-  __device__ __forceinline__ void next_segment(const RngArgs& r, unsigned seg) { sg.next_segment_rk(r.rk, r.step, seg); }
-  __device__ __forceinline__ Num<P> uniform(const RngArgs&, unsigned seg) { return sg.uniform(seg); }
-  __device__ __forceinline__ Num<P> randexp(unsigned seg) { return sg.randexp(seg); }
+  template <int PAR = -1> __device__ __forceinline__ void next_segment(const RngArgs& r, unsigned seg) { sg.template next_segment_rk<PAR>(r.rk, r.step, seg); }
+  template <int PAR = -1> __device__ __forceinline__ Num<P> uniform(const RngArgs&, unsigned seg) { return sg.template uniform<PAR>(seg); }
+  template <int PAR = -1> __device__ __forceinline__ Num<P> randexp(unsigned seg) { return sg.template randexp<PAR>(seg); }
   __device__ __forceinline__ bool over() const { return false; }
 };
 template <class P, bool LEAN>
 struct HistDraw<P, true, LEAN> {
   TapeDraw<P> tp;
   __device__ __forceinline__ void init(const RngArgs& r, unsigned long long, long long slot) { tp.init(r.uni, r.n_uni, r.ex, r.n_exp, (size_t)r.stride, (size_t)slot); }
-  __device__ __forceinline__ void next_segment(const RngArgs&, unsigned) {}
-  __device__ __forceinline__ Num<P> uniform(const RngArgs&, unsigned) { return tp.uniform(); }
-  __device__ __forceinline__ Num<P> randexp(unsigned) { return tp.randexp(); }
+  template <int PAR = -1> __device__ __forceinline__ void next_segment(const RngArgs&, unsigned) {}
+  template <int PAR = -1> __device__ __forceinline__ Num<P> uniform(const RngArgs&, unsigned) { return tp.uniform(); }
+  template <int PAR = -1> __device__ __forceinline__ Num<P> randexp(unsigned) { return tp.randexp(); }
   __device__ __forceinline__ bool over() const { return tp.exhausted(); }
 };
 
@@ -538,6 +564,8 @@ struct TallyArgs {
   int copies;        // shared-memory accumulator sets per block (a power of two): warp w deposits into set w % copies, so that
                      // the compare-and-swap loops of different warps do not collide
   int nacc;          // Nc * Ns
+  int dep_f32;       // ATOMIC deposits in global memory accumulate in Float32 (Float16 / Float32 decks): g_acc viewed as float[nacc]
+  float* g_dep32;    // Float32 deposit accumulators (dep_f32)
   double* g_acc;     // reduce buffer viewed as Float64 (ATOMIC)
   long long* g_fx;   // reduce buffer viewed as int64 (FIXED)
   double fx_mul;     // 2^S for densities
@@ -604,13 +632,12 @@ struct Tally {
       else atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + idx, (unsigned long long)q);
     } else {
       if (K::smem(a)) atomicAdd(&s_acc[idx], (A)v.v);
-#if IMC_DEBUG_TALLY == 1 || IMC_DEBUG_TALLY == 4      /* measurement only: no deposit */
-      else if (v.v == (typename P::comp_t)123456.0f) atomicAdd(a.g_acc + idx, v.d());
-#elif IMC_DEBUG_TALLY == 2    /* measurement only: Float32 atomics on the same buffer */
-      else atomicAdd(reinterpret_cast<float*>(a.g_acc) + 2 * idx, (float)v.v);
-#else
+      // global ATOMIC accumulators: Float32 for Float16 / Float32 decks — the reference itself accumulates
+      // `energydep[cell] += dep` in the deck precision (imc_transport.jl:120) — as one RED.F32 per deposit (half the
+      // L2 footprint of the tally and no F2F conversion; the region's first nacc 4-byte words, TallyArgs::dep_f32);
+      // Float64 decks keep Float64
+      else if (IMC_DEP_F32 && P::id != 2 && (TK == TK_ATOMIC_G || (TK == TK_RUNTIME && a.dep_f32))) atomicAdd(a.g_dep32 + (size_t)idx * IMC_DEP_STRIDE, (float)v.v);
       else atomicAdd(a.g_acc + idx, v.d());
-#endif
     }
   }
   // 1-D decks: the lanes of a warp mostly deposit into the same one or two cells, and a shared-memory Float32 / 64-bit
@@ -658,40 +685,34 @@ struct Tally {
   }
 };
 
-// Event counters and lost energy live in shared memory (one set per block), not in registers: they are
-// touched once per history (warp-aggregated), and 18 fewer live registers in the tracking loop buy a fourth
-// resident block per SM.  Slot RB_LOST holds a Float64 (ATOMIC) or a fixed-point integer (FIXED).
+// Event counters and lost energy live in shared memory, not in registers: they are touched once per history, and 18
+// fewer live registers in the tracking loop buy a fourth resident block per SM.
+//   * per THREAD: segments (64-bit) and the four outcome counts (32-bit; a thread ends fewer than 2^32 histories because
+//     the engine refuses more than 2^32 particles per GPU).  Thread-private slots need no atomics, no votes and no
+//     leader election: the end of a history costs three load-add-store triples.  (Round 1 kept one slot set per block
+//     and updated it with warp-aggregated shared atomics: ~200 SASS instructions per write-back, 5 % of the kernel.)
+//     Layout [counter][thread]: consecutive lanes hit consecutive words, conflict-free.
+//   * per BLOCK: RB_LOST (a Float64 in ATOMIC mode, a fixed-point integer in FIXED mode), updated atomically (escapes are rare).
 struct Counters {
-  unsigned long long* s;
+  unsigned long long* s;     // block slots [RB_NSCALARS]
+  unsigned long long* seg;   // [blockDim.x]
+  unsigned* evn;             // [5][blockDim.x]: census, absorbed, escaped, random-walk kill; [4] = numeric errors
   __device__ __forceinline__ void init(unsigned long long* slots) {
     s = slots;
+    seg = slots + RB_NSCALARS + threadIdx.x;
+    evn = reinterpret_cast<unsigned*>(slots + RB_NSCALARS + blockDim.x) + threadIdx.x;
     if (threadIdx.x < RB_NSCALARS) s[threadIdx.x] = 0ull;
+    *seg = 0ull;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) evn[k * blockDim.x] = 0u;
     __syncthreads();
   }
   // end of one history: outcome ev (0 census, 1 absorbed, 2 escaped, 3 random-walk kill) after nseg segments
   __device__ __forceinline__ void finish(int ev, int nseg) {
-    const unsigned m = __activemask();
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    const unsigned segs = __reduce_add_sync(m, (unsigned)nseg);
-    const unsigned c0 = __ballot_sync(m, ev == 0), c2 = __ballot_sync(m, ev == 2);
-    if (lane == leader) {
-      add64(RB_SEG, segs);
-      add64(RB_HIST, (unsigned)__popc(m));
-      if (c0) add64(RB_CENSUS, (unsigned)__popc(c0));
-      if (c2) add64(RB_ESCAPED, (unsigned)__popc(c2));
-      const int nabs = __popc(m) - __popc(c0) - __popc(c2);
-      if (nabs) add64(RB_ABSORBED, (unsigned)nabs);
-    }
+    *seg += (unsigned long long)(unsigned)nseg;
+    evn[ev * blockDim.x] += 1u;
   }
-  // 64-bit counter += 32-bit value with native 32-bit shared-memory atomics (a 64-bit shared atomicAdd is a compare-and-swap
-  // loop on sm_100): low word, then the carry into the high word.  The counters are read only after a __syncthreads().
-  __device__ __forceinline__ void add64(int k, unsigned v) {
-    unsigned* w = reinterpret_cast<unsigned*>(&s[k]);
-    const unsigned old = atomicAdd(w, v);
-    if (old > 0xffffffffu - v) atomicAdd(w + 1, 1u);
-  }
-  __device__ __forceinline__ void error() { add64(RB_ERRORS, 1u); }
-  __device__ __forceinline__ void rw() { add64(RB_RW, 1u); }
+  __device__ __forceinline__ void error() { evn[4 * blockDim.x] += 1u; }
   template <int TK = TK_RUNTIME>
   __device__ __forceinline__ void lose_value(const TallyArgs& a, double e_over_scale) {
     if (TKind<TK>::fixed(a)) atomicAdd(&s[RB_LOST], (unsigned long long)__double2ll_rn(e_over_scale * a.fx_mul_lost));
@@ -706,14 +727,34 @@ struct Counters {
   __device__ __forceinline__ void commit(const TallyArgs& a) {
     __syncthreads();
     if (TKind<TK>::exact(a) && a.pass == 1) return;
+    // per-thread slots -> one sum per warp -> the reduce buffer
+    unsigned long long sg = *seg;
+    unsigned c0 = evn[0], c1 = evn[blockDim.x], c2 = evn[2 * blockDim.x], c3 = evn[3 * blockDim.x], c4 = evn[4 * blockDim.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sg += __shfl_xor_sync(IMC_FULL_MASK, sg, o);
+    c0 = __reduce_add_sync(IMC_FULL_MASK, c0); c1 = __reduce_add_sync(IMC_FULL_MASK, c1);
+    c2 = __reduce_add_sync(IMC_FULL_MASK, c2); c3 = __reduce_add_sync(IMC_FULL_MASK, c3); c4 = __reduce_add_sync(IMC_FULL_MASK, c4);
+    const int lane = threadIdx.x & 31;
+    if (lane < RB_NSCALARS && lane != RB_LOST) {
+      // per-warp sums < 2^32 * 32 fit 64 bits; counts are exact in Float64 below 2^53
+      const unsigned long long hist = (unsigned long long)c0 + c1 + c2 + c3;
+      const unsigned long long v = lane == RB_SEG ? sg : lane == RB_HIST ? hist : lane == RB_CENSUS ? (unsigned long long)c0
+                                 : lane == RB_ABSORBED ? (unsigned long long)c1 + c3 : lane == RB_ESCAPED ? (unsigned long long)c2
+                                 : lane == RB_RW ? (unsigned long long)c3 : (unsigned long long)c4;
+      if (v) {
+        if (TKind<TK>::fixed(a)) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + a.sc0 + lane, v);
+        else atomicAdd(a.g_acc + a.sc0 + lane, (double)v);
+      }
+    }
     const int k = threadIdx.x;
-    if (k >= RB_NSCALARS || s[k] == 0ull) return;
-    if (TKind<TK>::fixed(a)) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + a.sc0 + k, s[k]);
-    else if (k == RB_LOST) atomicAdd(a.g_acc + a.sc0 + k, *reinterpret_cast<double*>(&s[k]));
-    else atomicAdd(a.g_acc + a.sc0 + k, (double)s[k]);
+    if (k == RB_LOST && s[k] != 0ull) {
+      if (TKind<TK>::fixed(a)) atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + a.sc0 + k, s[k]);
+      else atomicAdd(a.g_acc + a.sc0 + k, *reinterpret_cast<double*>(&s[k]));
+    }
   }
 };
-constexpr int COUNTER_SMEM_BYTES = RB_NSCALARS * 8;
+// dynamic shared memory of every tracking kernel ahead of the tally accumulators: block slots + per-thread slots
+constexpr int COUNTER_SMEM_BYTES = RB_NSCALARS * 8 + TRACK_THREADS * 8 + 5 * TRACK_THREADS * 4;
 
 // ======================================================================================
 // Transport.MC — 1-D history-based tracking
@@ -891,7 +932,7 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   h.rec_base = (exact && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], pi);
   MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
-  h.rvx = recip_of(h.vx); h.rvy = recip_of(h.vy);
+  recip_dir(h.vx, h.vy, h.rvx, h.rvy);
   { const AxisProp<P>* tab = exact ? a.m.ax_d : a.m.ax_inv;
     const AxisProp<P> ax = tab[h.xi], ay = tab[a.m.nx + h.yi];
     h.wxc = N(P::unpack(ax.w)); h.wyc = N(P::unpack(ay.w)); h.qx = N(P::unpack(ax.q)); h.qy = N(P::unpack(ay.q)); }
@@ -911,7 +952,8 @@ __device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, D& d
   if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
   if (d.over()) atomicAdd(a.over_flag, 1ull);
 }
-template <class P, class D, int TK>
+// PAR: parity of the segment index (h.nseg before the increment) when the caller's loop is unrolled by two, else -1
+template <int PAR = -1, class P, class D, int TK>
 __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, Tally<P, TK>& tal, Counters& cn) {
   using N = Num<P>;
   const N zero;
@@ -920,14 +962,16 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   const bool exact = TKind<TK>::exact(a.tally);
   ++h.nseg;
   const unsigned seg = (unsigned)h.nseg - 1u;
-  d.next_segment(a.rng, seg);
+  d.template next_segment<PAR>(a.rng, seg);
   // the cell's {sigma_a (1 - f) + sigma_s, -sigma_a f} stay in registers and are re-read when the particle enters
   // another cell
   const N sig_col = h.sig_col, neg_saf = h.neg_saf;
-  const N dist_bx = nabs(div_dir(h.vx > zero ? h.wxc - h.x : h.x, h.vx, h.rvx));    // :538-542
-  const N dist_by = nabs(div_dir(h.vy > zero ? h.wyc - h.y : h.y, h.vy, h.rvy));    // :544-548
+  N qbx, qby;
+  div_dir2<P>(h.vx > zero ? h.wxc - h.x : h.x, h.vx, h.rvx, h.vy > zero ? h.wyc - h.y : h.y, h.vy, h.rvy, qbx, qby);
+  const N dist_bx = nabs(qbx);                                                      // :538-542
+  const N dist_by = nabs(qby);                                                      // :544-548
   const N dist_b = min_nonnan(dist_bx, dist_by);                                    // :551-557
-  const N dist_col = d.randexp(seg) / sig_col;                                      // :561
+  const N dist_col = d.template randexp<PAR>(seg) / sig_col;                        // :561
   const N dist_cen = (c_light * (dt - h.t)) * ds;                                   // :569
   const N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                        // :571
   if (is_nan(dist) || dist_col < zero) cn.error();
@@ -965,8 +1009,10 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   h.x = h.x + dist * h.vx;                                                          // :615
   h.y = h.y + dist * h.vy;                                                          // :616
   { N dd = dist;                                                                    // :617 (dist / ds) / c; x / 1 == x exactly
-#pragma unroll 1
-    for (int r = 0; r < a.m.n_tdiv; ++r) dd = div_cached(dd, N(a.m.tdiv[r]), a.m.tdiv_r[r]);
+    if (a.m.n_tdiv != 0) {                                                          // kernel-uniform branches
+      dd = div_cached(dd, N(a.m.tdiv[0]), a.m.tdiv_r[0]);
+      if (a.m.n_tdiv == 2) dd = div_cached(dd, N(a.m.tdiv[1]), a.m.tdiv_r[1]);
+    }
     h.t = h.t + dd; }
   h.E = newE;                                                                       // :618
   if (face) {
@@ -987,15 +1033,15 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
     if (a.m.bc[side] == IMC_REFLECT) {                                              // :626-628 / :666-668
       h.mu = isx ? MathDet::atan2<P>(h.vy, -h.vx) : MathDet::atan2<P>(-h.vy, h.vx);
       MathDet::sincos<P>(h.mu, &h.vy, &h.vx);
-      h.rvx = recip_of(h.vx); h.rvy = recip_of(h.vy);
+      recip_dir(h.vx, h.vy, h.rvx, h.rvy);
       return -1;
     }
     cn.lose<P, TK>(a.tally, h.E / N(a.m.scales[h.k]), h.pi, h.E.d());               // VACUUM :629-636 ...
     h.E = N::from_d(-1.0);
     return 2;
   }
-  if (dist == dist_col) { h.mu = N::from_d(6.283185307179586 * d.uniform(a.rng, seg).d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx);
-                           h.rvx = recip_of(h.vx); h.rvy = recip_of(h.vy); }  // :706-710
+  if (dist == dist_col) { h.mu = N::from_d(6.283185307179586 * d.template uniform<PAR>(a.rng, seg).d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx);
+                           recip_dir(h.vx, h.vy, h.rvx, h.rvy); }  // :706-710
   if (dist == dist_cen) { h.t = zero; return 0; }                      // :712-717
   return -1;
 }
@@ -1010,8 +1056,8 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track2
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
     Hist2<P> h; HistDraw<P, TAPE, true> d;
     if (!load2d<P, HistDraw<P, TAPE, true>, TK>(a, pi, h, d, cn)) continue;
-    int ev;
-    while ((ev = seg2d(a, h, d, tal, cn)) < 0) {}
+    int ev;   // two segments per trip: the parity of the segment index is static (one Philox block per pair)
+    while ((ev = seg2d<0>(a, h, d, tal, cn)) < 0 && (ev = seg2d<1>(a, h, d, tal, cn)) < 0) {}
     store2d<P, HistDraw<P, TAPE, true>, TK>(a, h, d, ev, cn);
   }
   tal.flush();
@@ -1019,11 +1065,13 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track2
 }
 
 // ---- dynamic schedule: warp-level refill from a global particle queue --------------------------------
-// Every loop iteration each active lane tracks one segment.  When at least `refill_min` lanes of the warp
-// are idle (or all are), the idle lanes first write back the histories they finished (together: one
-// warp-aggregated counter update, coalescing stores), then lane 0 claims that many consecutive particle indices
-// with one atomicAdd and the idle lanes load them.  Per-particle results do not depend on the lane that tracks
-// them (Philox is keyed by particle id, the tape by particle slot), so both schedules give identical particle state.
+// Every trip of the loop each active lane tracks TWO segments (an even and an odd one: the parity of the segment index
+// is static, so the Philox block of the pair is generated in the first half by every lane and the second half carries
+// no parity test).  Before a trip, when at least `refill_min` lanes of the warp are idle (or all are), the idle lanes
+// write back the histories they finished (thread-private counters, coalescing stores), lane 0 claims that many
+// consecutive particle indices with one atomicAdd and the idle lanes load them.  Per-particle results do not depend on
+// the lane that tracks them (Philox is keyed by particle id and segment, the tape by particle slot), so both schedules
+// give identical particle state.
 template <class P, int GEOM, bool TAPE, int TK>
 __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_refill(TrackArgs<P> a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1036,15 +1084,12 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_
   const unsigned lt_mask = (1u << lane) - 1u;
   int st = ST_EMPTY;
   bool drained = false;
-  unsigned iter = 0;
   if (a.timeline && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(a.timeline, t); }
   Hist1<P> h1; Hist2<P> h2; Dr d;
   while (true) {
     unsigned idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
-    // new histories start on even iterations only: SegDraw makes one Philox block per two segments (Float16/32),
-    // so all lanes of the warp then generate their blocks in the same iterations.  refill_min <= 32, so a warp
-    // with no active lane always refills.
-    if ((iter & 1u) == 0u && __popc(idle) >= a.refill_min) {
+    // refill_min <= 32, so a warp with no active lane always refills
+    if (__popc(idle) >= a.refill_min) {
       if (st >= 0) {
         if constexpr (GEOM == 1) store1d<P, Dr, TK>(a, h1, d, st, cn); else store2d<P, Dr, TK>(a, h2, d, st, cn);
         st = ST_EMPTY;
@@ -1068,21 +1113,21 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_
         }
         idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
       }
-    }
-    ++iter;
-    if (idle == IMC_FULL_MASK) {
-      if (drained) break;
-      iter = 0;
-      continue;
+      if (idle == IMC_FULL_MASK) {
+        if (drained) break;
+        continue;
+      }
     }
     if (st == ST_ACTIVE) {
       int ev;
-      if constexpr (GEOM == 1) ev = seg1d(a, h1, d, tal, cn); else ev = seg2d(a, h2, d, tal, cn);
+      if constexpr (GEOM == 1) ev = seg1d(a, h1, d, tal, cn); else ev = seg2d<0>(a, h2, d, tal, cn);
       if (ev >= 0) st = ev;
     }
-  }
-  if (st >= 0) {   // histories that finished after the last refill
-    if constexpr (GEOM == 1) store1d<P, Dr, TK>(a, h1, d, st, cn); else store2d<P, Dr, TK>(a, h2, d, st, cn);
+    if (st == ST_ACTIVE) {
+      int ev;
+      if constexpr (GEOM == 1) ev = seg1d(a, h1, d, tal, cn); else ev = seg2d<1>(a, h2, d, tal, cn);
+      if (ev >= 0) st = ev;
+    }
   }
   if (a.timeline && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMax(a.timeline + 2, t); }
   tal.flush();
@@ -1238,7 +1283,6 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
       D R0 = dyn_min(dyn_abs(dyn_sub(D(dx), x)), dyn_abs(x));                       // :286
       N inv_sigma = N::from_i(1) / N::load(a.m.sigma_static, cell);                 // 1/mesh.sigma[cellindex] (Q4)
       if (R0.v > inv_sigma.d() && dist_col.v < R0.v) {                              // :289
-        cn.rw();
         const N sa = N::load(a.m.sa, cell), f = N::load(a.m.fleck, cell);
         N u = d.uniform();                                                          // :290
         N Dc = c_light / ((three * sa) * (one - f));                                // :292
@@ -1630,13 +1674,14 @@ __global__ void k_exact_lost(const double* __restrict__ lost_val, const unsigned
   *lost_io = lost;
 }
 
-// reduce buffer -> energydep (T)
+// reduce buffer -> energydep (T).  kind: 0 Float64 accumulators, 1 fixed-point int64, 2 Float32 accumulators (the first n
+// 4-byte words of the region)
 template <class P>
-__global__ void k_acc_to_field(const double* g_acc, const long long* g_fx, int fixed, double fx_mul, long long n,
-                               typename P::store_t* out) {
+__global__ void k_acc_to_field(const double* g_acc, int kind, double fx_mul, long long n, typename P::store_t* out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double v = fixed ? (double)g_fx[i] / fx_mul : g_acc[i];
+  double v = kind == 1 ? (double)reinterpret_cast<const long long*>(g_acc)[i] / fx_mul
+           : kind == 2 ? (double)reinterpret_cast<const float*>(g_acc)[i * IMC_DEP_STRIDE] : g_acc[i];
   Num<P>::from_d(v).store(out, i);
 }
 

@@ -439,11 +439,13 @@ IMC_HD float expm1_f(float x) {
   return expm1_from_core_f(em, n);
 }
 IMC_HD void exp_expm1_f(float x, float* e, float* em1) {
-  if (!(x <= 88.0f && x >= -17.0f)) { *e = exp_f(x); *em1 = expm1_f(x); return; }
   float ax = x < 0 ? -x : x;
   // |x| < ln2/2 (the usual case in tracking: one segment attenuates little): n = 0, so the reduction leaves
-  // r = x, c = 0 and the scaling is by 2^0 — the same operations as below with the no-ops removed, bit-identical
-  if (rint_f(x * IMC_LOG2E_F) == 0.0f) {
+  // r = x, c = 0 and the scaling is by 2^0 — the same operations as below with the no-ops removed, bit-identical.
+  // n = rint(x log2e) == 0  <=>  |RN(x log2e)| <= 1/2 (ties go to the even 0); NaN and the out-of-range arguments fail the
+  // test and take the general path below
+  const float z = x * IMC_LOG2E_F;
+  if ((z < 0 ? -z : z) <= 0.5f) {
     float q = 1.0f / 40320.0f;
     q = fma_f(q, x, 1.0f / 5040.0f);
     q = fma_f(q, x, 1.0f / 720.0f);
@@ -456,6 +458,7 @@ IMC_HD void exp_expm1_f(float x, float* e, float* em1) {
     *em1 = (ax < 2.98023223876953125e-08f) ? x : em0;
     return;
   }
+  if (!(x <= 88.0f && x >= -17.0f)) { *e = exp_f(x); *em1 = expm1_f(x); return; }
   int n;
   float em = exp_core_f(x, &n);
   *e = scale_f(1.0f + em, n);

@@ -217,19 +217,23 @@ struct SegDrawLean {
     id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32);
     buf[0] = buf[1] = buf[2] = buf[3] = 0u;
   }
+  // PAR: the parity of `seg` when the caller knows it at compile time (loops unrolled by two segments), else -1
+  template <int PAR = -1>
   IMC_HD void next_segment_rk(const uint32_t* rk, uint32_t step, uint32_t seg) {   // seg: 0-based segment of the history
-    if (P::id == 2 || (seg & 1u) == 0u) {
+    if (P::id == 2 || (PAR < 0 ? (seg & 1u) == 0u : PAR == 0)) {
       uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? seg : (seg >> 1))};
       Philox::block_rk(c, rk, buf);
     }
   }
+  template <int PAR = -1>
   IMC_HD Num<P> randexp(uint32_t seg) const {
     if constexpr (P::id == 2) return Num<P>(randexp64_from_word(((uint64_t)buf[1] << 32) | buf[0]));
-    else return Num<P>(P::rnd(randexp32_from_word((seg & 1u) ? buf[2] : buf[0])));
+    else return Num<P>(P::rnd(randexp32_from_word((PAR < 0 ? (seg & 1u) != 0u : PAR == 1) ? buf[2] : buf[0])));
   }
+  template <int PAR = -1>
   IMC_HD Num<P> uniform(uint32_t seg) const {
     if constexpr (P::id == 2) return uniform_from_word<P>(((uint64_t)buf[3] << 32) | buf[2]);
-    else return uniform_from_word<P>((uint64_t)((seg & 1u) ? buf[3] : buf[1]));
+    else return uniform_from_word<P>((uint64_t)((PAR < 0 ? (seg & 1u) != 0u : PAR == 1) ? buf[3] : buf[1]));
   }
 };
 

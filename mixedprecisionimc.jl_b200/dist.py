@@ -31,13 +31,26 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
 
 
-def reduce_buffer_tensor(engine: _lib.Engine) -> torch.Tensor:
-    ptr, n, is_int = engine.reduce_buffer()
+def reduce_buffer_parts(engine: _lib.Engine):
+    """The engine's reduce buffer as two tensors that share its memory: the deposits [energydep Nc*Ns] and the tail
+    [radenergydens Nc | lostenergy | counters].  Element types follow imc_reduce_buffer's `kind`: 0 = Float64 throughout,
+    1 = int64 throughout (FIXED tallies), 2 = Float32 deposits (the region's first Nc*Ns 4-byte words: Float16 / Float32
+    decks with ATOMIC tallies in global memory accumulate in the deck's own width or wider, like the reference's
+    `energydep[cell] += dep`) followed by a Float64 tail at byte offset 8*Nc*Ns."""
+    ptr, n, kind = engine.reduce_buffer()
+    n_dep = engine.nc * engine.ns
     if engine.lib.backend.startswith("cuda"):
-        return torch.as_tensor(_DevArray(ptr, n, "<i8" if is_int else "<f8"), device=f"cuda:{engine.cfg.device}")
-    ctype = C.c_int64 if is_int else C.c_double
-    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
-    return torch.from_numpy(arr)
+        dev = f"cuda:{engine.cfg.device}"
+        t8 = "<i8" if kind == 1 else "<f8"
+        dep = torch.as_tensor(_DevArray(ptr, n_dep, "<f4" if kind == 2 else t8), device=dev)
+        tail = torch.as_tensor(_DevArray(ptr + 8 * n_dep, n - n_dep, t8), device=dev)
+        return dep, tail
+    ctype = C.c_int64 if kind == 1 else C.c_double
+    arr = torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)))
+    if kind == 2:
+        dep = torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(n_dep,)))
+        return dep, arr[n_dep:]
+    return arr[:n_dep], arr[n_dep:]
 
 
 def advance_sharded(sim: _driver.Simulation, group=None) -> dict:
@@ -56,21 +69,21 @@ def advance_sharded(sim: _driver.Simulation, group=None) -> dict:
     # [radenergydens | scalars] tail of the buffer); the tail is reduced afterwards.  Two collectives per step, same bytes.
     # (The oracle fills its host-side buffer only in tally_local, so there the whole buffer is reduced afterwards.)
     if on_gpu:
-        buf = reduce_buffer_tensor(eng)
-        n_dep = eng.nc * eng.ns
-        work = dist.all_reduce(buf[:n_dep], group=group, async_op=True)
+        dep, tail = reduce_buffer_parts(eng)
+        work = dist.all_reduce(dep, group=group, async_op=True)
         _driver.Clean.clean(parts)
         eng.tally_local()
         # tally_local only enqueues the census tally on the engine's own stream, which the collective's stream does not
         # know about: imc_reduce_buffer waits for that stream, so the tail is complete before it is reduced
         eng.reduce_buffer()
-        dist.all_reduce(buf[n_dep:], group=group)
+        dist.all_reduce(tail, group=group)
         work.wait()
         torch.cuda.current_stream().synchronize()
     else:
         _driver.Clean.clean(parts)
         eng.tally_local()
-        dist.all_reduce(reduce_buffer_tensor(eng), group=group)
+        for part in reduce_buffer_parts(eng):
+            dist.all_reduce(part, group=group)
     rec["tally"] = eng.tally_finish(float(sv.t), float(sv.dt))
     rec["energy"] = eng.energycheck()
     _driver.timestep(str(inputs["TIMESTEPPING"]).upper(), sv)

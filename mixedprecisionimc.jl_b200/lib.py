@@ -316,10 +316,11 @@ class Engine:
         return {"source": _as_dict(a), "transport": _as_dict(b), "tally": _as_dict(c_), "energy": _as_dict(d)}
 
     def reduce_buffer(self):
-        """(address, n_elements, is_int64) of the buffer to all-reduce between tally_local and tally_finish."""
-        p = C.c_void_p(); n = C.c_int64(); isint = C.c_int32()
-        self._check(self.lib.dll.imc_reduce_buffer(self._h, C.byref(p), C.byref(n), C.byref(isint)))
-        return p.value, n.value, bool(isint.value)
+        """(address, n_elements, kind) of the buffer to all-reduce between tally_local and tally_finish; kind: 0 = Float64,
+        1 = int64 (FIXED tallies), 2 = Float32 deposits + Float64 tail (include/imc.h)."""
+        p = C.c_void_p(); n = C.c_int64(); kind = C.c_int32()
+        self._check(self.lib.dll.imc_reduce_buffer(self._h, C.byref(p), C.byref(n), C.byref(kind)))
+        return p.value, n.value, int(kind.value)
 
     # -- state access ------------------------------------------------------------------------
     def field(self, name: str, out: Optional[np.ndarray] = None) -> np.ndarray:
