@@ -93,6 +93,7 @@ struct EngineT : EngineBase {
   DBuf<double> red;
   long long red_n = 0;
   bool red_fixed = false;
+  bool y_fastest = false, dep_perm = false;   // layout of the CellProp2 table / of the deposit accumulators of the last transport (MeshDev::csx ...)
   DBuf<float> dep_strided;   // experiment (IMC_DEP_STRIDE > 2)
   bool dep_f32 = false;   // the [energydep] region holds Float32 accumulators (its first nc*ns 4-byte words): Float16 / Float32 decks,
                           // ATOMIC tallies in global memory, Philox history kernels (Tally::add)
@@ -320,6 +321,16 @@ struct EngineT : EngineBase {
     for (int r = 0; r < 2; ++r) {   // RN(1/divisor) for the cached-reciprocal division (imc_fastdiv.cuh); 0 outside its range
       const double d = std::fabs((double)m.tdiv[r]);
       m.tdiv_r[r] = (P::id != 2 && d >= 0x1p-40 && d < 0x1p40) ? (Cc)(1.0f / (float)m.tdiv[r]) : (Cc)0;
+    }
+    // internal layout of the per-cell tracking tables (MeshDev::csx ...): the more frequently crossed axis fastest
+    {
+      double lx = 0, ly = 0;
+      for (int i = 0; i < nx; ++i) lx += std::fabs(dx_[i]);
+      if (geom == 2) for (int j = 0; j < ny; ++j) ly += std::fabs(dy_[j]);
+      static const int force = getenv("IMC_CELL_ORDER") ? atoi(getenv("IMC_CELL_ORDER")) : 0;   // 1: x fastest, 2: y fastest (experiments)
+      y_fastest = geom == 2 && (force ? force == 2 : (double)ny * lx > (double)nx * ly);   // ny / ly > nx / lx: y faces are crossed more often
+      m.csx = y_fastest ? ny : 1; m.csy = y_fastest ? 1 : nx;
+      m.tsx = 1; m.tsy = nx;
     }
     k_widths<P><<<grid_for(std::max(nx, ny), 256), 256, 0, stream>>>(m); ++n_launch;
     IMC_CK(cudaGetLastError());
@@ -605,6 +616,9 @@ struct EngineT : EngineBase {
     // decided from the deck and the mesh alone, so that every rank of a multi-GPU run reduces the same element type
     dep_f32 = IMC_DEP_F32 && P::id != 2 && mode == IMC_TALLY_ATOMIC && !a.tally.use_smem;
     a.tally.dep_f32 = dep_f32 ? 1 : 0;
+    static const int tforce = getenv("IMC_TALLY_ORDER") ? atoi(getenv("IMC_TALLY_ORDER")) : 0;   // 1: x fastest, 2: y fastest (experiments)
+    dep_perm = geom == 2 && tforce == 2 && mode != IMC_TALLY_EXACT && !a.tally.use_smem;
+    a.m.tsx = dep_perm ? ny : 1; a.m.tsy = dep_perm ? 1 : nx;
     a.tally.g_dep32 = IMC_DEP_STRIDE > 2 ? dep_strided.p : reinterpret_cast<float*>(red.p);
     if (IMC_DEP_STRIDE > 2 && dep_f32) IMC_CK(cudaMemsetAsync(dep_strided.p, 0, (size_t)nc * ns * IMC_DEP_STRIDE * sizeof(float), stream));
     // outcome records for replay checks (small populations only)
@@ -653,6 +667,15 @@ struct EngineT : EngineBase {
       a.timeline = timeline.p;
     }
     a.refill_min = refill_min_env();
+    {   // visiting order of the dynamic schedule's queue (k_track_refill)
+      static const long long want = getenv("IMC_QUEUE_MULT") ? atoll(getenv("IMC_QUEUE_MULT")) : 1;
+      a.queue_chunks = (unsigned long long)((n_part + QUEUE_CHUNK - 1) / QUEUE_CHUNK);
+      auto gcd = [](unsigned long long x, unsigned long long y) { while (y) { unsigned long long t = x % y; x = y; y = t; } return x; };
+      unsigned long long mult = a.queue_chunks > 1 ? (unsigned long long)std::max<long long>(want, 1) % a.queue_chunks : 1ull;
+      if (mult == 0) mult = 1;
+      while (mult > 1 && gcd(mult, a.queue_chunks) != 1) { if (++mult >= a.queue_chunks) mult = 1; }
+      a.queue_mult = mult;
+    }
     if (n_part > 0) {
       int blocks_per_sm = 2048 / TRACK_THREADS;
       if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / (smem + COUNTER_SMEM_BYTES)));
@@ -677,6 +700,7 @@ struct EngineT : EngineBase {
           smem = smem_for(mode, nc * ns); a.tally.use_smem = smem_fits(smem, COUNTER_SMEM_BYTES) ? 1 : 0;
           a.tally.copies = a.tally.use_smem ? smem_copies(smem, COUNTER_SMEM_BYTES) : 1; smem = a.tally.use_smem ? smem * a.tally.copies : 0;
           dep_f32 = IMC_DEP_F32 && P::id != 2 && mode == IMC_TALLY_ATOMIC && !a.tally.use_smem; a.tally.dep_f32 = dep_f32 ? 1 : 0;
+          dep_perm = false; a.m.tsx = 1; a.m.tsy = nx;
           IMC_RC(launch_track(a, variant, grid, smem));
         } else {
           for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)std::max<long long>(R, 1))); IMC_CK(rec_val[b].ensure((size_t)std::max<long long>(R, 1))); }
@@ -797,8 +821,9 @@ struct EngineT : EngineBase {
   int tally_finish(double t_, double dt_, imc_tally_stats* out) override {
     if (!have_mesh) { err = "tally before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
-    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>((IMC_DEP_STRIDE > 2 && dep_f32 && !red_fixed) ? reinterpret_cast<double*>(dep_strided.p) : red.p + rb_dep0(), red_fixed ? 1 : (dep_f32 ? 2 : 0), fx_mul_dep, nc * ns, energydep.p); ++n_launch;
-    k_acc_to_field<P><<<grid_for(nc, 256), 256, 0, stream>>>(red.p + rb_rad0(), red_fixed ? 1 : 0, fx_mul_rad, nc, radenergydens.p); ++n_launch;
+    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>((IMC_DEP_STRIDE > 2 && dep_f32 && !red_fixed) ? reinterpret_cast<double*>(dep_strided.p) : red.p + rb_dep0(), red_fixed ? 1 : (dep_f32 ? 2 : 0), fx_mul_dep, nc * ns, energydep.p,
+                                                                     nc, dep_perm ? nx : 0, ny, 1); ++n_launch;
+    k_acc_to_field<P><<<grid_for(nc, 256), 256, 0, stream>>>(red.p + rb_rad0(), red_fixed ? 1 : 0, fx_mul_rad, nc, radenergydens.p, nc, 0, 0, 0); ++n_launch;
     TallyScratch<P> s; s.q_dep = q_dep.p; s.q_tot = q_tot.p; s.q_rad = q_rad.p;
     k_tally_finish<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, s, P::from_d(dt_), t_ == 0.0 ? 1 : 0, cfg.linearized, temp_wide ? 1 : 0); ++n_launch;
     IMC_CK(cudaGetLastError());

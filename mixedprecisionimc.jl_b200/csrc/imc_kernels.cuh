@@ -27,7 +27,8 @@ namespace imc {
 #define IMC_EARLY_NEXT_CELL 1   // MC2D: request the next cell's constants as soon as the event is known (0: in the face branch)
 #endif
 #ifndef IMC_CELL_GATHER_CG
-#define IMC_CELL_GATHER_CG 1    // MC2D: gather the per-cell constants through L2 only (0: default caching in L1)
+#define IMC_CELL_GATHER_CG 0    // MC2D: 1 = gather the per-cell constants through L2 only; 0 = cached in L1 (the table is laid out so that
+                                // consecutive cells of a history mostly share a sector, MeshDev::csx)
 #endif
 #ifndef IMC_DEP_F32
 #define IMC_DEP_F32 0           // Float16 / Float32 decks: ATOMIC deposits in global memory accumulate in Float32 (RED.F32)
@@ -42,6 +43,7 @@ namespace imc {
 #define IMC_TRACK_MIN_BLOCKS 4
 #endif
 constexpr int TRACK_THREADS = IMC_TRACK_THREADS;
+constexpr int QUEUE_CHUNK = 32;   // particles per claim of the dynamic schedule's queue
 // resident blocks per SM the history kernels are compiled for: 4 x 256 threads (64 registers) for Float16 / Float32; Float64
 // histories hold twice the registers — 3 blocks (80 registers) spill less and measured 5 % faster (crookedpipe_f64)
 template <class P> constexpr int track_min_blocks() { return P::id == 2 && IMC_TRACK_MIN_BLOCKS == 4 ? 3 : IMC_TRACK_MIN_BLOCKS; }
@@ -130,6 +132,13 @@ struct MeshDev {
   S* tsurf[4];  // bottom, top, left, right (1-D: left = [2][0], right = [3][0])
   CellProp1<P>* cp1;
   CellProp2<P>* cp2;
+  // Index maps of the two tables the 2-D history kernels touch once per segment by cell: index = xi*sx + yi*sy.
+  // The fields themselves are column-major [xindex, yindex] (x fastest, like Julia); these internal tables are laid
+  // out with the axis that particles cross MORE OFTEN (the one with the smaller mean cell width) fastest, so that
+  // consecutive cells of a history mostly share a 32-byte sector: the gather of the next cell's constants then hits
+  // L1 and consecutive deposits go to one L2 sector.  csx/csy: CellProp2 table (fixed at set_mesh); tsx/tsy: the
+  // deposit accumulators of this launch (linear for EXACT records and for shared-memory accumulators).
+  int csx, csy, tsx, tsy;
   AxisProp<P>*ax_inv, *ax_d;   // [nx + ny]: x entries, then y entries
   int ds_is_one, c_is_one;  // x / 1 == x exactly: the divisions by distancescale / phys_c can be skipped
   int n_tdiv; Cc tdiv[2], tdiv_r[2];   // tdiv_r: cached reciprocals (0 = take the plain division)   // the divisors of `(dist / ds) / c` that are not 1, in that order (a counted loop: the compiler
@@ -259,7 +268,7 @@ __global__ void k_update(MeshDev<P> m, typename P::comp_t dt_, int linearized, i
   } else {
     CellProp2<P> c;
     c.sig_col = P::pack(sig_col.v); c.neg_saf = P::pack(neg_saf.v);
-    m.cp2[i] = c;
+    m.cp2[m.geom == 2 ? (i % m.nx) * (long long)m.csx + (i / m.nx) * (long long)m.csy : i] = c;
   }
 }
 
@@ -780,7 +789,8 @@ struct TrackArgs {
   int* ev_nseg;               // [n] segments tracked so far
   unsigned* ev_extra;         // [n] extra-stream words consumed so far
   // dynamic schedule
-  unsigned long long* queue;  // next unclaimed particle index
+  unsigned long long* queue;  // next unclaimed chunk ticket
+  unsigned long long queue_chunks, queue_mult;   // chunks of QUEUE_CHUNK particles; ticket -> chunk multiplier (coprime to queue_chunks)
   int refill_min;             // refill when at least this many lanes of a warp are idle
   // optional timeline of the dynamic schedule (IMC_TRACK_TIMING=1): [0] first block start, [1] first time a warp found the
   // queue empty, [2] last block exit (globaltimer ns)
@@ -936,7 +946,7 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   { const AxisProp<P>* tab = exact ? a.m.ax_d : a.m.ax_inv;
     const AxisProp<P> ax = tab[h.xi], ay = tab[a.m.nx + h.yi];
     h.wxc = N(P::unpack(ax.w)); h.wyc = N(P::unpack(ay.w)); h.qx = N(P::unpack(ax.q)); h.qy = N(P::unpack(ay.q)); }
-  { const CellProp2<P> cp = load_cell2(a.m.cp2, h.xi + a.m.nx * h.yi);
+  { const CellProp2<P> cp = load_cell2(a.m.cp2, h.xi * a.m.csx + h.yi * a.m.csy);
     h.sig_col = N(P::unpack(cp.sig_col)); h.neg_saf = N(P::unpack(cp.neg_saf)); }
   return true;
 }
@@ -987,13 +997,13 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
   const bool interior = face && (pos ? idx != (isx ? nx : a.m.ny) - 1 : idx != 0);
   const int ni = pos ? idx + 1 : idx - 1;
   const int nxi = isx ? ni : h.xi, nyi = isx ? h.yi : ni;
-  const long long acc = (long long)h.k * a.m.nc + (h.xi + nx * h.yi);   // nc < 2^31 (checked at set_mesh)
+  const long long acc = (long long)h.k * a.m.nc + (h.xi * a.m.tsx + h.yi * a.m.tsy);   // nc < 2^31 (checked at set_mesh)
   AxisProp<P> nax; CellProp2<P> ncp;
   nax.w = nax.q = ncp.sig_col = ncp.neg_saf = typename P::store_t(0);
 #if IMC_EARLY_NEXT_CELL
   if (interior) {
     nax = (exact ? a.m.ax_d : a.m.ax_inv)[(isx ? 0 : nx) + ni];
-    ncp = load_cell2(a.m.cp2, nxi + nx * nyi);
+    ncp = load_cell2(a.m.cp2, nxi * a.m.csx + nyi * a.m.csy);
   }
 #endif
   N ex, em1; MathDet::exp_expm1<P>(neg_saf * dist, &ex, &em1);
@@ -1019,7 +1029,7 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
     if (interior) {                                                                 // neighbour cell
 #if !IMC_EARLY_NEXT_CELL
       nax = (exact ? a.m.ax_d : a.m.ax_inv)[(isx ? 0 : nx) + ni];
-      ncp = load_cell2(a.m.cp2, nxi + nx * nyi);
+      ncp = load_cell2(a.m.cp2, nxi * a.m.csx + nyi * a.m.csy);
 #endif
       const N w(P::unpack(nax.w)), q(P::unpack(nax.q));
       const N np = pos ? zero : w;                                                  // enters at 0 or at the far edge dx*ds
@@ -1084,6 +1094,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_
   const unsigned lt_mask = (1u << lane) - 1u;
   int st = ST_EMPTY;
   bool drained = false;
+  long long cbase = 0; int crem = 0;   // the warp's chunk of the particle list: next index, particles left (warp-uniform)
   if (a.timeline && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(a.timeline, t); }
   Hist1<P> h1; Hist2<P> h2; Dr d;
   while (true) {
@@ -1095,21 +1106,31 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_
         st = ST_EMPTY;
       }
       if (!drained) {
-        const int nidle = __popc(idle);
-        long long base = 0;
-        if (lane == 0) base = (long long)atomicAdd(a.queue, (unsigned long long)nidle);
-        base = __shfl_sync(IMC_FULL_MASK, base, 0);
-        if (st != ST_ACTIVE) {
-          long long pi = base + __popc(idle & lt_mask);
-          if (pi < a.n) {
+        // the warp works through a private chunk of QUEUE_CHUNK consecutive particles (coalesced loads) and claims the
+        // next one with a ticket from the global queue; chunk = ticket * queue_mult mod n_chunks visits the particle
+        // list in a scattered order (queue_mult coprime to n_chunks; 1 = list order)
+        if (crem == 0) {
+          unsigned long long t = 0;
+          if (lane == 0) t = atomicAdd(a.queue, 1ull);
+          t = __shfl_sync(IMC_FULL_MASK, t, 0);
+          if (t >= a.queue_chunks) {
+            if (a.timeline && lane == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); atomicMin(a.timeline + 1, tt); }
+            drained = true;
+          } else {
+            cbase = (long long)((t * a.queue_mult) % a.queue_chunks) * QUEUE_CHUNK;
+            crem = (int)min((long long)QUEUE_CHUNK, a.n - cbase);
+          }
+        }
+        if (!drained) {
+          const int take = min(__popc(idle), crem);
+          const int rank = __popc(idle & lt_mask);
+          if (st != ST_ACTIVE && rank < take) {
+            const long long pi = cbase + rank;
             bool ok;
             if constexpr (GEOM == 1) ok = load1d<P, Dr, TK>(a, pi, h1, d, cn); else ok = load2d<P, Dr, TK>(a, pi, h2, d, cn);
             if (ok) st = ST_ACTIVE;
           }
-        }
-        if (base + nidle >= a.n) {
-          if (a.timeline && !drained && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(a.timeline + 1, t); }
-          drained = true;
+          cbase += take; crem -= take;
         }
         idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
       }
@@ -1676,12 +1697,16 @@ __global__ void k_exact_lost(const double* __restrict__ lost_val, const unsigned
 
 // reduce buffer -> energydep (T).  kind: 0 Float64 accumulators, 1 fixed-point int64, 2 Float32 accumulators (the first n
 // 4-byte words of the region)
+// (nx, sx, sy): accumulator of cell (xi, yi) of plane k sits at k*nc + xi*sx + yi*sy (MeshDev::tsx / tsy); nx = 0: linear
 template <class P>
-__global__ void k_acc_to_field(const double* g_acc, int kind, double fx_mul, long long n, typename P::store_t* out) {
+__global__ void k_acc_to_field(const double* g_acc, int kind, double fx_mul, long long n, typename P::store_t* out,
+                               long long nc, int nx, int sx, int sy) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double v = kind == 1 ? (double)reinterpret_cast<const long long*>(g_acc)[i] / fx_mul
-           : kind == 2 ? (double)reinterpret_cast<const float*>(g_acc)[i * IMC_DEP_STRIDE] : g_acc[i];
+  long long j = i;
+  if (nx > 0) { const long long k = i / nc, c = i - k * nc; j = k * nc + (c % nx) * (long long)sx + (c / nx) * (long long)sy; }
+  double v = kind == 1 ? (double)reinterpret_cast<const long long*>(g_acc)[j] / fx_mul
+           : kind == 2 ? (double)reinterpret_cast<const float*>(g_acc)[j * IMC_DEP_STRIDE] : g_acc[j];
   Num<P>::from_d(v).store(out, i);
 }
 
