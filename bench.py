@@ -53,22 +53,41 @@ WORKLOADS = {
 }
 
 
-def make_inputs(w: dict, particles: int, mesh, world: int = 1):
+def workload_cellmin(w: dict, world: int = 1, scaling: str = "weak") -> int:
+    """CELLMIN of the synthetic deck.  Crooked pipe: every cell emits at least CELLMIN particles per step (Q9), so under weak
+    scaling it grows with the GPU count to keep the per-GPU work fixed (the shipped deck has CELLMIN 10 on 106 x 47 cells;
+    on 4096^2 cells that alone would be 1.7e8 particles per step); under strong scaling it stays 1."""
+    if w["deck"] == "crooked_pipe":
+        return max(1, world) if scaling == "weak" else 1
+    return 5 if w["deck"] == "marshak" else 1
+
+
+def make_inputs(w: dict, particles: int, mesh, world: int = 1, pairwise: str = "FALSE", scaling: str = "weak"):
+    """particles = the deck's NMAX (global); NINPUT = NMAX / 2."""
     from mpimc_b200 import decks
     n_max = int(particles)
     n_input = max(n_max // 2, 1)
+    cellmin = workload_cellmin(w, world, scaling)
     if w["deck"] == "crooked_pipe":
-        # CELLMIN (every cell emits at least that many particles per step, Q9) grows with the GPU count so that the
-        # per-GPU work stays fixed under weak scaling
         es = dict(energyscales=(1024.0,)) if w["precision"] == "FLOAT16" else {}
-        return decks.crooked_pipe(precision=w["precision"], n_input=n_input, n_max=n_max, cellmin=max(1, world),
-                                  mesh_cells=mesh, pairwise="FALSE", **es)
+        return decks.crooked_pipe(precision=w["precision"], n_input=n_input, n_max=n_max, cellmin=cellmin,
+                                  mesh_cells=mesh, pairwise=pairwise, **es)
     if w["deck"] == "marshak":
         return decks.marshak(precision=w["precision"], n_cells=mesh[0], nonuniform=True, randomwalk="TRUE", n_input=n_input,
-                             n_max=n_max, cellmin=5, pairwise="FALSE")
+                             n_max=n_max, cellmin=cellmin, pairwise=pairwise)
     if w["deck"] == "suolson":
-        return decks.suolson(precision=w["precision"], n_input=n_input, n_max=n_max, pairwise="FALSE")
+        return decks.suolson(precision=w["precision"], n_input=n_input, n_max=n_max, pairwise=pairwise)
     raise ValueError(w["deck"])
+
+
+def cpu_sample_mesh(w: dict, mesh, particles: int, sample: int):
+    """Mesh of the bounded CPU sample: 1-D decks keep theirs; the 2-D mesh is scaled so that the sample has the GPU workload's
+    particles per cell (cells ~ sample / particles), because every cell emits at least CELLMIN particles per step and the
+    number of face crossings per history follows the resolution."""
+    if w["geom"] == 1:
+        return tuple(mesh)
+    f = min(1.0, (sample / max(particles, 1)) ** 0.5)
+    return (max(256, int(mesh[0] * f)), max(256, int(mesh[1] * f)))
 
 
 def bytes_per_segment(geom: int, s: int, seg_per_hist: float) -> float:
@@ -119,7 +138,7 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _cpu_shard_worker(rank, world, store_path, workload, mesh, sample, steps, warmup, q):
+def _cpu_shard_worker(rank, world, store_path, workload, mesh, sample, steps, warmup, q, pairwise="FALSE"):
     """One shard of the multi-process CPU run: the oracle behind the particle-sharded step of dist.py over gloo."""
     # under torchrun the parent's environment would steer this private group to the elastic agent's store
     for k in [k for k in os.environ if k.startswith("TORCHELASTIC") or k in ("MASTER_ADDR", "MASTER_PORT", "RANK", "WORLD_SIZE", "LOCAL_RANK",
@@ -131,7 +150,7 @@ def _cpu_shard_worker(rank, world, store_path, workload, mesh, sample, steps, wa
     from mpimc_b200 import driver, lib
     from mpimc_b200 import dist as imc_dist
     dist.init_process_group("gloo", init_method=f"file://{store_path}", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
-    sim = driver.setup(make_inputs(WORKLOADS[workload], sample, mesh), lib.ImcLib(entry.ORACLE_LIB), rank=rank, world=world)
+    sim = driver.setup(make_inputs(WORKLOADS[workload], sample, mesh, pairwise=pairwise), lib.ImcLib(entry.ORACLE_LIB), rank=rank, world=world)
     sim.save_history = False
     for _ in range(warmup):
         imc_dist.advance_sharded(sim)
@@ -145,7 +164,7 @@ def _cpu_shard_worker(rank, world, store_path, workload, mesh, sample, steps, wa
     dist.destroy_process_group()
 
 
-def cpu_port_run_parallel(workload, mesh, sample, steps, warmup, procs):
+def cpu_port_run_parallel(workload, mesh, sample, steps, warmup, procs, pairwise="FALSE"):
     """The oracle on `procs` host cores: one process per core, particles sharded exactly as the engine shards them over
     GPUs (striped emission, one all-reduce of the tallies per step over gloo).  Returns (segments/s, seconds, segments)."""
     import tempfile
@@ -157,7 +176,7 @@ def cpu_port_run_parallel(workload, mesh, sample, steps, warmup, procs):
     store_path = os.path.join(tmp, "store")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_cpu_shard_worker, args=(r, procs, store_path, workload, mesh, sample, steps, warmup, q)) for r in range(procs)]
+    ps = [ctx.Process(target=_cpu_shard_worker, args=(r, procs, store_path, workload, mesh, sample, steps, warmup, q, pairwise)) for r in range(procs)]
     for p_ in ps:
         p_.start()
     try:
@@ -178,14 +197,15 @@ def cpu_port_run_parallel(workload, mesh, sample, steps, warmup, procs):
     return seg / dt, dt, seg
 
 
-def traffic_from_profile(workload, mesh, particles):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the tracking kernel (bytes per launch) from the committed
-    `ncu --set full` capture of this workload (profiles/traffic.json), or None when no capture matches."""
+def traffic_from_profile(workload, mesh, particles, segments_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tracking kernel per launch.  ncu cannot run inside the timed bench,
+    so the figure is the committed `ncu --set full` capture of this workload (profiles/traffic.json: DRAM bytes and segments
+    of the captured launch) scaled to this run's segments per launch; None when no capture of this workload / mesh exists."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         for e in json.load(open(p)):
             if e["workload"] == workload and list(e["mesh"]) == list(mesh) and e["particles_per_gpu"] == particles:
-                return e["dram_bytes_per_launch"]
+                return e["dram_bytes_per_launch"] / e["segments_per_launch"] * segments_per_launch
     except Exception:
         pass
     return None
@@ -213,14 +233,14 @@ def tally_rel_err(w, mesh, sample_particles: int, glib, tally_mode, device: int)
     return out
 
 
-def cpu_port_run(w, mesh, sample_particles: int, steps: int, warmup: int):
+def cpu_port_run(w, mesh, sample_particles: int, steps: int, warmup: int, pairwise: str = "FALSE"):
     """Time the oracle (1 thread, like the reference) on a bounded sample of the workload."""
     import __graft_entry__ as entry
     from mpimc_b200 import driver, lib
     if not os.path.exists(entry.ORACLE_LIB):
         entry.build_oracle()
     olib = lib.ImcLib(entry.ORACLE_LIB)
-    inputs = make_inputs(w, sample_particles, mesh)
+    inputs = make_inputs(w, sample_particles, mesh, pairwise=pairwise)
     sim = driver.setup(inputs, olib)
     sim.save_history = False
     for _ in range(warmup):
@@ -249,17 +269,29 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tally", default="auto", choices=["auto", "atomic", "fixed"])
     ap.add_argument("--track", default="auto", choices=["auto", "history", "refill", "event"], help="tracking schedule (auto = measured)")
+    ap.add_argument("--pairwise", default="FALSE", choices=["FALSE", "TRUE"], help="the deck's PAIRWISE keyword (CrookedPipe.txt:96 ships TRUE)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --particles per GPU (NMAX grows with the GPU count); strong: --global-particles in total, split over the GPUs")
+    ap.add_argument("--global-particles", type=int, default=1_000_000_000, help="NMAX of the strong-scaling run (BASELINE config 5: 1e9)")
     args = ap.parse_args()
 
     w = WORKLOADS[args.workload]
     mesh = tuple(args.mesh) if args.mesh else w["mesh"]
-    particles = args.particles or w["particles"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{args.workload}: {w['deck']} {w['precision']} mesh {'x'.join(map(str, mesh))}, "
-                          f"{particles} particles per GPU (NMAX), NINPUT = NMAX/2, PAIRWISE FALSE",
-              "mesh": list(mesh), "particles_per_gpu": particles, "precision": w["precision"],
+    if args.scaling == "strong":
+        n_global = args.global_particles
+        particles = n_global // world
+    else:
+        particles = args.particles or w["particles"]
+        n_global = particles * world
+    cellmin = workload_cellmin(w, world, args.scaling)
+    config = {"workload": f"{args.workload}: {w['deck']} {w['precision']} mesh {'x'.join(map(str, mesh))}, NMAX = {n_global} particles "
+                          f"({particles} per GPU; NMAX caps the census + source population, the histories tracked per step are reported "
+                          f"as histories_per_step), NINPUT = NMAX/2, CELLMIN {cellmin}, PAIRWISE {args.pairwise}",
+              "mesh": list(mesh), "particles_per_gpu": particles, "nmax_global": n_global, "cellmin": cellmin, "pairwise": args.pairwise,
+              "precision": w["precision"], "scaling_mode": args.scaling,
               "l2_policy": "inputs larger than L2 (particle state >> 126 MB); no explicit flush",
               "tally_mode": args.tally, "tracking": f"schedule {args.track} (history static grid-stride | history warp-refill | event-based), 256 threads/block"}
 
@@ -268,31 +300,43 @@ def main():
         if rank != 0:
             return
         sample = args.cpu_sample or 10_000_000
-        cmesh = mesh if w["geom"] == 1 else (min(mesh[0], 256), min(mesh[1], 256))
+        cmesh = cpu_sample_mesh(w, mesh, particles, sample)
         nsteps, nwarm = max(1, min(args.steps, 3)), min(args.warmup, 1)
         # The reference itself is single-threaded Julia (no Threads / Distributed anywhere in the package); its C++ port is
         # timed here on all host cores it can use by sharding the particles over processes the way the engine shards them
         # over GPUs, and on one core the way the reference runs.
         cores = max(1, min(os.cpu_count() or 1, 32))
-        seg_1, dt_1, seg1, _ = cpu_port_run(w, cmesh, sample, nsteps, nwarm)
-        seg_s, dt, seg, used, psample = seg_1, dt_1, seg1, 1, sample
+        seg_1, dt_1, seg1, _ = cpu_port_run(w, cmesh, sample, nsteps, nwarm, args.pairwise)
+        seg_s, dt, seg, used, psample, pmesh = seg_1, dt_1, seg1, 1, sample, cmesh
         if cores > 1:
             try:
                 psample = sample * max(1, cores // 8)   # keep >= 1 s of work per timed step on a many-core host
-                seg_s, dt, seg = cpu_port_run_parallel(args.workload, cmesh, psample, nsteps, nwarm, cores)
+                pmesh = cpu_sample_mesh(w, mesh, particles, psample)
+                seg_s, dt, seg = cpu_port_run_parallel(args.workload, pmesh, psample, nsteps, nwarm, cores, args.pairwise)
                 used = cores
             except Exception as e:  # keep the single-core number rather than lose the arm
                 sys.stderr.write(f"bench.py: multi-process CPU run failed ({e}); reporting the single-core run\n")
+                psample, pmesh = sample, cmesh
+        # this arm's OWN configuration: a bounded sample of the workload (same deck, same physics, mesh scaled to keep the
+        # workload's particles per cell), not the GPU arm's mesh and population
+        rconfig = dict(config)
+        rconfig.update({"workload": f"{args.workload}: bounded CPU sample of that workload — {w['deck']} {w['precision']} mesh "
+                                    f"{'x'.join(map(str, pmesh))}, NMAX = {psample} particles, NINPUT = NMAX/2, CELLMIN {workload_cellmin(w)}, "
+                                    f"PAIRWISE {args.pairwise}, {nsteps} steps after {nwarm} warm-up from t = 0",
+                        "mesh": list(pmesh), "particles_per_gpu": None, "nmax_global": psample, "cellmin": workload_cellmin(w),
+                        "gpu_arm_mesh": list(mesh), "gpu_arm_nmax_global": n_global,
+                        "tally_mode": "reference order (sequential += / Base.sum)", "tracking": "history-based, one thread per process"})
         line = {"metric": "tracked particle-segments/sec", "value": seg_s, "unit": "segments/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / nsteps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["precision"].lower().replace("float", "f"),
-                "data": "synthetic", "config": config, "impl": "reference",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": w["precision"].lower().replace("float", "f"),
+                "data": "synthetic", "config": rconfig, "impl": "reference",
                 "cpu_baseline": {"value": seg_s, "unit": "segments/s", "cores": used, "kind": "port", "single_core_value": seg_1,
-                                 "sample": f"oracle (C++ restatement of the single-threaded Julia reference) on {psample if used > 1 else sample} particles, mesh "
-                                           f"{'x'.join(map(str, cmesh))} (every cell emits >= CELLMIN particles, so the mesh bounds the sample), "
+                                 "sample": f"oracle (C++ restatement of the single-threaded Julia reference) on {psample} particles, mesh "
+                                           f"{'x'.join(map(str, pmesh))}, "
                                            f"{nsteps} steps after {nwarm} warm-up: {seg} segments in {dt:.2f} s on {used} process(es), "
                                            f"particles sharded over processes like the engine shards them over GPUs (gloo all-reduce of the "
-                                           f"tallies); one process on {sample} particles: {seg1} segments in {dt_1:.2f} s"},
+                                           f"tallies); one process (the way the single-threaded reference runs) on {sample} particles, mesh "
+                                           f"{'x'.join(map(str, cmesh))}: {seg1} segments in {dt_1:.2f} s"},
                 "e2e": {"value": seg_s, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -313,7 +357,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     glib = lib.ImcLib(entry.LIB)
     tally_mode = {"auto": lib.TALLY_AUTO, "atomic": lib.TALLY_ATOMIC, "fixed": lib.TALLY_FIXED}[args.tally]
-    inputs = make_inputs(w, particles * world, mesh, world)  # NMAX / NINPUT are global; each rank emits its stripe
+    inputs = make_inputs(w, n_global, mesh, world, args.pairwise, args.scaling)  # NMAX / NINPUT are global; each rank emits its stripe
     track_mode = {"auto": lib.TRACK_AUTO, "history": lib.TRACK_HISTORY, "refill": lib.TRACK_REFILL, "event": lib.TRACK_EVENT}[args.track]
     sim = driver.setup(inputs, glib, device=local_rank, rank=rank, world=world, tally_mode=tally_mode, track_mode=track_mode)
     sim.save_history = False
@@ -344,9 +388,17 @@ def main():
             eng.field_native(k, out=pin[k])
         return r
 
+    import copy
     for _ in range(args.warmup):
         step_resident()
     barrier()
+    # Restart point: the resident loop and the host-buffer (e2e) loop below both run time steps W .. W+K-1 of the same
+    # simulation from this state (imc_checkpoint copies the engine's state on the device; the host's t / dt / step are
+    # copied here), so their step times compare one to one.
+    for k in pin:
+        eng.field_native(k, out=pin[k])
+    eng.checkpoint("save")
+    sv0 = copy.deepcopy(sim.simvars)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -354,6 +406,7 @@ def main():
     seg = hist = 0
     kms = 0.0
     variants = []
+    modes = set()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     estream = torch.cuda.ExternalStream(eng.stream(), device=dev)   # the stream the engine launches its kernels on
@@ -364,28 +417,34 @@ def main():
         r = step_resident()
         seg += r["transport"]["segments"]; hist += r["transport"]["histories"]; kms += r["transport"]["kernel_ms"]
         variants.append({1: "static", 2: "refill", 3: "event"}.get(r["transport"]["variant"], "?"))
+        modes.add({0: "auto", 1: "atomic", 2: "fixed", 3: "exact"}.get(r["transport"].get("tally_mode", -1), "?"))
     ev1.record(estream)
     barrier()
     wall = time.perf_counter() - t0
     dev_s = ev0.elapsed_time(ev1) * 1e-3          # device time of the K steps on the engine's stream
     launches = eng.kernel_launches() - l0
     n_part = eng.num_particles()
-    # end-to-end: same steps through host buffers
-    if pin["temp"].dtype != eng.field_dtype("temp"):   # mesh.temp turned Float64 during the resident steps (Q12)
-        pin["temp"] = torch.empty(nc, dtype=torch.float64).pin_memory().numpy()
-    for k in pin:
-        eng.field_native(k, out=pin[k])
+    # end-to-end: the SAME K time steps again, through host buffers
+    eng.checkpoint("restore")
+    sim.simvars = copy.deepcopy(sv0)
+    if pin["temp"].dtype != eng.field_dtype("temp"):   # element type of mesh.temp at the restart point (Q12)
+        pin["temp"] = torch.empty(nc, dtype=tdt[eng.field_dtype("temp")]).pin_memory().numpy()
+        eng.field_native("temp", out=pin["temp"])
     barrier()
     ev2.record(estream)
     t1 = time.perf_counter()
     seg_e = 0
     for _ in range(args.steps):
+        if pin["temp"].dtype != eng.field_dtype("temp"):   # mesh.temp turned Float64 in the previous step (Q12, first LINEARIZED tally)
+            pin["temp"] = torch.empty(nc, dtype=torch.float64).pin_memory().numpy()
+            eng.field_native("temp", out=pin["temp"])
         r = step_e2e()
         seg_e += r["transport"]["segments"]
     ev3.record(estream)
     barrier()
     wall_e = time.perf_counter() - t1
     dev_e_s = ev2.elapsed_time(ev3) * 1e-3
+    eng.checkpoint("drop")
     io_bytes = sum(int(v.nbytes) for v in pin.values())
     if rank == 0:
         sampler.stop_flag.set()
@@ -408,30 +467,34 @@ def main():
         line = {
             "metric": "tracked particle-segments/sec", "value": seg_g / wall_g, "unit": "segments/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall_g / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": w["precision"].lower().replace("float", "f"), "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": w["precision"].lower().replace("float", "f"), "data": "synthetic",
             "config": config,
-            "histories_per_s": hist_g / wall_g, "segments_per_history": sph, "particles_resident": n_part_g,
+            "histories_per_s": hist_g / wall_g, "histories_per_step": hist_g / args.steps, "segments_per_step": seg_g / args.steps,
+            "segments_per_history": sph, "particles_resident": n_part_g, "tally_modes_run": sorted(modes),
             "tracking_kernel_ms_per_step": kms_g / args.steps, "tracking_kernel_share_of_step": kms_g / (1e3 * wall_g),
             "timing": "CUDA events on the engine's stream, max over ranks", "host_wall_ms_per_step": 1e3 * host_wall_g / args.steps,
             "e2e": {"value": seg_e_g / wall_e_g, "unit": "segments/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                     "ms_per_step": 1e3 * wall_e_g / args.steps, "host_wall_ms_per_step": 1e3 * host_wall_e_g / args.steps,
-                    "path": "imc_set_state_native (pinned Array{T} -> device) + the step + imc_get_field_native x3 (device -> pinned Array{T})"},
+                    "segments_per_step": seg_e_g / args.steps,
+                    "path": "imc_set_state_native (pinned Array{T} -> device) + the step + imc_get_field_native x3 (device -> pinned Array{T}); "
+                            "the same K time steps as `value`, restarted from imc_checkpoint"},
             "gpu_launches": launches, "schedule_per_step": variants,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_from_profile(args.workload, mesh, particles),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_from_profile(args.workload, mesh, particles, seg / max(args.steps, 1)),
+                         "traffic_source": "profiles/traffic.json: dram__bytes of the committed ncu capture of this kernel, scaled by segments per launch",
                          "kernel": ("k_track1d_rw" if w["deck"] == "marshak" else
                                     {"refill": f"k_track_refill<{w['geom']}-D>", "static": f"k_track{w['geom']}d", "event": "k_track_event"}.get(variants[-1], "?")),
                          "bytes_per_segment": bps, "peak_source": peak_src},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:   # the CPU legs run on rank 0 at N = 1 only
-            sample = args.cpu_sample or 10_000_000
-            cmesh = mesh if w["geom"] == 1 else (min(mesh[0], 256), min(mesh[1], 256))
-            seg_s, dt, cseg, chist = cpu_port_run(w, cmesh, sample, 2, 1)
+            sample = args.cpu_sample or 4_000_000
+            cmesh = cpu_sample_mesh(w, mesh, particles, sample)
+            seg_s, dt, cseg, chist = cpu_port_run(w, cmesh, sample, 2, 1, args.pairwise)
             line["cpu_baseline"] = {"value": seg_s, "unit": "segments/s", "cores": 1, "kind": "port",
                                     "sample": f"oracle (C++ restatement of the Julia reference, single-threaded like it) on {sample} particles, "
                                               f"mesh {'x'.join(map(str, cmesh))}, 2 steps after 1 warm-up: {cseg} segments in {dt:.1f} s"}
             try:
-                line["tally_rel_err"] = tally_rel_err(w, cmesh, min(sample, 2_000_000), glib, tally_mode, local_rank)
+                line["tally_rel_err"] = tally_rel_err(w, cpu_sample_mesh(w, mesh, particles, min(sample, 2_000_000)), min(sample, 2_000_000), glib, tally_mode, local_rank)
             except Exception as e:  # a reported metric, never a reason to lose the bench line
                 line["tally_rel_err"] = {"error": str(e)}
         print(json.dumps(line))

@@ -203,13 +203,9 @@ int imc_step(imc_handle h, double t, double dt, int64_t n_input, double cellmin,
 
 /* The buffer a multi-GPU host must sum over ranks between imc_tally_local and imc_tally_finish:
  * [energydep Nc*Ns | radenergydens Nc | lostenergy | counters...], n slots of 8 bytes.  *kind says how to sum them:
- *   0  Float64 throughout;
- *   1  int64 throughout (the engine accumulates in fixed point: FIXED tallies);
- *   2  the [energydep] region holds Nc*Ns Float32 accumulators in its first 4*Nc*Ns bytes (Float16 / Float32 decks with
- *      ATOMIC tallies in global memory: deposits accumulate in Float32, as the reference's `energydep[cell] += dep`
- *      does in the deck precision, imc_transport.jl:120) — sum those as Float32 — and the tail, at byte offset
- *      8*Nc*Ns, is Float64.
- * The kind follows from the deck, the mesh size and the tally mode alone, so it is the same on every rank.
+ *   0  Float64 throughout (ATOMIC and EXACT tallies);
+ *   1  int64 throughout (the engine accumulates in fixed point: FIXED tallies; sums are then independent of the GPU count).
+ * The kind follows from the deck, the tally mode and replicated quantities alone, so it is the same on every rank.
  * *ptr is a device pointer for the CUDA library, a host pointer for the oracle (always kind 0).
  * The call waits for the engine's stream, i.e. for everything issued before it (the tracking kernel, imc_tally_local's
  * census tally): a host that runs its collective on another stream calls it immediately before reducing each part —
@@ -274,6 +270,16 @@ int imc_set_source_tape(imc_handle h, const double* uniforms, int32_t n_uni, int
  * terminate when the first draw exceeds the largest value 90 nsum / pi^4 can reach in the deck precision (Float32:
  * 0.9999989); such a sample is returned as NaN after 100000 terms. */
 int imc_sample_planck(imc_handle h, int64_t n, int64_t step, double* out);
+
+/* Restart point inside the library (the reference has none: its state lives in Julia objects a host can copy with
+ * `deepcopy(mesh)`, `deepcopy(particles)`; here the engine owns that state, MixedPrecisionIMC.jl:112-133).
+ * op = IMC_CKPT_SAVE copies everything a later call can change — the particle population, the per-cell fields
+ * (temp, fleck, sigma_a/s, beta, bee, the energy densities, energydep / emittedenergy), lostenergy, the scalars of
+ * imc_*_stats — into a second set of device buffers; IMC_CKPT_RESTORE makes that copy current again (any number of
+ * times); IMC_CKPT_DROP frees it.  The host restores its own step counter / t / dt.  bench.py uses it to time the
+ * resident and the host-buffer path over the SAME time steps. */
+enum { IMC_CKPT_SAVE = 0, IMC_CKPT_RESTORE = 1, IMC_CKPT_DROP = 2 };
+int imc_checkpoint(imc_handle h, int32_t op);
 
 /* per-particle outcome of the last imc_transport call, for replay checks:
  * event[i] = 0 census, 1 absorbed (energy cut-off), 2 escaped (VACUUM), 3 random-walk kill;

@@ -41,6 +41,7 @@ struct EngineBase {
   virtual int set_source_tape(const double*, int, int64_t) = 0;
   virtual int get_outcomes(int32_t*, int32_t*, int64_t) = 0;
   virtual int sample_planck(int64_t, int64_t, double*) = 0;
+  virtual int checkpoint(int) = 0;
 };
 
 EngineBase* make_engine_f16(const imc_config& cfg);

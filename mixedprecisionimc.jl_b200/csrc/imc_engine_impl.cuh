@@ -94,9 +94,6 @@ struct EngineT : EngineBase {
   long long red_n = 0;
   bool red_fixed = false;
   bool y_fastest = false, dep_perm = false;   // layout of the CellProp2 table / of the deposit accumulators of the last transport (MeshDev::csx ...)
-  DBuf<float> dep_strided;   // experiment (IMC_DEP_STRIDE > 2)
-  bool dep_f32 = false;   // the [energydep] region holds Float32 accumulators (its first nc*ns 4-byte words): Float16 / Float32 decks,
-                          // ATOMIC tallies in global memory, Philox history kernels (Tally::add)
   double fx_mul_dep = 1, fx_mul_rad = 1, fx_mul_lost = 1;
   // sourcing scratch
   SrcLayout L;
@@ -144,6 +141,10 @@ struct EngineT : EngineBase {
   double totalenergy = 0, totalenergydep = 0, radenergyold = 0;
   uint64_t iterations = 0;
   long long n_transport_calls = 0;
+  // replicated quantities behind the EXACT-or-not decision of AUTO (identical on every rank of a multi-GPU run): the segments
+  // all ranks tracked in the previous step (read from the all-reduced buffer by tally_finish) and the global population
+  // after sourcing
+  double last_global_segments = 0; long long n_global_after_source = 0;
   double rate_static = 0, rate_refill = 0;  // segments per ms of each schedule, last measured
   static int refill_min_env() { const char* e = getenv("IMC_REFILL_MIN"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 32 ? 32 : v); }
   int64_t n_launch = 0;  // kernels launched by this engine (bench.py reports it as gpu_launches)
@@ -295,7 +296,6 @@ struct EngineT : EngineBase {
     if (geom == 1) IMC_CK(cp1.alloc(nc)); else IMC_CK(cp2.alloc(nc));
     red_n = nc * ns + nc + RB_NSCALARS;
     IMC_CK(red.alloc(red_n));
-    if (IMC_DEP_STRIDE > 2) IMC_CK(dep_strided.alloc((size_t)nc * ns * IMC_DEP_STRIDE));   // experiment
     // sourcing / tally scratch
     long long M = L.total();
     IMC_CK(src_e.alloc(M)); IMC_CK(src_q.alloc(M)); IMC_CK(src_nrg.alloc(M)); IMC_CK(src_ks.alloc(M)); IMC_CK(src_cnt.alloc(M));
@@ -383,6 +383,7 @@ struct EngineT : EngineBase {
   // ---- Sourcing.sourcing ---------------------------------------------------------------------
   int source(double dt_, int64_t n_input, double cellmin_, int64_t step, int64_t n_census_global, imc_source_stats* out) override {
     if (!have_mesh) { err = "source before set_mesh"; return IMC_ERR_STATE; }
+    if (step < 0 || step >= (1ll << 24)) { err = "time-step index outside [0, 2^24): particle ids are step << 40 | ordinal and the Philox counter carries the step in 28 bits"; return IMC_ERR_ARG; }
     IMC_RC(use_device());
     Cc dt = P::from_d(dt_), cellmin = P::from_d(cellmin_);
     SrcArrays<P> s; s.e = src_e.p; s.q = src_q.p; s.ks = src_ks.p; s.cnt = src_cnt.p; s.nrg = src_nrg.p; s.q_em = src_qem.p;
@@ -428,6 +429,7 @@ struct EngineT : EngineBase {
       if (over) { err = "source tape exhausted"; return IMC_ERR_TAPE; }
     }
     n_part += n_local;
+    n_global_after_source = (n_census_global >= 0 ? (long long)n_census_global : n_part - n_local) + total;
     if (out) {
       out->totalenergy = totalenergy; out->emitted_sum = (double)h_emsum; out->n_source = (int64_t)hsc.nsrc;
       out->n_new_global = total; out->n_new_local = n_local; out->n_particles = n_part;
@@ -488,7 +490,13 @@ struct EngineT : EngineBase {
     }
     fx_mul_dep = pow2_floor_mul(tot / min_vol_h);
     fx_mul_rad = pow2_floor_mul(tot / (min_vol_h * min_scale_h));
-    fx_mul_lost = pow2_floor_mul(tot / min_scale_h);
+    // lostenergy keeps accumulating across transport calls until energycheck resets it: an integer already stored at the
+    // previous scale is carried over to the new one (both are powers of two)
+    const double new_lost = pow2_floor_mul(tot / min_scale_h);
+    if (red_fixed && new_lost != fx_mul_lost) {
+      k_rescale_fixed<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(red.p) + rb_sc0() + RB_LOST, new_lost / fx_mul_lost); ++n_launch;
+    }
+    fx_mul_lost = new_lost;
     ta.fx_mul = fx_mul_dep; ta.fx_mul_lost = fx_mul_lost;
     return IMC_OK;
   }
@@ -589,6 +597,7 @@ struct EngineT : EngineBase {
   int transport(double dt_, int64_t step, imc_transport_stats* out) override {
     if (!have_mesh) { err = "transport before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
+    if (step < 0 || step >= (1ll << 24)) { err = "time-step index outside [0, 2^24)"; return IMC_ERR_ARG; }
     if (cfg.randomwalk && !have_rw) { err = "random-walk tables not set (imc_rw_table)"; return IMC_ERR_STATE; }
     if (cfg.rng_mode == IMC_RNG_TAPE && n_part > tt_slots) { err = "transport tape has fewer slots than particles"; return IMC_ERR_TAPE; }
     if (n_part >= (1ll << 32)) { err = "more than 2^32 particles on one GPU"; return IMC_ERR_ARG; }
@@ -613,14 +622,9 @@ struct EngineT : EngineBase {
     a.tally.use_smem = (smem_fits(smem, COUNTER_SMEM_BYTES) && mode != IMC_TALLY_EXACT) ? 1 : 0;
     a.tally.copies = a.tally.use_smem ? smem_copies(smem, COUNTER_SMEM_BYTES) : 1;
     smem = a.tally.use_smem ? smem * a.tally.copies : 0;
-    // decided from the deck and the mesh alone, so that every rank of a multi-GPU run reduces the same element type
-    dep_f32 = IMC_DEP_F32 && P::id != 2 && mode == IMC_TALLY_ATOMIC && !a.tally.use_smem;
-    a.tally.dep_f32 = dep_f32 ? 1 : 0;
     static const int tforce = getenv("IMC_TALLY_ORDER") ? atoi(getenv("IMC_TALLY_ORDER")) : 0;   // 1: x fastest, 2: y fastest (experiments)
     dep_perm = geom == 2 && tforce == 2 && mode != IMC_TALLY_EXACT && !a.tally.use_smem;
     a.m.tsx = dep_perm ? ny : 1; a.m.tsy = dep_perm ? 1 : nx;
-    a.tally.g_dep32 = IMC_DEP_STRIDE > 2 ? dep_strided.p : reinterpret_cast<float*>(red.p);
-    if (IMC_DEP_STRIDE > 2 && dep_f32) IMC_CK(cudaMemsetAsync(dep_strided.p, 0, (size_t)nc * ns * IMC_DEP_STRIDE * sizeof(float), stream));
     // outcome records for replay checks (small populations only)
     bool record = n_part <= (1ll << 22);
     if (record) {
@@ -681,7 +685,20 @@ struct EngineT : EngineBase {
       if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / (smem + COUNTER_SMEM_BYTES)));
       unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
       IMC_CK(cudaEventRecord(ev0, stream));
-      if (mode == IMC_TALLY_EXACT) {
+      const long long budget = cfg.exact_record_budget > 0 ? cfg.exact_record_budget : (1ll << 28);
+      const bool auto_mode = cfg.tally_mode == IMC_TALLY_AUTO;
+      bool skip_exact = false;
+      if (mode == IMC_TALLY_EXACT && auto_mode) {
+        // AUTO: one deposit record per segment.  Predict this rank's records from replicated quantities — the segments all
+        // ranks tracked in the previous step, at least one per particle of the global population — with a margin for the
+        // growth from one step to the next, and go straight to the order-free accumulation when they cannot fit: the
+        // count-only pass is a whole tracking pass (it used to run, and be thrown away, every step at scale), and every
+        // rank must take the same branch because the host sums the buffers element by element.
+        const double world_d = (double)(cfg.world > 0 ? cfg.world : 1);
+        const double pred = std::max(last_global_segments, (double)std::max(n_global_after_source, n_part)) / world_d;
+        skip_exact = 1.5 * pred > (double)budget;
+      }
+      if (mode == IMC_TALLY_EXACT && !skip_exact) {
         // pass 1: count the deposits of every particle (no side effects), scan -> record offsets
         IMC_CK(rec_cnt.ensure((size_t)n_part)); IMC_CK(rec_off.ensure((size_t)n_part + 1)); IMC_CK(lost_val.ensure((size_t)n_part));
         a.tally.pass = 1; a.tally.rec_cnt = rec_cnt.p;
@@ -690,18 +707,14 @@ struct EngineT : EngineBase {
         long long R = 0;
         IMC_CK(cudaMemcpyAsync(&R, scan_total.p, sizeof R, cudaMemcpyDeviceToHost, stream));
         IMC_CK(cudaStreamSynchronize(stream));
-        long long budget = cfg.exact_record_budget > 0 ? cfg.exact_record_budget : (1ll << 28);
         if (R > budget) {
           if (cfg.tally_mode == IMC_TALLY_EXACT) { err = "EXACT tally mode: deposit records exceed exact_record_budget"; return IMC_ERR_NOMEM; }
-          mode = cfg.pairwise ? IMC_TALLY_FIXED : IMC_TALLY_ATOMIC;  // AUTO: fall back to order-free fixed point / float atomics
-          if (mode == IMC_TALLY_FIXED && !red_fixed) { IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream)); red_fixed = true; }
-          a.tally.mode = mode; a.tally.pass = 0;
-          if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
-          smem = smem_for(mode, nc * ns); a.tally.use_smem = smem_fits(smem, COUNTER_SMEM_BYTES) ? 1 : 0;
-          a.tally.copies = a.tally.use_smem ? smem_copies(smem, COUNTER_SMEM_BYTES) : 1; smem = a.tally.use_smem ? smem * a.tally.copies : 0;
-          dep_f32 = IMC_DEP_F32 && P::id != 2 && mode == IMC_TALLY_ATOMIC && !a.tally.use_smem; a.tally.dep_f32 = dep_f32 ? 1 : 0;
-          dep_perm = false; a.m.tsx = 1; a.m.tsy = nx;
-          IMC_RC(launch_track(a, variant, grid, smem));
+          if (cfg.world > 1) {
+            err = "AUTO tally mode: this rank's deposit records exceed exact_record_budget although the replicated prediction fitted; "
+                  "every rank must accumulate in the same representation — set the tally mode explicitly or raise exact_record_budget";
+            return IMC_ERR_NOMEM;
+          }
+          skip_exact = true;   // single GPU: fall back now (the prediction had no history yet)
         } else {
           for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)std::max<long long>(R, 1))); IMC_CK(rec_val[b].ensure((size_t)std::max<long long>(R, 1))); }
           IMC_CK(cudaMemsetAsync(lost_val.p, 0xFF, (size_t)n_part * sizeof(double), stream));  // NaN = no loss
@@ -721,7 +734,18 @@ struct EngineT : EngineBase {
           }
           IMC_CK(cudaGetLastError());
         }
-      } else {
+      }
+      if (mode == IMC_TALLY_EXACT && skip_exact) {   // AUTO: order-free fixed point (PAIRWISE) / float atomics instead
+        mode = cfg.pairwise ? IMC_TALLY_FIXED : IMC_TALLY_ATOMIC;
+        if (mode == IMC_TALLY_FIXED && !red_fixed) { IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream)); red_fixed = true; }
+        a.tally.mode = mode; a.tally.pass = 0;
+        if (mode == IMC_TALLY_FIXED) IMC_RC(prepare_fixed(a.tally));
+        smem = smem_for(mode, nc * ns); a.tally.use_smem = smem_fits(smem, COUNTER_SMEM_BYTES) ? 1 : 0;
+        a.tally.copies = a.tally.use_smem ? smem_copies(smem, COUNTER_SMEM_BYTES) : 1; smem = a.tally.use_smem ? smem * a.tally.copies : 0;
+        dep_perm = false; a.m.tsx = 1; a.m.tsy = nx;
+        if (smem > 0) grid = (unsigned)std::min<long long>(grid, (long long)sm_count * std::max<size_t>(1, std::min<size_t>(2048 / TRACK_THREADS, (200 * 1024) / (smem + COUNTER_SMEM_BYTES))));
+        IMC_RC(launch_track(a, variant, grid, smem));
+      } else if (mode != IMC_TALLY_EXACT) {
         IMC_RC(launch_track(a, variant, grid, smem));
       }
       IMC_CK(cudaEventRecord(ev1, stream));
@@ -796,7 +820,7 @@ struct EngineT : EngineBase {
     IMC_CK(cudaMemsetAsync(red.p + rb_rad0(), 0, nc * sizeof(double), stream));
     if (n_part == 0) return IMC_OK;
     TallyArgs ta;
-    ta.pass = 0; ta.rec_cnt = nullptr; ta.rec_off = nullptr; ta.rec_key = nullptr; ta.rec_val = nullptr; ta.lost_val = nullptr; ta.dep_f32 = 0; ta.g_dep32 = nullptr;
+    ta.pass = 0; ta.rec_cnt = nullptr; ta.rec_off = nullptr; ta.rec_key = nullptr; ta.rec_val = nullptr; ta.lost_val = nullptr;
     if (mode == IMC_TALLY_EXACT) {  // per-cell vectors + Julia sum, in particle order (imc_tally.jl:84-113, Q19)
       for (int b = 0; b < 2; ++b) { IMC_CK(rec_key[b].ensure((size_t)n_part)); IMC_CK(rec_val[b].ensure((size_t)n_part)); }
       ta.mode = mode; ta.nacc = (int)nc; ta.use_smem = 0; ta.copies = 1; ta.g_acc = nullptr; ta.g_fx = nullptr; ta.fx_mul = 1; ta.fx_mul_lost = 1; ta.sc0 = 0;
@@ -821,7 +845,7 @@ struct EngineT : EngineBase {
   int tally_finish(double t_, double dt_, imc_tally_stats* out) override {
     if (!have_mesh) { err = "tally before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
-    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>((IMC_DEP_STRIDE > 2 && dep_f32 && !red_fixed) ? reinterpret_cast<double*>(dep_strided.p) : red.p + rb_dep0(), red_fixed ? 1 : (dep_f32 ? 2 : 0), fx_mul_dep, nc * ns, energydep.p,
+    k_acc_to_field<P><<<grid_for(nc * ns, 256), 256, 0, stream>>>(red.p + rb_dep0(), red_fixed ? 1 : 0, fx_mul_dep, nc * ns, energydep.p,
                                                                      nc, dep_perm ? nx : 0, ny, 1); ++n_launch;
     k_acc_to_field<P><<<grid_for(nc, 256), 256, 0, stream>>>(red.p + rb_rad0(), red_fixed ? 1 : 0, fx_mul_rad, nc, radenergydens.p, nc, 0, 0, 0); ++n_launch;
     TallyScratch<P> s; s.q_dep = q_dep.p; s.q_tot = q_tot.p; s.q_rad = q_rad.p;
@@ -848,12 +872,14 @@ struct EngineT : EngineBase {
     IMC_CK(cudaMemsetAsync(d_flag.p, 0, sizeof(int), stream));
     k_max_f64<<<sm_count * 2, 256, 0, stream>>>(temp.p, nc, d_max.p, d_flag.p); ++n_launch;
     IMC_CK(cudaGetLastError());
-    Cc h2[3]; double mx; int has_nan;
+    Cc h2[3]; double mx; int has_nan; double gseg = 0;
+    IMC_CK(cudaMemcpyAsync(&gseg, red.p + rb_sc0() + RB_SEG, sizeof gseg, cudaMemcpyDeviceToHost, stream));   // summed over ranks by the host
     IMC_CK(cudaMemcpyAsync(h2, sums.p + 12, 3 * sizeof(Cc), cudaMemcpyDeviceToHost, stream));
     IMC_CK(cudaMemcpyAsync(&mx, d_max.p, sizeof mx, cudaMemcpyDeviceToHost, stream));
     IMC_CK(cudaMemcpyAsync(&has_nan, d_flag.p, sizeof has_nan, cudaMemcpyDeviceToHost, stream));
     IMC_CK(cudaStreamSynchronize(stream));
     rad_total_h = (double)h2[2];
+    if (red_fixed) { long long v; memcpy(&v, &gseg, 8); last_global_segments = (double)v; } else last_global_segments = gseg;
     IMC_RC(history_push());
     if (out) {
       out->totalenergydep = totalenergydep; out->energy_increase = (double)h2[0];
@@ -888,7 +914,7 @@ struct EngineT : EngineBase {
     if (!have_mesh) { err = "reduce_buffer before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     IMC_CK(cudaStreamSynchronize(stream));  // the host's collective runs on another stream
-    *ptr = red.p; *n = red_n; *is_int = red_fixed ? 1 : (dep_f32 ? 2 : 0);
+    *ptr = red.p; *n = red_n; *is_int = red_fixed ? 1 : 0;
     return IMC_OK;
   }
 
@@ -1121,6 +1147,64 @@ struct EngineT : EngineBase {
     IMC_CK(cudaMemcpyAsync(&over, over_flag.p, sizeof over, cudaMemcpyDeviceToHost, stream));
     IMC_CK(cudaStreamSynchronize(stream));
     if (over) { err = "source tape exhausted"; return IMC_ERR_TAPE; }
+    return IMC_OK;
+  }
+  // ---- restart point in device memory (include/imc.h imc_checkpoint) ------------------------------------------
+  struct CkptHost {
+    long long n_part; bool temp_wide, red_fixed, dep_perm; double fx_mul_dep, fx_mul_rad, fx_mul_lost, rad_total_h;
+    int last_mode; double totalenergy, totalenergydep, radenergyold; uint64_t iterations; long long n_transport_calls;
+    double rate_static, rate_refill, rate_event; long long hist_n, hist_dropped; double last_global_segments; long long n_global_after_source;
+  };
+  DBuf<unsigned char> ckpt_blob;
+  CkptHost ckpt_host;
+  bool ckpt_valid = false;
+  // every device array a step can change, as (address, bytes); particles: the live prefix of the current buffer
+  std::vector<std::pair<void*, size_t>> ckpt_items(long long np) {
+    std::vector<std::pair<void*, size_t>> v;
+    auto add = [&](void* p, size_t b) { if (p && b) v.emplace_back(p, b); };
+    const size_t S_ = sizeof(S);
+    add(sa.p, nc * S_); add(ss.p, nc * S_); add(fleck.p, nc * S_); add(beta.p, nc * S_); add(bee.p, nc * S_);
+    add(temp.p, nc * sizeof(double)); add(matenergydens.p, nc * S_); add(radenergydens.p, nc * S_); add(nrg_inc.p, nc * S_);
+    add(energydep.p, nc * ns * S_); add(emittedenergy.p, nc * ns * S_);
+    if (geom == 1) add(cp1.p, nc * sizeof(CellProp1<P>)); else add(cp2.p, nc * sizeof(CellProp2<P>));
+    add(red.p, (size_t)red_n * sizeof(double));
+    PartBufs<P>& b = pb[cur];
+    add(b.t.p, np * S_); add(b.x.p, np * S_); add(b.mu.p, np * S_); add(b.E.p, np * S_); add(b.E0.p, np * S_);
+    add(b.cx.p, np * sizeof(int)); add(b.ks.p, (size_t)np); add(b.id.p, np * sizeof(unsigned long long));
+    if (geom == 2) { add(b.y.p, np * S_); add(b.cy.p, np * sizeof(int)); } else add(b.origin.p, np * sizeof(int));
+    return v;
+  }
+  int checkpoint(int op) override {
+    if (!have_mesh) { err = "checkpoint before set_mesh"; return IMC_ERR_STATE; }
+    IMC_RC(use_device());
+    if (op == IMC_CKPT_DROP) { IMC_CK(cudaStreamSynchronize(stream)); ckpt_blob.release(); ckpt_valid = false; return IMC_OK; }
+    if (op == IMC_CKPT_SAVE) {
+      auto items = ckpt_items(n_part);
+      size_t total = 0;
+      for (auto& it : items) total += (it.second + 255) & ~(size_t)255;
+      IMC_CK(ckpt_blob.ensure(total));
+      size_t off = 0;
+      for (auto& it : items) { IMC_CK(cudaMemcpyAsync(ckpt_blob.p + off, it.first, it.second, cudaMemcpyDeviceToDevice, stream)); off += (it.second + 255) & ~(size_t)255; }
+      ckpt_host = CkptHost{n_part, temp_wide, red_fixed, dep_perm, fx_mul_dep, fx_mul_rad, fx_mul_lost, rad_total_h, last_mode, totalenergy,
+                           totalenergydep, radenergyold, iterations, n_transport_calls, rate_static, rate_refill, rate_event, hist_n, hist_dropped, last_global_segments, n_global_after_source};
+      IMC_CK(cudaStreamSynchronize(stream));
+      ckpt_valid = true;
+      return IMC_OK;
+    }
+    if (op != IMC_CKPT_RESTORE) { err = "checkpoint: unknown op"; return IMC_ERR_ARG; }
+    if (!ckpt_valid) { err = "checkpoint: nothing saved"; return IMC_ERR_STATE; }
+    IMC_RC(ensure_capacity(ckpt_host.n_part));
+    const CkptHost& c = ckpt_host;
+    n_part = c.n_part; temp_wide = c.temp_wide; red_fixed = c.red_fixed; dep_perm = c.dep_perm;
+    fx_mul_dep = c.fx_mul_dep; fx_mul_rad = c.fx_mul_rad; fx_mul_lost = c.fx_mul_lost; rad_total_h = c.rad_total_h; last_mode = c.last_mode;
+    totalenergy = c.totalenergy; totalenergydep = c.totalenergydep; radenergyold = c.radenergyold; iterations = c.iterations;
+    n_transport_calls = c.n_transport_calls; rate_static = c.rate_static; rate_refill = c.rate_refill; rate_event = c.rate_event;
+    hist_n = std::min(hist_n, c.hist_n); hist_dropped = c.hist_dropped;
+    last_global_segments = c.last_global_segments; n_global_after_source = c.n_global_after_source;
+    auto items = ckpt_items(n_part);   // same order and sizes as at save time: the mesh is fixed, n_part restored above
+    size_t off = 0;
+    for (auto& it : items) { IMC_CK(cudaMemcpyAsync(it.first, ckpt_blob.p + off, it.second, cudaMemcpyDeviceToDevice, stream)); off += (it.second + 255) & ~(size_t)255; }
+    IMC_CK(cudaStreamSynchronize(stream));
     return IMC_OK;
   }
   int get_outcomes(int32_t* ev, int32_t* nseg, int64_t capacity) override {

@@ -30,12 +30,6 @@ namespace imc {
 #define IMC_CELL_GATHER_CG 0    // MC2D: 1 = gather the per-cell constants through L2 only; 0 = cached in L1 (the table is laid out so that
                                 // consecutive cells of a history mostly share a sector, MeshDev::csx)
 #endif
-#ifndef IMC_DEP_F32
-#define IMC_DEP_F32 0           // Float16 / Float32 decks: ATOMIC deposits in global memory accumulate in Float32 (RED.F32)
-#endif
-#ifndef IMC_DEP_STRIDE
-#define IMC_DEP_STRIDE 1        // experiment: Float32 accumulators every IMC_DEP_STRIDE 4-byte words
-#endif
 #ifndef IMC_FASTDIV_DIR
 #define IMC_FASTDIV_DIR 1       // MC2D: divide by the direction cosines with cached reciprocals (imc_fastdiv.cuh)
 #endif
@@ -52,24 +46,25 @@ template <class P> constexpr int track_min_blocks() { return P::id == 2 && IMC_T
 enum { RB_LOST = 0, RB_SEG, RB_HIST, RB_CENSUS, RB_ABSORBED, RB_ESCAPED, RB_RW, RB_ERRORS, RB_NSCALARS };
 
 template <class P> struct CellProp1 { typename P::store_t w, dx, sig_col, neg_saf; };   // w = dx*ds
-template <class P> struct CellProp2 { typename P::store_t sig_col, neg_saf; };
+template <class P> struct alignas(2 * sizeof(typename P::store_t)) CellProp2 { typename P::store_t sig_col, neg_saf; };
 // per-axis-index constants {w = d*ds, q}: q = 1/d in the table the ATOMIC / FIXED tallies read (deposit = E (1/dx)(1/dy) ..),
 // q = d in the table the EXACT tallies read (deposit = (E/dx)/dy as the reference writes it); one 2-element load
 template <class P> struct alignas(2 * sizeof(typename P::store_t)) AxisProp { typename P::store_t w, q; };
 
-// The per-cell constants are gathered by cell index, once per cell entered: read through L2 only (ld.global.cg),
-// so that the gathers do not evict the small per-axis tables and the particle stream from L1.
+// The per-cell constants are gathered by cell index, once per cell entered, as one vector load.
 template <class P>
-__device__ __forceinline__ CellProp2<P> load_cell2(const CellProp2<P>* tab, int c) {
+__device__ __forceinline__ CellProp2<P> load_cell2(const CellProp2<P>* tab, long long c) {
+  CellProp2<P> r;   // one 4 / 8 / 16-byte load
 #if IMC_CELL_GATHER_CG
-  CellProp2<P> r;
   if constexpr (P::id == 0) { const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(tab) + c); r.sig_col = (uint16_t)(v & 0xffffu); r.neg_saf = (uint16_t)(v >> 16); }
   else if constexpr (P::id == 1) { const float2 v = __ldcg(reinterpret_cast<const float2*>(tab) + c); r.sig_col = v.x; r.neg_saf = v.y; }
   else { const double2 v = __ldcg(reinterpret_cast<const double2*>(tab) + c); r.sig_col = v.x; r.neg_saf = v.y; }
-  return r;
 #else
-  return tab[c];
+  if constexpr (P::id == 0) { const unsigned v = reinterpret_cast<const unsigned*>(tab)[c]; r.sig_col = (uint16_t)(v & 0xffffu); r.neg_saf = (uint16_t)(v >> 16); }
+  else if constexpr (P::id == 1) { const float2 v = reinterpret_cast<const float2*>(tab)[c]; r.sig_col = v.x; r.neg_saf = v.y; }
+  else { const double2 v = reinterpret_cast<const double2*>(tab)[c]; r.sig_col = v.x; r.neg_saf = v.y; }
 #endif
+  return r;
 }
 
 // a / b for a divisor whose refined reciprocal r is cached (imc_fastdiv.cuh): Float16 / Float32 only — Float16 divides in
@@ -573,8 +568,6 @@ struct TallyArgs {
   int copies;        // shared-memory accumulator sets per block (a power of two): warp w deposits into set w % copies, so that
                      // the compare-and-swap loops of different warps do not collide
   int nacc;          // Nc * Ns
-  int dep_f32;       // ATOMIC deposits in global memory accumulate in Float32 (Float16 / Float32 decks): g_acc viewed as float[nacc]
-  float* g_dep32;    // Float32 deposit accumulators (dep_f32)
   double* g_acc;     // reduce buffer viewed as Float64 (ATOMIC)
   long long* g_fx;   // reduce buffer viewed as int64 (FIXED)
   double fx_mul;     // 2^S for densities
@@ -641,11 +634,6 @@ struct Tally {
       else atomicAdd(reinterpret_cast<unsigned long long*>(a.g_fx) + idx, (unsigned long long)q);
     } else {
       if (K::smem(a)) atomicAdd(&s_acc[idx], (A)v.v);
-      // global ATOMIC accumulators: Float32 for Float16 / Float32 decks — the reference itself accumulates
-      // `energydep[cell] += dep` in the deck precision (imc_transport.jl:120) — as one RED.F32 per deposit (half the
-      // L2 footprint of the tally and no F2F conversion; the region's first nacc 4-byte words, TallyArgs::dep_f32);
-      // Float64 decks keep Float64
-      else if (IMC_DEP_F32 && P::id != 2 && (TK == TK_ATOMIC_G || (TK == TK_RUNTIME && a.dep_f32))) atomicAdd(a.g_dep32 + (size_t)idx * IMC_DEP_STRIDE, (float)v.v);
       else atomicAdd(a.g_acc + idx, v.d());
     }
   }
@@ -1695,8 +1683,7 @@ __global__ void k_exact_lost(const double* __restrict__ lost_val, const unsigned
   *lost_io = lost;
 }
 
-// reduce buffer -> energydep (T).  kind: 0 Float64 accumulators, 1 fixed-point int64, 2 Float32 accumulators (the first n
-// 4-byte words of the region)
+// reduce buffer -> energydep (T).  kind: 0 Float64 accumulators, 1 fixed-point int64
 // (nx, sx, sy): accumulator of cell (xi, yi) of plane k sits at k*nc + xi*sx + yi*sy (MeshDev::tsx / tsy); nx = 0: linear
 template <class P>
 __global__ void k_acc_to_field(const double* g_acc, int kind, double fx_mul, long long n, typename P::store_t* out,
@@ -1705,8 +1692,7 @@ __global__ void k_acc_to_field(const double* g_acc, int kind, double fx_mul, lon
   if (i >= n) return;
   long long j = i;
   if (nx > 0) { const long long k = i / nc, c = i - k * nc; j = k * nc + (c % nx) * (long long)sx + (c / nx) * (long long)sy; }
-  double v = kind == 1 ? (double)reinterpret_cast<const long long*>(g_acc)[j] / fx_mul
-           : kind == 2 ? (double)reinterpret_cast<const float*>(g_acc)[j * IMC_DEP_STRIDE] : g_acc[j];
+  double v = kind == 1 ? (double)reinterpret_cast<const long long*>(g_acc)[j] / fx_mul : g_acc[j];
   Num<P>::from_d(v).store(out, i);
 }
 
@@ -1778,6 +1764,9 @@ static __global__ void k_max_f64(const double* __restrict__ v, long long n, doub
     } while (assumed != old);
   }
 }
+
+// fixed-point slot: value * ratio (a power of two), when the scale of the slot changes between two calls
+static __global__ void k_rescale_fixed(long long* slot, double ratio) { *slot = __double2ll_rn((double)*slot * ratio); }
 
 // max particle energy (for the fixed-point scale)
 template <class P>

@@ -68,7 +68,8 @@ struct Philox {
 enum : uint32_t { STREAM_SOURCE = 0u, STREAM_TRACK = 1u, STREAM_TRACK_EXTRA = 2u, STREAM_PLANCK = 3u };
 
 // One particle's draw stream for one time step.  Words are consumed in order; a new Philox
-// block is generated every 4 words.  counter = (id_lo, id_hi, step, stream<<28 | block).
+// block is generated every 4 words.  counter = (id_lo, id_hi, stream<<28 | step, block): the block index has a whole
+// word to itself (2^32 blocks per history and stream), the time step 28 bits (the engines refuse step >= 2^28).
 struct PhiloxStream {
   uint32_t key[2];
   uint32_t ctr[4];
@@ -79,8 +80,8 @@ struct PhiloxStream {
     key[1] = (uint32_t)(seed >> 32);
     ctr[0] = (uint32_t)id;
     ctr[1] = (uint32_t)(id >> 32);
-    ctr[2] = step;
-    ctr[3] = stream << 28;
+    ctr[2] = step | (stream << 28);
+    ctr[3] = 0u;
     buf[0] = buf[1] = buf[2] = buf[3] = 0u;
     used = 4;
   }
@@ -170,7 +171,7 @@ struct SegDraw {
     extra_n &= 0x3fffffffu;
     if (P::id == 2 || (n & 1u) == 0u || stale) {
       uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-      uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? n : (n >> 1))};
+      uint32_t c[4] = {id_lo, id_hi, step | (STREAM_TRACK << 28), P::id == 2 ? n : (n >> 1)};
       Philox::block(c, key, buf);
     }
   }
@@ -179,7 +180,7 @@ struct SegDraw {
     const bool stale = (extra_n & 0x40000000u) != 0u;
     extra_n &= 0x3fffffffu;
     if (P::id == 2 || (n & 1u) == 0u || stale) {
-      uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? n : (n >> 1))};
+      uint32_t c[4] = {id_lo, id_hi, step | (STREAM_TRACK << 28), P::id == 2 ? n : (n >> 1)};
       Philox::block_rk(c, rk, buf);
     }
   }
@@ -191,7 +192,7 @@ struct SegDraw {
     uint32_t j = extra_n & 0x3fffffffu;
     extra_n += 1u;
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK_EXTRA << 28) | (j >> 2)}, o[4];
+    uint32_t c[4] = {id_lo, id_hi, step | (STREAM_TRACK_EXTRA << 28), j >> 2}, o[4];
     Philox::block(c, key, o);
     return (j & 3u) == 0u ? o[0] : (j & 3u) == 1u ? o[1] : (j & 3u) == 2u ? o[2] : o[3];
   }
@@ -221,7 +222,7 @@ struct SegDrawLean {
   template <int PAR = -1>
   IMC_HD void next_segment_rk(const uint32_t* rk, uint32_t step, uint32_t seg) {   // seg: 0-based segment of the history
     if (P::id == 2 || (PAR < 0 ? (seg & 1u) == 0u : PAR == 0)) {
-      uint32_t c[4] = {id_lo, id_hi, step, (STREAM_TRACK << 28) | (P::id == 2 ? seg : (seg >> 1))};
+      uint32_t c[4] = {id_lo, id_hi, step | (STREAM_TRACK << 28), P::id == 2 ? seg : (seg >> 1)};
       Philox::block_rk(c, rk, buf);
     }
   }

@@ -24,6 +24,10 @@ from . import driver as _driver
 from . import lib as _lib
 
 
+# Float16 / Float32 decks, float (ATOMIC / EXACT) tallies: exchange the per-cell sums as Float32 (see _all_reduce_field)
+NARROW_FIELD_REDUCE = True
+
+
 class _DevArray:
     """__cuda_array_interface__ view of a raw device pointer."""
 
@@ -32,25 +36,34 @@ class _DevArray:
 
 
 def reduce_buffer_parts(engine: _lib.Engine):
-    """The engine's reduce buffer as two tensors that share its memory: the deposits [energydep Nc*Ns] and the tail
-    [radenergydens Nc | lostenergy | counters].  Element types follow imc_reduce_buffer's `kind`: 0 = Float64 throughout,
-    1 = int64 throughout (FIXED tallies), 2 = Float32 deposits (the region's first Nc*Ns 4-byte words: Float16 / Float32
-    decks with ATOMIC tallies in global memory accumulate in the deck's own width or wider, like the reference's
-    `energydep[cell] += dep`) followed by a Float64 tail at byte offset 8*Nc*Ns."""
+    """The engine's reduce buffer as (deposits [energydep Nc*Ns], fields [radenergydens Nc], scalars [lostenergy | counters],
+    kind): three tensors that share its memory; kind 0 = Float64, 1 = int64 (FIXED tallies) — imc_reduce_buffer."""
     ptr, n, kind = engine.reduce_buffer()
-    n_dep = engine.nc * engine.ns
+    n_dep, nc = engine.nc * engine.ns, engine.nc
     if engine.lib.backend.startswith("cuda"):
-        dev = f"cuda:{engine.cfg.device}"
-        t8 = "<i8" if kind == 1 else "<f8"
-        dep = torch.as_tensor(_DevArray(ptr, n_dep, "<f4" if kind == 2 else t8), device=dev)
-        tail = torch.as_tensor(_DevArray(ptr + 8 * n_dep, n - n_dep, t8), device=dev)
-        return dep, tail
-    ctype = C.c_int64 if kind == 1 else C.c_double
-    arr = torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)))
-    if kind == 2:
-        dep = torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(n_dep,)))
-        return dep, arr[n_dep:]
-    return arr[:n_dep], arr[n_dep:]
+        buf = torch.as_tensor(_DevArray(ptr, n, "<i8" if kind == 1 else "<f8"), device=f"cuda:{engine.cfg.device}")
+    else:
+        ctype = C.c_int64 if kind == 1 else C.c_double
+        buf = torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)))
+    return buf[:n_dep], buf[n_dep:n_dep + nc], buf[n_dep + nc:], kind
+
+
+def _all_reduce_field(part: torch.Tensor, narrow: bool, group=None, async_op: bool = False):
+    """Sum one per-cell part of the reduce buffer over the ranks.  narrow: Float16 / Float32 decks with float tallies — the
+    sums end up in an Array{T} of that precision anyway (and the reference accumulates them in T, imc_transport.jl:120),
+    so the ranks exchange Float32 images of their Float64 partial sums: half the bytes on the wire.  Returns a callable
+    that completes the reduction (waits, converts back)."""
+    if not narrow:
+        work = dist.all_reduce(part, group=group, async_op=async_op)
+        return (lambda: work.wait()) if async_op else (lambda: None)
+    img = part.to(torch.float32)
+    work = dist.all_reduce(img, group=group, async_op=async_op)
+
+    def finish():
+        if async_op:
+            work.wait()
+        part.copy_(img)
+    return finish
 
 
 def advance_sharded(sim: _driver.Simulation, group=None) -> dict:
@@ -69,20 +82,23 @@ def advance_sharded(sim: _driver.Simulation, group=None) -> dict:
     # [radenergydens | scalars] tail of the buffer); the tail is reduced afterwards.  Two collectives per step, same bytes.
     # (The oracle fills its host-side buffer only in tally_local, so there the whole buffer is reduced afterwards.)
     if on_gpu:
-        dep, tail = reduce_buffer_parts(eng)
-        work = dist.all_reduce(dep, group=group, async_op=True)
+        dep, rad, scalars, kind = reduce_buffer_parts(eng)
+        narrow = kind == 0 and eng.cfg.precision != _lib.F64 and NARROW_FIELD_REDUCE
+        done_dep = _all_reduce_field(dep, narrow, group, async_op=True)
         _driver.Clean.clean(parts)
         eng.tally_local()
         # tally_local only enqueues the census tally on the engine's own stream, which the collective's stream does not
         # know about: imc_reduce_buffer waits for that stream, so the tail is complete before it is reduced
         eng.reduce_buffer()
-        dist.all_reduce(tail, group=group)
-        work.wait()
+        done_rad = _all_reduce_field(rad, narrow, group)
+        dist.all_reduce(scalars, group=group)     # lostenergy and the event counters stay 8-byte
+        done_rad(); done_dep()
         torch.cuda.current_stream().synchronize()
     else:
         _driver.Clean.clean(parts)
         eng.tally_local()
-        for part in reduce_buffer_parts(eng):
+        dep, rad, scalars, _ = reduce_buffer_parts(eng)
+        for part in (dep, rad, scalars):
             dist.all_reduce(part, group=group)
     rec["tally"] = eng.tally_finish(float(sv.t), float(sv.dt))
     rec["energy"] = eng.energycheck()

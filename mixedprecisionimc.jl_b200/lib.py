@@ -124,6 +124,7 @@ ABI = [
     ("imc_set_source_tape", C.c_int, [C.c_void_p, _DP, C.c_int32, C.c_int64]),
     ("imc_get_outcomes", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64]),
     ("imc_sample_planck", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_double)]),
+    ("imc_checkpoint", C.c_int, [C.c_void_p, C.c_int32]),
 ]
 
 
@@ -315,9 +316,13 @@ class Engine:
                                           C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
         return {"source": _as_dict(a), "transport": _as_dict(b), "tally": _as_dict(c_), "energy": _as_dict(d)}
 
+    def checkpoint(self, op: str = "save"):
+        """Restart point inside the library (include/imc.h imc_checkpoint): 'save' | 'restore' | 'drop'."""
+        self._check(self.lib.dll.imc_checkpoint(self._h, {"save": 0, "restore": 1, "drop": 2}[op]))
+
     def reduce_buffer(self):
         """(address, n_elements, kind) of the buffer to all-reduce between tally_local and tally_finish; kind: 0 = Float64,
-        1 = int64 (FIXED tallies), 2 = Float32 deposits + Float64 tail (include/imc.h)."""
+        1 = int64 (FIXED tallies) (include/imc.h)."""
         p = C.c_void_p(); n = C.c_int64(); kind = C.c_int32()
         self._check(self.lib.dll.imc_reduce_buffer(self._h, C.byref(p), C.byref(n), C.byref(kind)))
         return p.value, n.value, int(kind.value)

@@ -163,6 +163,7 @@ struct EngineBase {
   virtual int set_source_tape(const double*, int, int64_t) = 0;
   virtual int get_outcomes(int32_t*, int32_t*, int64_t) = 0;
   virtual int sample_planck(int64_t, int64_t, double*) = 0;
+  virtual int checkpoint(int) = 0;
 };
 
 template <class P, class M>
@@ -354,6 +355,7 @@ struct Oracle : EngineBase {
 
   int source(double dt_, int64_t n_input, double cellmin_, int64_t step, int64_t n_census_global, imc_source_stats* out) override {
     if (!have_mesh) { err = "source before set_mesh"; return IMC_ERR_STATE; }
+    if (step < 0 || step >= (1ll << 24)) { err = "time-step index outside [0, 2^24)"; return IMC_ERR_ARG; }
     N dt = N::from_d(dt_), cellmin = N::from_d(cellmin_);
     const N* sc = scales.data();
     std::vector<N> e_body(nc), e_rad(nc), es_body(nc, N::from_d(1.0)), es_rad(nc, N::from_d(1.0)), es_em(nc, N::from_d(1.0));
@@ -636,6 +638,7 @@ struct Oracle : EngineBase {
 
   int transport(double dt_, int64_t step, imc_transport_stats* out) override {
     if (!have_mesh) { err = "transport before set_mesh"; return IMC_ERR_STATE; }
+    if (step < 0 || step >= (1ll << 24)) { err = "time-step index outside [0, 2^24)"; return IMC_ERR_ARG; }
     if (cfg.rng_mode == IMC_RNG_TAPE && (int64_t)particles.size() > tt_slots) { err = "transport tape has fewer slots than particles"; return IMC_ERR_TAPE; }
     imc_transport_stats st{};
     out_event.assign(particles.size(), 0); out_nseg.assign(particles.size(), 0);
@@ -1110,6 +1113,22 @@ struct Oracle : EngineBase {
   }
   int set_source_tape(const double* u, int nu, int64_t slots) override {
     st_uni.assign(u, u + (size_t)nu * slots); st_nuni = nu; st_slots = slots;
+    return IMC_OK;
+  }
+  // ---- restart point (include/imc.h imc_checkpoint): what `deepcopy(mesh), deepcopy(particles), deepcopy(simvars)` would
+  // give a Julia host — a copy of this whole object
+  Oracle* ckpt = nullptr;
+  ~Oracle() override { delete ckpt; }
+  int checkpoint(int op) override {
+    Oracle* held = ckpt;
+    ckpt = nullptr;                                  // the copy must not own (or copy) a restart point itself
+    if (op == IMC_CKPT_SAVE) { delete held; held = new Oracle(*this); }
+    else if (op == IMC_CKPT_RESTORE) {
+      if (!held) { err = "checkpoint: nothing saved"; return IMC_ERR_STATE; }
+      *this = *held;
+    } else if (op == IMC_CKPT_DROP) { delete held; held = nullptr; }
+    else { ckpt = held; err = "checkpoint: unknown op"; return IMC_ERR_ARG; }
+    ckpt = held;
     return IMC_OK;
   }
   // ---- Sourcing.sample_planck (imc_sourcing.jl:372-399): Fleck-Cummings series method.  Never called by the reference's

@@ -91,6 +91,7 @@ int imc_set_transport_tape(imc_handle h, const double* u, int32_t nu, const doub
 int imc_set_source_tape(imc_handle h, const double* u, int32_t nu, int64_t slots) { GUARD(h->e->set_source_tape(u, nu, slots)); }
 int imc_get_outcomes(imc_handle h, int32_t* ev, int32_t* nseg, int64_t cap) { GUARD(h->e->get_outcomes(ev, nseg, cap)); }
 int imc_sample_planck(imc_handle h, int64_t n, int64_t step, double* out) { GUARD(h->e->sample_planck(n, step, out)); }
+int imc_checkpoint(imc_handle h, int32_t op) { GUARD(h->e->checkpoint(op)); }
 
 // ---- test hooks (oracle only): evaluate the shared math / number helpers on arrays -------------
 // fn: 0 exp 1 expm1 2 log 3 sin 4 cos 5 atan2(x,y) 6 pow(x,y) 7 round-to-precision 8 sqrt 9 mul 10 add 11 div
