@@ -395,6 +395,8 @@ def main():
     # Restart point: the resident loop and the host-buffer (e2e) loop below both run time steps W .. W+K-1 of the same
     # simulation from this state (imc_checkpoint copies the engine's state on the device; the host's t / dt / step are
     # copied here), so their step times compare one to one.
+    if pin["temp"].dtype != eng.field_dtype("temp"):   # mesh.temp turned Float64 during the warm-up (Q12: first LINEARIZED tally)
+        pin["temp"] = torch.empty(nc, dtype=tdt[eng.field_dtype("temp")]).pin_memory().numpy()
     for k in pin:
         eng.field_native(k, out=pin[k])
     eng.checkpoint("save")

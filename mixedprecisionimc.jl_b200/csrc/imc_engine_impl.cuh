@@ -530,8 +530,14 @@ struct EngineT : EngineBase {
     k_exact_reduce<P><<<grid_for(nacc, 128), 128, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, pairwise, out); ++n_launch;
     if (R >= EXACT_WARP_MIN) {   // cells with many records: a warp per cell, same order of additions
       unsigned grid = (unsigned)std::min<long long>((nacc * 32 + 255) / 256, (long long)sm_count * 8);
-      static const int skip_stagnant = getenv("IMC_EXACT_SKIP") ? atoi(getenv("IMC_EXACT_SKIP")) : 0;   // experimental, see warp_seq_add_skip
+      // sequential sums skip their stagnant stretches (warp_seq_add_skip: same bits, 4x faster on the Float16 Su-Olson deck);
+      // IMC_EXACT_SKIP=0 selects the plain chain for A/B runs
+      static const int skip_stagnant = getenv("IMC_EXACT_SKIP") ? atoi(getenv("IMC_EXACT_SKIP")) : 1;
       k_exact_reduce_warp<P><<<grid, 256, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, pairwise, skip_stagnant, out); ++n_launch;
+    }
+    if (!pairwise && R >= EXACT_SEQBLOCK_MIN) {   // very long sequential segments: a block per cell, stagnant chunks skipped
+      unsigned grid = (unsigned)std::min<long long>(nacc, (long long)sm_count * 2);
+      k_exact_reduce_seqblock<P><<<grid, EXACT_BLOCK_THREADS, 0, stream>>>(rec_key[1].p, rec_val[1].p, rec_start.p, nacc, out); ++n_launch;
     }
     if (pairwise && R >= EXACT_BLOCK_MIN) {   // very long pairwise segments: a block per cell, leaves in parallel
       unsigned grid = (unsigned)std::min<long long>(nacc, (long long)sm_count * 2);
@@ -569,11 +575,14 @@ struct EngineT : EngineBase {
   // are compiled per tally kind (no mode tests in the segment loop); EXACT passes and replay tapes read TallyArgs.
   template <bool TAPE, int TK>
   void launch_history(TrackArgs<P>& a, int variant, unsigned grid, size_t smem) {
+    const bool rw = geom == 1 && cfg.randomwalk;
     if (variant == IMC_TRACK_REFILL) {
-      if (geom == 1) k_track_refill<P, 1, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      if (rw) k_track_refill<P, 3, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      else if (geom == 1) k_track_refill<P, 1, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
       else k_track_refill<P, 2, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
     } else {
-      if (geom == 1) k_track1d<P, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      if (rw) k_track1d_rw<P, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
+      else if (geom == 1) k_track1d<P, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
       else k_track2d<P, TAPE, TK><<<grid, TRACK_THREADS, smem, stream>>>(a);
     }
   }
@@ -582,8 +591,7 @@ struct EngineT : EngineBase {
     IMC_CK(cudaMemsetAsync(over_flag.p + 1, 0, sizeof(unsigned long long), stream));
     smem += COUNTER_SMEM_BYTES;
     const bool tape = a.rng.tape != 0;
-    if (geom == 1 && cfg.randomwalk) k_track1d_rw<P><<<grid, TRACK_THREADS, smem, stream>>>(a);
-    else if (tape) launch_history<true, TK_RUNTIME>(a, variant, grid, smem);
+    if (tape) launch_history<true, TK_RUNTIME>(a, variant, grid, smem);
     else if (a.tally.mode == IMC_TALLY_ATOMIC && !a.tally.use_smem) launch_history<false, TK_ATOMIC_G>(a, variant, grid, smem);
     else if (a.tally.mode == IMC_TALLY_ATOMIC) launch_history<false, TK_ATOMIC_S>(a, variant, grid, smem);
     else if (a.tally.mode == IMC_TALLY_FIXED && !a.tally.use_smem) launch_history<false, TK_FIXED_G>(a, variant, grid, smem);
@@ -638,7 +646,6 @@ struct EngineT : EngineBase {
     // steps, re-probing every 32 calls) and keeps the one with the higher segments/s.
     int variant = cfg.track_mode;
     const bool event_ok = !(geom == 1 && cfg.randomwalk) && mode != IMC_TALLY_EXACT && cfg.rng_mode != IMC_RNG_TAPE && n_part < (1ll << 32);
-    if (geom == 1 && cfg.randomwalk) variant = IMC_TRACK_HISTORY;
     if (variant == IMC_TRACK_EVENT && !event_ok) variant = IMC_TRACK_AUTO;
     if (variant == IMC_TRACK_AUTO) {
       // measured selection: the two history schedules are probed on the first two calls and re-probed every

@@ -40,7 +40,14 @@ constexpr int TRACK_THREADS = IMC_TRACK_THREADS;
 constexpr int QUEUE_CHUNK = 32;   // particles per claim of the dynamic schedule's queue
 // resident blocks per SM the history kernels are compiled for: 4 x 256 threads (64 registers) for Float16 / Float32; Float64
 // histories hold twice the registers — 3 blocks (80 registers) spill less and measured 5 % faster (crookedpipe_f64)
-template <class P> constexpr int track_min_blocks() { return P::id == 2 && IMC_TRACK_MIN_BLOCKS == 4 ? 3 : IMC_TRACK_MIN_BLOCKS; }
+#ifndef IMC_TRACK_MIN_BLOCKS_F64
+#define IMC_TRACK_MIN_BLOCKS_F64 3
+#endif
+#ifndef IMC_UNROLL2_F64
+#define IMC_UNROLL2_F64 0   // Float64 histories make one Philox block per segment (no parity to exploit) and the second copy of the
+                            // segment body costs registers at the 80-register cap: one segment per loop trip (crookedpipe_f64: 23.5 vs 29.3 ms)
+#endif
+template <class P> constexpr int track_min_blocks() { return P::id == 2 ? IMC_TRACK_MIN_BLOCKS_F64 : IMC_TRACK_MIN_BLOCKS; }
 
 // reduce-buffer scalar slots that follow [energydep Nc*Ns | radenergydens Nc]
 enum { RB_LOST = 0, RB_SEG, RB_HIST, RB_CENSUS, RB_ABSORBED, RB_ESCAPED, RB_RW, RB_ERRORS, RB_NSCALARS };
@@ -1062,88 +1069,6 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track2
   cn.commit<TK>(a.tally);
 }
 
-// ---- dynamic schedule: warp-level refill from a global particle queue --------------------------------
-// Every trip of the loop each active lane tracks TWO segments (an even and an odd one: the parity of the segment index
-// is static, so the Philox block of the pair is generated in the first half by every lane and the second half carries
-// no parity test).  Before a trip, when at least `refill_min` lanes of the warp are idle (or all are), the idle lanes
-// write back the histories they finished (thread-private counters, coalescing stores), lane 0 claims that many
-// consecutive particle indices with one atomicAdd and the idle lanes load them.  Per-particle results do not depend on
-// the lane that tracks them (Philox is keyed by particle id and segment, the tape by particle slot), so both schedules
-// give identical particle state.
-template <class P, int GEOM, bool TAPE, int TK>
-__global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_refill(TrackArgs<P> a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
-  Tally<P, TK> tal(a.tally, smem + COUNTER_SMEM_BYTES);
-  tal.zero();
-  using Dr = HistDraw<P, TAPE, GEOM == 2>;
-  constexpr int ST_EMPTY = -2, ST_ACTIVE = -1;   // >= 0: history finished with that outcome, not yet written back
-  const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  int st = ST_EMPTY;
-  bool drained = false;
-  long long cbase = 0; int crem = 0;   // the warp's chunk of the particle list: next index, particles left (warp-uniform)
-  if (a.timeline && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(a.timeline, t); }
-  Hist1<P> h1; Hist2<P> h2; Dr d;
-  while (true) {
-    unsigned idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
-    // refill_min <= 32, so a warp with no active lane always refills
-    if (__popc(idle) >= a.refill_min) {
-      if (st >= 0) {
-        if constexpr (GEOM == 1) store1d<P, Dr, TK>(a, h1, d, st, cn); else store2d<P, Dr, TK>(a, h2, d, st, cn);
-        st = ST_EMPTY;
-      }
-      if (!drained) {
-        // the warp works through a private chunk of QUEUE_CHUNK consecutive particles (coalesced loads) and claims the
-        // next one with a ticket from the global queue; chunk = ticket * queue_mult mod n_chunks visits the particle
-        // list in a scattered order (queue_mult coprime to n_chunks; 1 = list order)
-        if (crem == 0) {
-          unsigned long long t = 0;
-          if (lane == 0) t = atomicAdd(a.queue, 1ull);
-          t = __shfl_sync(IMC_FULL_MASK, t, 0);
-          if (t >= a.queue_chunks) {
-            if (a.timeline && lane == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); atomicMin(a.timeline + 1, tt); }
-            drained = true;
-          } else {
-            cbase = (long long)((t * a.queue_mult) % a.queue_chunks) * QUEUE_CHUNK;
-            crem = (int)min((long long)QUEUE_CHUNK, a.n - cbase);
-          }
-        }
-        if (!drained) {
-          const int take = min(__popc(idle), crem);
-          const int rank = __popc(idle & lt_mask);
-          if (st != ST_ACTIVE && rank < take) {
-            const long long pi = cbase + rank;
-            bool ok;
-            if constexpr (GEOM == 1) ok = load1d<P, Dr, TK>(a, pi, h1, d, cn); else ok = load2d<P, Dr, TK>(a, pi, h2, d, cn);
-            if (ok) st = ST_ACTIVE;
-          }
-          cbase += take; crem -= take;
-        }
-        idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
-      }
-      if (idle == IMC_FULL_MASK) {
-        if (drained) break;
-        continue;
-      }
-    }
-    if (st == ST_ACTIVE) {
-      int ev;
-      if constexpr (GEOM == 1) ev = seg1d(a, h1, d, tal, cn); else ev = seg2d<0>(a, h2, d, tal, cn);
-      if (ev >= 0) st = ev;
-    }
-    if (st == ST_ACTIVE) {
-      int ev;
-      if constexpr (GEOM == 1) ev = seg1d(a, h1, d, tal, cn); else ev = seg2d<1>(a, h2, d, tal, cn);
-      if (ev >= 0) st = ev;
-    }
-  }
-  if (a.timeline && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMax(a.timeline + 2, t); }
-  tal.flush();
-  cn.commit<TK>(a.tally);
-}
-
-
 // ---- event-based schedule: every launch advances each in-flight particle by ONE segment -----------------
 // State is re-read and re-written every segment (B_hist per segment instead of per history) and the direction
 // vector / Philox block are recomputed, in exchange for warps whose lanes all do the same amount of work.
@@ -1234,7 +1159,10 @@ __device__ __forceinline__ double rw_P_r(double a) {
   for (int n = 1; n <= 100; ++n) {
     double pin = 3.141592653589793 * (double)n;
     double e = dm::exp_d(-a * (pin * pin));
-    if (e == 0.0) break;
+    // The terms decrease monotonically (a > 0), so once 2e is below a quarter of the last place of the running sum no
+    // later term can change it (round to nearest, |term| < ulp / 2 strictly): the remaining iterations of the reference's
+    // loop are no-ops and are skipped.  (e == 0: underflow, covers Pr == 0 as well.)  a < 0 or NaN: the test never fires.
+    if (e == 0.0 || e * 2.0 < (Pr < 0 ? -Pr : Pr) * 0x1p-55) break;
     Pr += (((n - 1) & 1) ? -1.0 : 1.0) * e * 2.0;
   }
   return Pr;
@@ -1254,115 +1182,263 @@ __device__ __forceinline__ int rw_bisection(const typename P::store_t* arr, int 
   return jl;
 }
 
+// Draw source of the MC_RW loops: words are consumed in sequence (a segment draws one Float64 exponential, a random-walk
+// trial one or two uniforms, a collision one or more), so there is a cursor — the Philox variant keeps only what differs
+// per thread (particle id, block index, the four buffered words); the key and the step sit in RngArgs.  Same words as
+// PhiloxDraw<P> on (seed, id, step, STREAM_TRACK), which the oracle uses.
+template <class P, bool TAPE> struct RwDraw;
 template <class P>
-__global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
+struct RwDraw<P, false> {
+  uint32_t id_lo, id_hi, blk, used, buf[4];
+  __device__ __forceinline__ void init(const RngArgs&, unsigned long long id, long long) { id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32); blk = 0u; used = 4u; buf[0] = buf[1] = buf[2] = buf[3] = 0u; }
+  __device__ __forceinline__ uint32_t word(const RngArgs& r) {
+    if (used == 4u) { const uint32_t c[4] = {id_lo, id_hi, r.step | (STREAM_TRACK << 28), blk}; Philox::block_rk(c, r.rk, buf); ++blk; used = 0u; }
+    const uint32_t w = used == 0u ? buf[0] : used == 1u ? buf[1] : used == 2u ? buf[2] : buf[3];
+    ++used;
+    return w;
+  }
+  __device__ __forceinline__ Num<P> uniform(const RngArgs& r) {
+    if constexpr (P::id == 2) { const uint64_t lo = word(r), hi = word(r); return uniform_from_word<P>((hi << 32) | lo); }
+    else return uniform_from_word<P>((uint64_t)word(r));
+  }
+  __device__ __forceinline__ double randexp64(const RngArgs& r) { const uint64_t lo = word(r), hi = word(r); return randexp64_from_word((hi << 32) | lo); }
+  __device__ __forceinline__ bool over() const { return false; }
+};
+template <class P>
+struct RwDraw<P, true> {
+  TapeDraw<P> tp;
+  __device__ __forceinline__ void init(const RngArgs& r, unsigned long long, long long slot) { tp.init(r.uni, r.n_uni, r.ex, r.n_exp, (size_t)r.stride, (size_t)slot); }
+  __device__ __forceinline__ Num<P> uniform(const RngArgs&) { return tp.uniform(); }
+  __device__ __forceinline__ double randexp64(const RngArgs&) { return tp.randexp64(); }
+  __device__ __forceinline__ bool over() const { return tp.exhausted(); }
+};
+
+// One MC_RW history in registers, and one loop iteration as a device function shared by the static and the warp-refill
+// schedule.  Returns -1 to continue or the outcome: 0 census, 1 absorbed, 2 escaped, 3 killed by a random-walk step (Q1).
+template <class P>
+struct HistRW {
+  DynD<P> t, x, E;      // values of T until the history's first move, Float64 afterwards (Q3)
+  Num<P> mu, E0, minE;
+  int cell, k, nseg;
+  unsigned pi;
+  long long rec_base;
+};
+template <class P, class D, int TK>
+__device__ __forceinline__ bool load_rw(const TrackArgs<P>& a, long long pi, HistRW<P>& h, D& d, Counters&) {
+  using N = Num<P>;
+  h.E0 = N::load(a.p.E0, pi);
+  if (h.E0.v == (typename P::comp_t)-1) return false;
+  h.pi = (unsigned)pi;
+  h.t = DynD<P>(N::load(a.p.t, pi)); h.x = DynD<P>(N::load(a.p.x, pi)); h.E = DynD<P>(N::load(a.p.E, pi));
+  h.mu = N::load(a.p.mu, pi);
+  h.cell = a.p.cx[pi]; h.k = a.p.ks[pi];
+  h.minE = N::from_d(0.01 * h.E0.d());                                              // :262
+  h.nseg = 0;
+  h.rec_base = (TKind<TK>::exact(a.tally) && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
+  d.init(a.rng, a.p.id[pi], pi);
+  return true;
+}
+template <class P, class D, int TK>
+__device__ __forceinline__ void store_rw(const TrackArgs<P>& a, HistRW<P>& h, D& d, int ev, Counters& cn) {
+  using N = Num<P>;
+  const long long pi = h.pi;
+  if (TKind<TK>::exact(a.tally) && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
+  cn.finish(ev, h.nseg);
+  if (ev == 0) {
+    N().store(a.p.t, pi); N::from_d(h.x.v).store(a.p.x, pi); h.mu.store(a.p.mu, pi); N::from_d(h.E.v).store(a.p.E, pi); a.p.cx[pi] = h.cell;
+  } else h.E0.store(a.p.E0, pi);
+  if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
+  if (d.over()) atomicAdd(a.over_flag, 1ull);
+}
+template <class P, class Dr, int TK>
+__device__ __forceinline__ int seg_rw(const TrackArgs<P>& a, HistRW<P>& h, Dr& d, Tally<P, TK>& tal, Counters& cn) {
   using N = Num<P>;
   using D = DynD<P>;
-  extern __shared__ __align__(16) unsigned char smem[];
-  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
-  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
-  tal.zero();
   const N one = N::from_d(1.0), two = N::from_i(2), three = N::from_i(3), zero;
   const N dt(a.dt), c_light(a.m.c);
   const int nc = (int)a.m.nc;
-  const bool reflect_l = a.m.bc[IMC_BC_LEFT] == IMC_REFLECT, reflect_r = a.m.bc[IMC_BC_RIGHT] == IMC_REFLECT;
+  const bool exact = TKind<TK>::exact(a.tally);
+  const long long acc = (long long)nc * h.k + h.cell;
+  ++h.nseg;                                                                         // :265
+  const CellProp1<P> cp = a.m.cp1[h.cell];
+  const N dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
+  const D dist_b = h.mu > zero ? dyn_div(dyn_sub(D(dx), h.x), D(h.mu)) : dyn_abs(dyn_div(h.x, D(h.mu)));   // :269-275 (no distancescale)
+  const double rex = d.randexp64(a.rng);
+  const D dist_col = D::w((rex < 0 ? -rex : rex) / sig_col.d());                    // :279 (Float64)
+  const D dist_cen = dyn_mul(D(c_light), dyn_sub(D(dt), h.t));                      // :281
+  const D dist = dyn_min(dyn_min(dist_b, dist_col), dist_cen);                      // :284
+  const D R0 = dyn_min(dyn_abs(dyn_sub(D(dx), h.x)), dyn_abs(h.x));                 // :286
+  const N inv_sigma = N::from_i(1) / N::load(a.m.sigma_static, h.cell);             // 1/mesh.sigma[cellindex] (Q4)
+  if (R0.v > inv_sigma.d() && dist_col.v < R0.v) {                                  // :289
+    const N sa = N::load(a.m.sa, h.cell), f = N::load(a.m.fleck, h.cell);
+    const N u = d.uniform(a.rng);                                                   // :290
+    const N Dc = c_light / ((three * sa) * (one - f));                              // :292
+    const D aa = dyn_div(dyn_mul(D(Dc), D(dt)), dyn_mul(R0, R0));                   // :294
+    const double Pr = rw_P_r(aa.v);                                                 // :296
+    const double Pt = 1.0 - Pr;                                                     // :297
+    const N lg = MathDet::log<P>(one - f);
+    N expo;
+    if (u.d() < Pt) {                                                               // :298
+      const int ai = rw_bisection<P>(a.ptVals, a.n_rw_table, u.d());                // :301
+      const D tp = dyn_div(dyn_mul(D(N::load(a.aVals, ai - 1)), dyn_mul(R0, R0)), D(Dc));
+      const N t_p = N::from_d(tp.v);                                                // :303
+      expo = (((t_p * c_light) * (one - f)) * sa) / lg;                             // :306
+    } else {
+      (void)d.uniform(a.rng);                                                       // u_prime :338
+      expo = (((c_light * (one - f)) * sa) * dt) / lg;                              // :346
+    }
+    // newenergy <= startenergy always holds (Q1): the random-walk step deposits and kills
+    N ex, em1; MathDet::exp_expm1<P>(expo, &ex, &em1);
+    const D newE = dyn_mul(h.E, D(ex));
+    const D depv = dyn_mul(dyn_mul(D(-one), dyn_div(h.E, D(dx))), D(em1));          // :317-320 / :352-356
+    if (exact) tal.add(acc, N::from_d(depv.v), h.rec_base + h.nseg - 1, depv.wide, depv.v);   // Float64 deposits: converted on push! / added in Float64 on setindex!
+    else tal.add_runs((int)acc, N::from_d(depv.v));
+    if (newE.v != newE.v) cn.error();
+    h.E0 = N::from_d(-1.0);
+    return 3;
+  }
+  D newE = dyn_mul(h.E, D::w(dm::exp_d(neg_saf.d() * dist.v)));                     // :376 (Float64)
+  if (newE.v <= h.minE.d()) newE = D(zero);                                         // :377-379
+  const D depv = dyn_sub(h.E, newE);                                                // :383 / :385 (not / dx, Q2)
+  if (exact) tal.add(acc, N::from_d(depv.v), h.rec_base + h.nseg - 1, depv.wide, depv.v);
+  else tal.add_runs((int)acc, N::from_d(depv.v));
+  if (newE.v == 0.0) { h.E0 = N::from_d(-1.0); return 1; }                          // :390-394
+  h.x = dyn_add(h.x, dyn_mul(D(h.mu), dist));                                       // :397
+  h.t = dyn_add(h.t, dyn_div(dist, D(c_light)));                                    // :398
+  h.E = newE;                                                                       // :399
+  bool dead = false;
+  if (dist.v == dist_b.v) {                                                         // :403-443
+    if (h.mu > zero) {
+      if (h.cell == nc - 1) { if (a.m.bc[IMC_BC_RIGHT] == IMC_REFLECT) h.mu = -h.mu; else dead = true; }
+      if (!dead) { h.cell += 1; h.x = D(zero); }
+    }
+    if (!dead && h.mu < zero) {
+      if (h.cell == 0) { if (a.m.bc[IMC_BC_LEFT] == IMC_REFLECT) h.mu = -h.mu; else dead = true; }
+      else { h.cell -= 1; h.x = D(N::load(a.m.dx, h.cell)); }
+    }
+  }
+  if (dead) {                                                                       // :414 / :433
+    const N escale(a.m.scales[h.k]);
+    if (exact) { if (a.tally.pass == 2) a.tally.lost_val[h.pi] = h.E.v; }
+    else if (h.E.wide) cn.lose_value<TK>(a.tally, h.E.v / escale.d());
+    else cn.lose<P, TK>(a.tally, h.E.narrow() / escale);
+    h.E0 = N::from_d(-1.0);
+    return 2;
+  }
+  if (dist.v == dist_col.v) {                                                       // :446-453
+    h.mu = one - two * d.uniform(a.rng);
+    while (h.mu == zero) h.mu = one - two * d.uniform(a.rng);
+  }
+  if (dist.v == dist_cen.v) return 0;                                               // :455-463
+  return -1;
+}
+
+// static schedule (thread t takes particles t, t + stride, ...)
+template <class P, bool TAPE, int TK>
+__global__ void __launch_bounds__(TRACK_THREADS) k_track1d_rw(TrackArgs<P> a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
+  Tally<P, TK> tal(a.tally, smem + COUNTER_SMEM_BYTES);
+  tal.zero();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < a.n; pi += stride) {
-    N E0 = N::load(a.p.E0, pi);
-    if (E0.v == (typename P::comp_t)-1) continue;
-    D t(N::load(a.p.t, pi)), x(N::load(a.p.x, pi)), E(N::load(a.p.E, pi));
-    N mu = N::load(a.p.mu, pi);
-    int cell = a.p.cx[pi];
-    const int k = a.p.ks[pi];
-    const N escale(a.m.scales[k]);
-    const N minE = N::from_d(0.01 * E0.d());                                       // :262
-    const long long kbase = (long long)nc * k;
-    Draw<P> d; d.init(a.rng, a.p.id[pi], STREAM_TRACK, pi);
-    int nseg = 0, ev = 0;
-    const long long rec_base = (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
-    while (true) {
-      ++nseg;                                                                       // :265
-      const CellProp1<P> cp = a.m.cp1[cell];
-      const N dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
-      D dist_b = mu > zero ? dyn_div(dyn_sub(D(dx), x), D(mu)) : dyn_abs(dyn_div(x, D(mu)));   // :269-275 (no distancescale)
-      double rex = d.randexp64();
-      D dist_col = D::w((rex < 0 ? -rex : rex) / sig_col.d());                      // :279 (Float64)
-      D dist_cen = dyn_mul(D(c_light), dyn_sub(D(dt), t));                          // :281
-      D dist = dyn_min(dyn_min(dist_b, dist_col), dist_cen);                        // :284
-      D R0 = dyn_min(dyn_abs(dyn_sub(D(dx), x)), dyn_abs(x));                       // :286
-      N inv_sigma = N::from_i(1) / N::load(a.m.sigma_static, cell);                 // 1/mesh.sigma[cellindex] (Q4)
-      if (R0.v > inv_sigma.d() && dist_col.v < R0.v) {                              // :289
-        const N sa = N::load(a.m.sa, cell), f = N::load(a.m.fleck, cell);
-        N u = d.uniform();                                                          // :290
-        N Dc = c_light / ((three * sa) * (one - f));                                // :292
-        D aa = dyn_div(dyn_mul(D(Dc), D(dt)), dyn_mul(R0, R0));                     // :294
-        double Pr = rw_P_r(aa.v);                                                   // :296
-        double Pt = 1.0 - Pr;                                                       // :297
-        N lg = MathDet::log<P>(one - f);
-        N expo;
-        if (u.d() < Pt) {                                                           // :298
-          int ai = rw_bisection<P>(a.ptVals, a.n_rw_table, u.d());                  // :301
-          D tp = dyn_div(dyn_mul(D(N::load(a.aVals, ai - 1)), dyn_mul(R0, R0)), D(Dc));
-          N t_p = N::from_d(tp.v);                                                  // :303
-          expo = (((t_p * c_light) * (one - f)) * sa) / lg;                         // :306
-        } else {
-          (void)d.uniform();                                                        // u_prime :338
-          expo = (((c_light * (one - f)) * sa) * dt) / lg;                          // :346
-        }
-        // newenergy <= startenergy always holds (Q1): the random-walk step deposits and kills
-        N ex, em1; MathDet::exp_expm1<P>(expo, &ex, &em1);
-        D newE = dyn_mul(E, D(ex));
-        D depv = dyn_mul(dyn_mul(D(-one), dyn_div(E, D(dx))), D(em1));              // :317-320 / :352-356
-        if (a.tally.mode == IMC_TALLY_EXACT) tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);  // Float64 deposits: converted on push! / added in Float64 on setindex!
-        else tal.add_runs((int)(kbase + cell), N::from_d(depv.v));
-        if (newE.v != newE.v) cn.error();
-        E0 = N::from_d(-1.0); ev = 3;
-        break;
-      }
-      D newE = dyn_mul(E, D::w(dm::exp_d(neg_saf.d() * dist.v)));                   // :376 (Float64)
-      if (newE.v <= minE.d()) newE = D(zero);                                       // :377-379
-      D depv = dyn_sub(E, newE);                                                    // :383 / :385 (not / dx, Q2)
-      if (a.tally.mode == IMC_TALLY_EXACT) tal.add(kbase + cell, N::from_d(depv.v), rec_base + nseg - 1, depv.wide, depv.v);
-      else tal.add_runs((int)(kbase + cell), N::from_d(depv.v));
-      if (newE.v == 0.0) { E0 = N::from_d(-1.0); ev = 1; break; }    // :390-394
-      x = dyn_add(x, dyn_mul(D(mu), dist));                                         // :397
-      t = dyn_add(t, dyn_div(dist, D(c_light)));                                    // :398
-      E = newE;                                                                     // :399
-      bool dead = false;
-      if (dist.v == dist_b.v) {                                                     // :403-443
-        if (mu > zero) {
-          if (cell == nc - 1) { if (reflect_r) mu = -mu; else dead = true; }
-          if (!dead) { cell += 1; x = D(zero); }
-        }
-        if (!dead && mu < zero) {
-          if (cell == 0) { if (reflect_l) mu = -mu; else dead = true; }
-          else { cell -= 1; x = D(N::load(a.m.dx, cell)); }
-        }
-      }
-      if (dead) {                                                                   // :414 / :433
-        if (a.tally.mode == IMC_TALLY_EXACT) { if (a.tally.pass == 2) a.tally.lost_val[pi] = E.v; }
-        else if (E.wide) cn.lose_value(a.tally, E.v / escale.d());
-        else cn.lose<P>(a.tally, E.narrow() / escale);
-        E0 = N::from_d(-1.0); ev = 2;
-        break;
-      }
-      if (dist.v == dist_col.v) {                                                   // :446-453
-        mu = one - two * d.uniform();
-        while (mu == zero) mu = one - two * d.uniform();
-      }
-      if (dist.v == dist_cen.v) { ev = 0; break; }                     // :455-463
-    }
-    if (a.tally.mode == IMC_TALLY_EXACT && a.tally.pass == 1) { a.tally.rec_cnt[pi] = nseg; continue; }
-    cn.finish(ev, nseg);
-    if (ev == 0) {
-      zero.store(a.p.t, pi); N::from_d(x.v).store(a.p.x, pi); mu.store(a.p.mu, pi); N::from_d(E.v).store(a.p.E, pi); a.p.cx[pi] = cell;
-    } else E0.store(a.p.E0, pi);
-    if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = nseg; }
-    if (d.over()) atomicAdd(a.over_flag, 1ull);
+    HistRW<P> h; RwDraw<P, TAPE> d;
+    if (!load_rw<P, RwDraw<P, TAPE>, TK>(a, pi, h, d, cn)) continue;
+    int ev;
+    while ((ev = seg_rw(a, h, d, tal, cn)) < 0) {}
+    store_rw<P, RwDraw<P, TAPE>, TK>(a, h, d, ev, cn);
   }
   tal.flush();
-  cn.commit(a.tally);
+  cn.commit<TK>(a.tally);
 }
+
+// ---- dynamic schedule: warp-level refill from a global particle queue --------------------------------
+// Every trip of the loop each active lane tracks TWO segments (an even and an odd one: the parity of the segment index
+// is static, so the Philox block of the pair is generated in the first half by every lane and the second half carries
+// no parity test).  Before a trip, when at least `refill_min` lanes of the warp are idle (or all are), the idle lanes
+// write back the histories they finished (thread-private counters, coalescing stores), lane 0 claims that many
+// consecutive particle indices with one atomicAdd and the idle lanes load them.  Per-particle results do not depend on
+// the lane that tracks them (Philox is keyed by particle id and segment, the tape by particle slot), so both schedules
+// give identical particle state.
+// GEOM: 1 = MC (1-D), 2 = MC2D, 3 = MC_RW (1-D with random-walk acceleration; its segments are Float64-heavy and carry no
+// parity, so one per trip)
+template <class P, int GEOM, bool TAPE> struct RefillDraw { using type = HistDraw<P, TAPE, GEOM == 2>; };
+template <class P, bool TAPE> struct RefillDraw<P, 3, TAPE> { using type = RwDraw<P, TAPE>; };
+template <class P, int GEOM, bool TAPE, int TK>
+__global__ void __launch_bounds__(TRACK_THREADS, (GEOM == 3 ? 3 : track_min_blocks<P>())) k_track_refill(TrackArgs<P> a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
+  Tally<P, TK> tal(a.tally, smem + COUNTER_SMEM_BYTES);
+  tal.zero();
+  using Dr = typename RefillDraw<P, GEOM, TAPE>::type;
+  constexpr int ST_EMPTY = -2, ST_ACTIVE = -1;   // >= 0: history finished with that outcome, not yet written back
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int st = ST_EMPTY;
+  bool drained = false;
+  long long cbase = 0; int crem = 0;   // the warp's chunk of the particle list: next index, particles left (warp-uniform)
+  if (a.timeline && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(a.timeline, t); }
+  Hist1<P> h1; Hist2<P> h2; HistRW<P> hr; Dr d;   // the two that GEOM does not use are never touched
+  while (true) {
+    unsigned idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
+    // refill_min <= 32, so a warp with no active lane always refills
+    if (__popc(idle) >= a.refill_min) {
+      if (st >= 0) {
+        if constexpr (GEOM == 1) store1d<P, Dr, TK>(a, h1, d, st, cn); else if constexpr (GEOM == 2) store2d<P, Dr, TK>(a, h2, d, st, cn); else store_rw<P, Dr, TK>(a, hr, d, st, cn);
+        st = ST_EMPTY;
+      }
+      if (!drained) {
+        // the warp works through a private chunk of QUEUE_CHUNK consecutive particles (coalesced loads) and claims the
+        // next one with a ticket from the global queue; chunk = ticket * queue_mult mod n_chunks visits the particle
+        // list in a scattered order (queue_mult coprime to n_chunks; 1 = list order)
+        if (crem == 0) {
+          unsigned long long t = 0;
+          if (lane == 0) t = atomicAdd(a.queue, 1ull);
+          t = __shfl_sync(IMC_FULL_MASK, t, 0);
+          if (t >= a.queue_chunks) {
+            if (a.timeline && lane == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); atomicMin(a.timeline + 1, tt); }
+            drained = true;
+          } else {
+            cbase = (long long)((t * a.queue_mult) % a.queue_chunks) * QUEUE_CHUNK;
+            crem = (int)min((long long)QUEUE_CHUNK, a.n - cbase);
+          }
+        }
+        if (!drained) {
+          const int take = min(__popc(idle), crem);
+          const int rank = __popc(idle & lt_mask);
+          if (st != ST_ACTIVE && rank < take) {
+            const long long pi = cbase + rank;
+            bool ok;
+            if constexpr (GEOM == 1) ok = load1d<P, Dr, TK>(a, pi, h1, d, cn); else if constexpr (GEOM == 2) ok = load2d<P, Dr, TK>(a, pi, h2, d, cn); else ok = load_rw<P, Dr, TK>(a, pi, hr, d, cn);
+            if (ok) st = ST_ACTIVE;
+          }
+          cbase += take; crem -= take;
+        }
+        idle = __ballot_sync(IMC_FULL_MASK, st != ST_ACTIVE);
+      }
+      if (idle == IMC_FULL_MASK) {
+        if (drained) break;
+        continue;
+      }
+    }
+    if (st == ST_ACTIVE) {
+      int ev;
+      if constexpr (GEOM == 1) ev = seg1d(a, h1, d, tal, cn); else if constexpr (GEOM == 2) ev = seg2d<0>(a, h2, d, tal, cn); else ev = seg_rw(a, hr, d, tal, cn);
+      if (ev >= 0) st = ev;
+    }
+    if constexpr ((P::id != 2 || IMC_UNROLL2_F64) && GEOM != 3) {
+    if (st == ST_ACTIVE) {
+      int ev;
+      if constexpr (GEOM == 1) ev = seg1d(a, h1, d, tal, cn); else ev = seg2d<1>(a, h2, d, tal, cn);
+      if (ev >= 0) st = ev;
+    }
+    }
+  }
+  if (a.timeline && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMax(a.timeline + 2, t); }
+  tal.flush();
+  cn.commit<TK>(a.tally);
+}
+
 
 // ======================================================================================
 // Sourcing.sample_planck (imc_sourcing.jl:372-399) — thread per sample.  Unused by the reference's step (every call
@@ -1579,8 +1655,10 @@ constexpr int EXACT_BLOCK_MIN = 8192;        // pairwise segments at least this 
 constexpr int EXACT_BLOCK_MAX_DEPTH = 12;    // ... while their tree has at most 2^12 leaf slots (4 Mi records)
 constexpr int EXACT_BLOCK_THREADS = 1024;
 __device__ __forceinline__ int jl_sum_depth_dev(long long n) { int d = 0; while (n > 1024) { n = (n + 1) / 2; ++d; } return d; }
+constexpr int EXACT_SEQBLOCK_MIN = 4096;     // sequential segments at least this long go to k_exact_reduce_seqblock
 __device__ __forceinline__ bool exact_block_segment(long long len, int pairwise) {
-  return pairwise && len >= EXACT_BLOCK_MIN && jl_sum_depth_dev(len) <= EXACT_BLOCK_MAX_DEPTH;
+  if (!pairwise) return len >= EXACT_SEQBLOCK_MIN;
+  return len >= EXACT_BLOCK_MIN && jl_sum_depth_dev(len) <= EXACT_BLOCK_MAX_DEPTH;
 }
 template <class P>
 __global__ void __launch_bounds__(EXACT_BLOCK_THREADS) k_exact_reduce_block(const double* __restrict__ vals, const long long* __restrict__ start,
@@ -1621,6 +1699,49 @@ __global__ void __launch_bounds__(EXACT_BLOCK_THREADS) k_exact_reduce_block(cons
     }
     if (threadIdx.x == 0) out[c] = (double)part[0];
     __syncthreads();
+  }
+}
+// `v = zero(T); v += record ...` (imc_transport.jl:101, :120) over a very long segment by a whole block.  The additions
+// are one dependent chain, but a Float16 / Float32 sum stops moving once it dwarfs the deposits (10^6 records per source
+// cell of the Float16 Su-Olson deck, a few thousand of which change the sum), and "this record leaves v unchanged" can be
+// tested for 1024 records at once: every thread adds ITS record to the running value; if no result differs from it the
+// chain over the chunk leaves it unchanged too and the chunk is skipped.  Otherwise warp 0 walks the chunk from shared
+// memory with warp_seq_add_skip (which jumps from one changing record to the next).  Same bits as the plain loop.
+template <class P>
+__global__ void __launch_bounds__(EXACT_BLOCK_THREADS) k_exact_reduce_seqblock(const unsigned* __restrict__ keys, const double* __restrict__ vals,
+                                                                              const long long* __restrict__ start, long long nacc, double* __restrict__ out) {
+  using N = Num<P>;
+  __shared__ double s_x[EXACT_BLOCK_THREADS];
+  __shared__ unsigned s_k[EXACT_BLOCK_THREADS];
+  __shared__ int s_any[EXACT_BLOCK_THREADS / 32];
+  __shared__ typename P::comp_t s_v;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (long long c = blockIdx.x; c < nacc; c += gridDim.x) {
+    const long long b = start[c], len = start[c + 1] - b;
+    if (!exact_block_segment(len, 0)) continue;
+    N v;                                                                            // zero(T)
+    for (long long base = 0; base < len; base += EXACT_BLOCK_THREADS) {
+      const long long i = base + threadIdx.x;
+      const bool have = i < len;
+      double x = 0.0; unsigned k = 0u;
+      if (have) { x = vals[b + i]; k = keys[b + i]; }
+      const N t = (k & 0x80000000u) ? N::from_d(v.d() + x) : v + N::from_d(x);
+      const bool same = (t.v == v.v && signbit(t.v) == signbit(v.v)) || (t.v != t.v && v.v != v.v);
+      const unsigned m = __ballot_sync(IMC_FULL_MASK, have && !same);
+      if (lane == 0) s_any[wid] = m != 0u;
+      s_x[threadIdx.x] = x; s_k[threadIdx.x] = k;
+      __syncthreads();
+      if (wid == 0) {
+        if (__ballot_sync(IMC_FULL_MASK, s_any[lane] != 0) != 0u) {
+          const long long cnt = len - base < EXACT_BLOCK_THREADS ? len - base : EXACT_BLOCK_THREADS;
+          v = warp_seq_add_skip<P>(v, s_k, s_x, 0, cnt - 1, lane);
+        }
+        if (lane == 0) s_v = v.v;
+      }
+      __syncthreads();
+      v = N(s_v);
+    }
+    if (threadIdx.x == 0) out[c] = v.d();
   }
 }
 // one thread per tally cell: PAIRWISE = FALSE -> `+=` in record order (imc_transport.jl:101,120); TRUE -> sum(vector) (:202)

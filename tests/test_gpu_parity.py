@@ -388,8 +388,7 @@ print("stagnation-skip reducer: identical")
 """
 
 
-@pytest.mark.skipif(os.environ.get("IMC_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental reducer (IMC_EXACT_SKIP=1, off by default): run with IMC_TEST_EXPERIMENTAL=1")
+@pytest.mark.gpu
 def test_stagnation_skip_reducer_is_bit_exact(built):
     """warp_seq_add_skip (sequential EXACT sums with their stagnant stretches skipped) against the oracle, in a process
     that has IMC_EXACT_SKIP=1: Float16 Su-Olson (long stagnant chains), a Float16 random-walk deck (Float64 records mixed
