@@ -701,10 +701,12 @@ struct Counters {
   unsigned long long* s;     // block slots [RB_NSCALARS]
   unsigned long long* seg;   // [blockDim.x]
   unsigned* evn;             // [5][blockDim.x]: census, absorbed, escaped, random-walk kill; [4] = numeric errors
+  double* park;              // [blockDim.x]: one value per thread that is needed only at the end of a history (Float64 MC2D: the angle)
   __device__ __forceinline__ void init(unsigned long long* slots) {
     s = slots;
     seg = slots + RB_NSCALARS + threadIdx.x;
     evn = reinterpret_cast<unsigned*>(slots + RB_NSCALARS + blockDim.x) + threadIdx.x;
+    park = reinterpret_cast<double*>(evn - threadIdx.x + 5 * blockDim.x + (blockDim.x & 1u)) + threadIdx.x;   // 8-byte aligned
     if (threadIdx.x < RB_NSCALARS) s[threadIdx.x] = 0ull;
     *seg = 0ull;
 #pragma unroll
@@ -758,7 +760,7 @@ struct Counters {
   }
 };
 // dynamic shared memory of every tracking kernel ahead of the tally accumulators: block slots + per-thread slots
-constexpr int COUNTER_SMEM_BYTES = RB_NSCALARS * 8 + TRACK_THREADS * 8 + 5 * TRACK_THREADS * 4;
+constexpr int COUNTER_SMEM_BYTES = RB_NSCALARS * 8 + TRACK_THREADS * 8 + 5 * TRACK_THREADS * 4 + 8 + TRACK_THREADS * 8;
 
 // ======================================================================================
 // Transport.MC — 1-D history-based tracking
@@ -921,6 +923,10 @@ struct Hist2 {
   unsigned pi;          // position in the particle list (< 2^32, checked by the engine)
   long long rec_base;
 };
+// The direction angle mu is read once per history (at the census write-back; the loop works with cos / sin): Float64
+// histories, which run at the register cap, keep it in the thread's shared-memory slot instead of two registers.
+template <class P> __device__ __forceinline__ void set_mu(Hist2<P>& h, Counters& cn, Num<P> v) { if constexpr (P::id == 2) *cn.park = v.v; else h.mu = v; }
+template <class P> __device__ __forceinline__ Num<P> get_mu(const Hist2<P>& h, const Counters& cn) { if constexpr (P::id == 2) return Num<P>(*cn.park); else return h.mu; }
 template <class P, class D, int TK>
 __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist2<P>& h, D& d, Counters& cn) {
   using N = Num<P>;
@@ -928,7 +934,8 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   if (h.E.v == (typename P::comp_t)-1) return false;  // 2-D dead flag lives in the energy slot (Q16)
   h.pi = (unsigned)pi;
   h.E0 = N::load(a.p.E0, pi);
-  h.t = N::load(a.p.t, pi); h.x = N::load(a.p.x, pi); h.y = N::load(a.p.y, pi); h.mu = N::load(a.p.mu, pi);
+  h.t = N::load(a.p.t, pi); h.x = N::load(a.p.x, pi); h.y = N::load(a.p.y, pi);
+  const N mu0 = N::load(a.p.mu, pi); set_mu(h, cn, mu0);
   h.xi = a.p.cx[pi]; h.yi = a.p.cy[pi];
   h.k = a.p.ks[pi];
   h.minE = N::from_d(0.01 * h.E0.d());                                              // :531
@@ -936,7 +943,7 @@ __device__ __forceinline__ bool load2d(const TrackArgs<P>& a, long long pi, Hist
   const bool exact = TKind<TK>::exact(a.tally);
   h.rec_base = (exact && a.tally.pass == 2) ? a.tally.rec_off[pi] : 0;
   d.init(a.rng, a.p.id[pi], pi);
-  MathDet::sincos<P>(h.mu, &h.vy, &h.vx);                                           // :534 (recomputed only when mu changes)
+  MathDet::sincos<P>(mu0, &h.vy, &h.vx);                                            // :534 (recomputed only when mu changes)
   recip_dir(h.vx, h.vy, h.rvx, h.rvy);
   { const AxisProp<P>* tab = exact ? a.m.ax_d : a.m.ax_inv;
     const AxisProp<P> ax = tab[h.xi], ay = tab[a.m.nx + h.yi];
@@ -951,7 +958,7 @@ __device__ __forceinline__ void store2d(const TrackArgs<P>& a, Hist2<P>& h, D& d
   if (TKind<TK>::exact(a.tally) && a.tally.pass == 1) { a.tally.rec_cnt[pi] = h.nseg; return; }
   cn.finish(ev, h.nseg);
   if (ev == 0) {
-    h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.y.store(a.p.y, pi); h.mu.store(a.p.mu, pi); h.E.store(a.p.E, pi);
+    h.t.store(a.p.t, pi); h.x.store(a.p.x, pi); h.y.store(a.p.y, pi); get_mu(h, cn).store(a.p.mu, pi); h.E.store(a.p.E, pi);
     a.p.cx[pi] = h.xi; a.p.cy[pi] = h.yi;
   } else h.E.store(a.p.E, pi);
   if (a.out_event) { a.out_event[pi] = (signed char)ev; a.out_nseg[pi] = h.nseg; }
@@ -1036,8 +1043,9 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
     }
     const int side = isx ? (pos ? IMC_BC_RIGHT : IMC_BC_LEFT) : (pos ? IMC_BC_TOP : IMC_BC_BOTTOM);
     if (a.m.bc[side] == IMC_REFLECT) {                                              // :626-628 / :666-668
-      h.mu = isx ? MathDet::atan2<P>(h.vy, -h.vx) : MathDet::atan2<P>(-h.vy, h.vx);
-      MathDet::sincos<P>(h.mu, &h.vy, &h.vx);
+      const N mu1 = isx ? MathDet::atan2<P>(h.vy, -h.vx) : MathDet::atan2<P>(-h.vy, h.vx);
+      set_mu(h, cn, mu1);
+      MathDet::sincos<P>(mu1, &h.vy, &h.vx);
       recip_dir(h.vx, h.vy, h.rvx, h.rvy);
       return -1;
     }
@@ -1045,7 +1053,7 @@ __device__ __forceinline__ int seg2d(const TrackArgs<P>& a, Hist2<P>& h, D& d, T
     h.E = N::from_d(-1.0);
     return 2;
   }
-  if (dist == dist_col) { h.mu = N::from_d(6.283185307179586 * d.template uniform<PAR>(a.rng, seg).d()); MathDet::sincos<P>(h.mu, &h.vy, &h.vx);
+  if (dist == dist_col) { const N mu1 = N::from_d(6.283185307179586 * d.template uniform<PAR>(a.rng, seg).d()); set_mu(h, cn, mu1); MathDet::sincos<P>(mu1, &h.vy, &h.vx);
                            recip_dir(h.vx, h.vy, h.rvx, h.rvy); }  // :706-710
   if (dist == dist_cen) { h.t = zero; return 0; }                      // :712-717
   return -1;
@@ -1104,7 +1112,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_
           h2.nseg = done;
           ev = seg2d(a, h2, d, tal, cn);
           if (ev >= 0) store2d<P, HistDraw<P, false>, TK_RUNTIME>(a, h2, d, ev, cn);
-          else { h2.t.store(a.p.t, pi); h2.x.store(a.p.x, pi); h2.y.store(a.p.y, pi); h2.mu.store(a.p.mu, pi); h2.E.store(a.p.E, pi);
+          else { h2.t.store(a.p.t, pi); h2.x.store(a.p.x, pi); h2.y.store(a.p.y, pi); get_mu(h2, cn).store(a.p.mu, pi); h2.E.store(a.p.E, pi);
                  a.p.cx[pi] = h2.xi; a.p.cy[pi] = h2.yi; a.ev_nseg[pi] = h2.nseg; }
         }
         if (ev < 0) { a.ev_extra[pi] = d.sg.extra_n & 0x3fffffffu; cont = true; }
