@@ -457,6 +457,11 @@ def main():
     if world > 1:
         dist.all_reduce(tot)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    kms_all = [kms]
+    if world > 1:   # per-rank tracking-kernel time: the max enters the step time, the spread says how much is rank imbalance
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([kms], dtype=torch.float64, device=dev))
+        kms_all = [float(g.item()) for g in gathered]
     seg_g, hist_g, seg_e_g, n_part_g = tot.tolist()
     wall_g, wall_e_g, kms_g, host_wall_g, host_wall_e_g = mx.tolist()   # the first two are CUDA-event times (max over ranks)
 
@@ -474,6 +479,7 @@ def main():
             "histories_per_s": hist_g / wall_g, "histories_per_step": hist_g / args.steps, "segments_per_step": seg_g / args.steps,
             "segments_per_history": sph, "particles_resident": n_part_g, "tally_modes_run": sorted(modes),
             "tracking_kernel_ms_per_step": kms_g / args.steps, "tracking_kernel_share_of_step": kms_g / (1e3 * wall_g),
+            "tracking_kernel_ms_per_step_by_rank": [k / args.steps for k in kms_all],
             "timing": "CUDA events on the engine's stream, max over ranks", "host_wall_ms_per_step": 1e3 * host_wall_g / args.steps,
             "e2e": {"value": seg_e_g / wall_e_g, "unit": "segments/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                     "ms_per_step": 1e3 * wall_e_g / args.steps, "host_wall_ms_per_step": 1e3 * host_wall_e_g / args.steps,

@@ -34,6 +34,9 @@ def test_reference_arm_prints_the_contract_line(built):
     assert d["impl"] == "reference" and d["metric"] == "tracked particle-segments/sec" and d["unit"] == "segments/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32"
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the arm describes what IT ran (a bounded sample), not the GPU arm's mesh and population
+    assert d["config"]["mesh"] != d["config"]["gpu_arm_mesh"] == [4096, 4096] and d["config"]["nmax_global"] < d["config"]["gpu_arm_nmax_global"]
+    assert "bounded CPU sample" in d["config"]["workload"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["sample"] and cb["single_core_value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
