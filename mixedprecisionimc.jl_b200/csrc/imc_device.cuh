@@ -107,6 +107,66 @@ __global__ void k_jlsum_fold(typename P::comp_t* part, const unsigned char* vali
   if (threadIdx.x == 0) *out = part[0];
 }
 
+// Several Julia sums in one launch pair (a time step needs 4-15 of them: seven per sourcing call, the energydep planes,
+// three more in the tally; at deck sizes that fit one SM the launches, not the additions, are their cost).  blockIdx.y
+// selects the sum; each sum has its own depth and its own [slots_max] stretch of the part / valid scratch.
+constexpr int JLSUM_BATCH = 8;
+template <class P>
+struct JlSumBatch {
+  const typename P::store_t* q[JLSUM_BATCH];
+  long long n[JLSUM_BATCH];
+  int depth[JLSUM_BATCH];
+  typename P::comp_t* out[JLSUM_BATCH];
+  int count;
+  long long slots_max;
+};
+template <class P>
+__global__ void k_jlsum_leaves_multi(JlSumBatch<P> b, typename P::comp_t* __restrict__ part_all, unsigned char* __restrict__ valid_all) {
+  const int s = blockIdx.y;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int depth = b.depth[s];
+  if (tid >= (1ll << depth)) return;
+  const typename P::store_t* __restrict__ q = b.q[s];
+  typename P::comp_t* part = part_all + (size_t)s * b.slots_max;
+  unsigned char* valid = valid_all + (size_t)s * b.slots_max;
+  const long long n = b.n[s];
+  if (n <= 0) { if (tid == 0) { part[0] = 0; valid[0] = 1; } return; }
+  long long first = 0, last = n - 1;
+  int d = 0;
+  while (true) {
+    if (last - first < 1024) {
+      int rem = depth - d;
+      if (rem > 0 && (tid & ((1ll << rem) - 1)) != 0) { valid[tid] = 0; return; }
+      Num<P> v = Num<P>::load(q, first);
+      for (long long i = first + 1; i <= last; ++i) v = v + Num<P>::load(q, i);
+      part[tid] = v.v;
+      valid[tid] = 1;
+      return;
+    }
+    long long mid = first + ((last - first) >> 1);
+    int bit = (int)((tid >> (depth - 1 - d)) & 1);
+    if (bit) first = mid + 1; else last = mid;
+    ++d;
+  }
+}
+template <class P>
+__global__ void k_jlsum_fold_multi(JlSumBatch<P> b, typename P::comp_t* part_all, const unsigned char* valid_all) {
+  const int s = blockIdx.x;
+  typename P::comp_t* part = part_all + (size_t)s * b.slots_max;
+  const unsigned char* valid = valid_all + (size_t)s * b.slots_max;
+  const int depth = b.depth[s];
+  for (int level = depth; level >= 1; --level) {
+    long long nodes = 1ll << (level - 1);
+    int sh = depth - level;
+    for (long long i = threadIdx.x; i < nodes; i += blockDim.x) {
+      long long ls = (2 * i) << sh, rs = (2 * i + 1) << sh;
+      if (valid[rs]) part[ls] = (Num<P>(part[ls]) + Num<P>(part[rs])).v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *b.out[s] = part[0];
+}
+
 // ---- exclusive scan int32 -> int64 (three-phase) ----------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;

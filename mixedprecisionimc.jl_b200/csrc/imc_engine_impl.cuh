@@ -154,6 +154,7 @@ struct EngineT : EngineBase {
     L.geom = geom; L.nx = nx; L.ny = ny; L.nc = nc;
   }
   ~EngineT() override {
+    if (hpin) cudaFreeHost(hpin);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -179,6 +180,20 @@ struct EngineT : EngineBase {
     return IMC_OK;
   }
   int use_device() { IMC_CK(cudaSetDevice(cfg.device)); return IMC_OK; }
+  // one gather launch + one copy into pinned memory + one synchronisation per stage (k_gather_scalars)
+  double* hpin = nullptr;
+  DBuf<double> dgather;
+  GatherList gl{};
+  void gl_reset() { gl.count = 0; }
+  int gl_add(const void* p, int kind) { gl.p[gl.count] = p; gl.kind[gl.count] = kind; return gl.count++; }
+  int gl_read() {   // results in hpin[0 .. count)
+    if (!hpin) { IMC_CK(cudaMallocHost((void**)&hpin, GATHER_MAX * sizeof(double))); IMC_CK(dgather.alloc(GATHER_MAX)); }
+    k_gather_scalars<P><<<1, GATHER_MAX, 0, stream>>>(gl, dgather.p); ++n_launch;
+    IMC_CK(cudaMemcpyAsync(hpin, dgather.p, gl.count * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaStreamSynchronize(stream));
+    return IMC_OK;
+  }
+  static long long raw_ll(double v) { long long r; memcpy(&r, &v, 8); return r; }
 
   // ---- helpers -----------------------------------------------------------------------------
   int upload(DBuf<S>& b, const double* src, size_t n) {
@@ -204,14 +219,26 @@ struct EngineT : EngineBase {
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
-  // Julia sum of q[0..n) into the device slot `out`
+  // Julia sums of q[0..n) into device slots: requests are queued and run as one launch pair per batch (jl_flush)
+  JlSumBatch<P> jl_batch{};
   int jl_sum(const S* q, long long n, Cc* out) {
-    int depth = jl_sum_depth(n);
-    size_t slots = (size_t)1 << depth;
-    IMC_CK(jl_part.ensure(slots));
-    IMC_CK(jl_valid.ensure(slots));
-    k_jlsum_leaves<P><<<grid_for((long long)slots, 128), 128, 0, stream>>>(q, n, depth, jl_part.p, jl_valid.p); ++n_launch;
-    k_jlsum_fold<P><<<1, 1024, 0, stream>>>(jl_part.p, jl_valid.p, depth, out); ++n_launch;
+    if (jl_batch.count == JLSUM_BATCH) IMC_RC(jl_flush());
+    const int k = jl_batch.count++;
+    jl_batch.q[k] = q; jl_batch.n[k] = n; jl_batch.depth[k] = jl_sum_depth(n); jl_batch.out[k] = out;
+    return IMC_OK;
+  }
+  int jl_flush() {
+    if (jl_batch.count == 0) return IMC_OK;
+    int dmax = 0;
+    for (int k = 0; k < jl_batch.count; ++k) dmax = std::max(dmax, jl_batch.depth[k]);
+    const size_t slots = (size_t)1 << dmax;
+    jl_batch.slots_max = (long long)slots;
+    IMC_CK(jl_part.ensure(slots * JLSUM_BATCH));
+    IMC_CK(jl_valid.ensure(slots * JLSUM_BATCH));
+    dim3 grid(grid_for((long long)slots, 128), (unsigned)jl_batch.count);
+    k_jlsum_leaves_multi<P><<<grid, 128, 0, stream>>>(jl_batch, jl_part.p, jl_valid.p); ++n_launch;
+    k_jlsum_fold_multi<P><<<(unsigned)jl_batch.count, 1024, 0, stream>>>(jl_batch, jl_part.p, jl_valid.p); ++n_launch;
+    jl_batch.count = 0;
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
@@ -299,7 +326,7 @@ struct EngineT : EngineBase {
     // sourcing / tally scratch
     long long M = L.total();
     IMC_CK(src_e.alloc(M)); IMC_CK(src_q.alloc(M)); IMC_CK(src_nrg.alloc(M)); IMC_CK(src_ks.alloc(M)); IMC_CK(src_cnt.alloc(M));
-    IMC_CK(src_offs.alloc(M + 1)); IMC_CK(src_qem.alloc(nc * ns)); IMC_CK(src_sc.alloc(1)); IMC_CK(sums.alloc(16));
+    IMC_CK(src_offs.alloc(M + 1)); IMC_CK(src_qem.alloc(nc * ns)); IMC_CK(src_sc.alloc(1)); IMC_CK(sums.alloc(16 + IMC_MAX_SCALES));
     IMC_CK(q_dep.alloc(nc * ns)); IMC_CK(q_tot.alloc(nc)); IMC_CK(q_rad.alloc(nc));
     IMC_CK(d_max.alloc(2)); IMC_CK(d_flag.alloc(2)); IMC_CK(over_flag.alloc(2));
     // device view
@@ -402,6 +429,7 @@ struct EngineT : EngineBase {
       IMC_RC(jl_sum(s.q + L.rad0(), nc, sums.p + 5));
     }
     IMC_RC(jl_sum(s.q_em, nc * ns, sums.p + 6));
+    IMC_RC(jl_flush());
     long long n_census = n_census_global >= 0 ? n_census_global : n_part;
     int wide_counts = (P::id == 0) && (std::max<int64_t>(n_input, cfg.n_max) > 65504);
     k_src_total<P><<<1, 1, 0, stream>>>(s, L, sums.p, src_sc.p, n_input, n_census, cfg.n_max, cellmin, wide_counts); ++n_launch;
@@ -409,10 +437,11 @@ struct EngineT : EngineBase {
     IMC_CK(cudaGetLastError());
     IMC_RC(scan_counts(s.cnt, src_offs.p, L.total()));
     SrcScalars hsc; long long total = 0; Cc h_emsum = 0;
-    IMC_CK(cudaMemcpyAsync(&hsc, src_sc.p, sizeof hsc, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaMemcpyAsync(&total, scan_total.p, sizeof total, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaMemcpyAsync(&h_emsum, sums.p + 6, sizeof(Cc), cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaStreamSynchronize(stream));
+    gl_reset();
+    gl_add(&src_sc.p->totalenergy, GK_RAW8); gl_add(&src_sc.p->nsrc, GK_RAW8); gl_add(&src_sc.p->bad, GK_I32);
+    gl_add(scan_total.p, GK_RAW8); gl_add(sums.p + 6, GK_T);
+    IMC_RC(gl_read());
+    hsc.totalenergy = hpin[0]; hsc.nsrc = hpin[1]; hsc.bad = (int)hpin[2]; total = raw_ll(hpin[3]); h_emsum = (Cc)hpin[4];
     totalenergy = hsc.totalenergy;
     const long long world = cfg.world > 0 ? cfg.world : 1, rank = cfg.rank;
     long long n_local = total > rank ? (total - rank + world - 1) / world : 0;
@@ -423,10 +452,12 @@ struct EngineT : EngineBase {
       k_src_emit<P><<<grid_for(n_local, 256), 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, n_part, n_local, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p);
       ++n_launch;
       IMC_CK(cudaGetLastError());
-      unsigned long long over = 0;
-      IMC_CK(cudaMemcpyAsync(&over, over_flag.p, sizeof over, cudaMemcpyDeviceToHost, stream));
-      IMC_CK(cudaStreamSynchronize(stream));
-      if (over) { err = "source tape exhausted"; return IMC_ERR_TAPE; }
+      if (cfg.rng_mode == IMC_RNG_TAPE) {   // only a tape can run out
+        unsigned long long over = 0;
+        IMC_CK(cudaMemcpyAsync(&over, over_flag.p, sizeof over, cudaMemcpyDeviceToHost, stream));
+        IMC_CK(cudaStreamSynchronize(stream));
+        if (over) { err = "source tape exhausted"; return IMC_ERR_TAPE; }
+      }
     }
     n_part += n_local;
     n_global_after_source = (n_census_global >= 0 ? (long long)n_census_global : n_part - n_local) + total;
@@ -759,9 +790,12 @@ struct EngineT : EngineBase {
     }
     double sc[RB_NSCALARS];
     unsigned long long over = 0;
-    IMC_CK(cudaMemcpyAsync(sc, red.p + rb_sc0(), sizeof sc, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaMemcpyAsync(&over, over_flag.p, sizeof over, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaStreamSynchronize(stream));
+    gl_reset();
+    for (int k = 0; k < RB_NSCALARS; ++k) gl_add(red.p + rb_sc0() + k, GK_RAW8);
+    gl_add(over_flag.p, GK_RAW8);
+    IMC_RC(gl_read());
+    for (int k = 0; k < RB_NSCALARS; ++k) sc[k] = hpin[k];
+    over = (unsigned long long)raw_ll(hpin[RB_NSCALARS]);
     float ms = 0;
     if (n_part > 0) IMC_CK(cudaEventElapsedTime(&ms, ev0, ev1));
     auto cnt = [&](int k) -> uint64_t {
@@ -807,8 +841,9 @@ struct EngineT : EngineBase {
     k_scan_small<<<1, 1024, 0, stream>>>(blk_cnt.p, blocks, scan_total.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     long long total = 0;
-    IMC_CK(cudaMemcpyAsync(&total, scan_total.p, sizeof total, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaStreamSynchronize(stream));
+    gl_reset(); gl_add(scan_total.p, GK_RAW8);
+    IMC_RC(gl_read());
+    total = raw_ll(hpin[0]);
     if (total == n_part) { if (n_alive) *n_alive = n_part; return IMC_OK; }   // nobody died (Su-Olson: most steps): the list is already compact
     k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, dst, n_part, geom, blk_cnt.p); ++n_launch;
     IMC_CK(cudaGetLastError());
@@ -859,32 +894,33 @@ struct EngineT : EngineBase {
     k_tally_finish<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, s, P::from_d(dt_), t_ == 0.0 ? 1 : 0, cfg.linearized, temp_wide ? 1 : 0); ++n_launch;
     IMC_CK(cudaGetLastError());
     if (cfg.linearized && P::id != 2) temp_wide = true;
-    // per-plane Julia sums of (energydep .* vol) ./ scale, four planes per readback
-    std::vector<Cc> plane(ns);
-    for (int k0 = 0; k0 < ns; k0 += 4) {
-      int kn = std::min(4, ns - k0);
-      for (int k = 0; k < kn; ++k) IMC_RC(jl_sum(q_dep.p + nc * (k0 + k), nc, sums.p + 8 + k));
-      IMC_CK(cudaMemcpyAsync(plane.data() + k0, sums.p + 8, kn * sizeof(Cc), cudaMemcpyDeviceToHost, stream));
-      IMC_CK(cudaStreamSynchronize(stream));
-    }
-    N ted;
-    for (int k = 0; k < ns; ++k) ted = ted + N(plane[k]);                            // :51 / :55
-    totalenergydep = ted.d();
+    // per-plane Julia sums of (energydep .* vol) ./ scale (device slots 16 ..), sum(nrg_inc), sum(matenergydens + radenergydens),
+    // the radiation energy: one batch, one readback below
+    for (int k = 0; k < ns; ++k) IMC_RC(jl_sum(q_dep.p + nc * k, nc, sums.p + 16 + k));
     IMC_RC(jl_sum(nrg_inc.p, nc, sums.p + 12));
     IMC_RC(jl_sum(q_tot.p, nc, sums.p + 13));
     k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p); ++n_launch;
     IMC_RC(jl_sum(q_rad.p, nc, sums.p + 14));
+    IMC_RC(jl_flush());
     double ninf = -INFINITY;
     IMC_CK(cudaMemcpyAsync(d_max.p, &ninf, sizeof ninf, cudaMemcpyHostToDevice, stream));
     IMC_CK(cudaMemsetAsync(d_flag.p, 0, sizeof(int), stream));
     k_max_f64<<<sm_count * 2, 256, 0, stream>>>(temp.p, nc, d_max.p, d_flag.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     Cc h2[3]; double mx; int has_nan; double gseg = 0;
-    IMC_CK(cudaMemcpyAsync(&gseg, red.p + rb_sc0() + RB_SEG, sizeof gseg, cudaMemcpyDeviceToHost, stream));   // summed over ranks by the host
-    IMC_CK(cudaMemcpyAsync(h2, sums.p + 12, 3 * sizeof(Cc), cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaMemcpyAsync(&mx, d_max.p, sizeof mx, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaMemcpyAsync(&has_nan, d_flag.p, sizeof has_nan, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaStreamSynchronize(stream));
+    std::vector<Cc> plane(ns);
+    gl_reset();
+    for (int k = 0; k < 3; ++k) gl_add(sums.p + 12 + k, GK_T);
+    gl_add(d_max.p, GK_RAW8); gl_add(d_flag.p, GK_I32);
+    gl_add(red.p + rb_sc0() + RB_SEG, GK_RAW8);                                     // summed over ranks by the host
+    for (int k = 0; k < ns; ++k) gl_add(sums.p + 16 + k, GK_T);
+    IMC_RC(gl_read());
+    for (int k = 0; k < 3; ++k) h2[k] = (Cc)hpin[k];
+    mx = hpin[3]; has_nan = (int)hpin[4]; gseg = hpin[5];
+    for (int k = 0; k < ns; ++k) plane[k] = (Cc)hpin[6 + k];
+    N ted;
+    for (int k = 0; k < ns; ++k) ted = ted + N(plane[k]);                            // :51 / :55
+    totalenergydep = ted.d();
     rad_total_h = (double)h2[2];
     if (red_fixed) { long long v; memcpy(&v, &gseg, 8); last_global_segments = (double)v; } else last_global_segments = gseg;
     IMC_RC(history_push());
@@ -902,10 +938,11 @@ struct EngineT : EngineBase {
     k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p); ++n_launch;
     IMC_CK(cudaGetLastError());
     IMC_RC(jl_sum(q_rad.p, nc, sums.p + 14));
+    IMC_RC(jl_flush());
     Cc h; double lost_raw;
-    IMC_CK(cudaMemcpyAsync(&h, sums.p + 14, sizeof h, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaMemcpyAsync(&lost_raw, red.p + rb_sc0() + RB_LOST, sizeof lost_raw, cudaMemcpyDeviceToHost, stream));
-    IMC_CK(cudaStreamSynchronize(stream));
+    gl_reset(); gl_add(sums.p + 14, GK_T); gl_add(red.p + rb_sc0() + RB_LOST, GK_RAW8);
+    IMC_RC(gl_read());
+    h = (Cc)hpin[0]; lost_raw = hpin[1];
     double lost;
     if (red_fixed) { long long v; memcpy(&v, &lost_raw, 8); lost = (double)v / fx_mul_lost; } else lost = lost_raw;
     N radenergy(h), te = N::from_d(totalenergy), ted = N::from_d(totalenergydep), old = N::from_d(radenergyold), lo = N::from_d(lost);

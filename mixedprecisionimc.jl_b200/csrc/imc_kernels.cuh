@@ -1894,6 +1894,22 @@ static __global__ void k_max_f64(const double* __restrict__ v, long long n, doub
   }
 }
 
+// Scalars a stage hands back to the host live in several device arrays (reduction slots, the reduce buffer's tail, flags).
+// One launch gathers up to GATHER_MAX of them as 8-byte words (values of T and ints converted to Float64, 8-byte values
+// copied bit for bit) so that the host needs ONE copy into pinned memory and one synchronisation per stage — each separate
+// cudaMemcpyAsync into pageable host memory is a synchronisation of its own.
+constexpr int GATHER_MAX = 32;
+enum { GK_T = 0, GK_RAW8 = 1, GK_I32 = 2 };
+struct GatherList { const void* p[GATHER_MAX]; int kind[GATHER_MAX]; int count; };
+template <class P>
+__global__ void k_gather_scalars(GatherList g, double* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i >= g.count) return;
+  if (g.kind[i] == GK_T) out[i] = (double)*static_cast<const typename P::comp_t*>(g.p[i]);
+  else if (g.kind[i] == GK_I32) out[i] = (double)*static_cast<const int*>(g.p[i]);
+  else out[i] = *static_cast<const double*>(g.p[i]);
+}
+
 // fixed-point slot: value * ratio (a power of two), when the scale of the slot changes between two calls
 static __global__ void k_rescale_fixed(long long* slot, double ratio) { *slot = __double2ll_rn((double)*slot * ratio); }
 

@@ -1,0 +1,10 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+{
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python scratch/shipped_decks.py 2>&1 | tail -8
+for wl in marshak_f32_rw suolson_f32 crookedpipe_f32; do timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('$wl value %.4g ms/step %.3f kernel %.3f frac %.4f e2e %.4g launches/step %.0f'%(d['value'],d['ms_per_step'],d['tracking_kernel_ms_per_step'],d['roofline']['frac'],d['e2e']['value'], d['gpu_launches']/d['steps']), d.get('tally_modes_run'), d['schedule_per_step'][-1])"; done
+} 2>&1 | tee gpurun_out/r2_call24.log
