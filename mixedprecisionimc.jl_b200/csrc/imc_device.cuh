@@ -10,33 +10,37 @@
 #include "imc_num.h"
 #include "imc_math.h"
 #include "imc_rng.h"
+#include "imc_sortnet.h"
 
 namespace imc {
 
 #define IMC_FULL_MASK 0xffffffffu
 
 // ---- Utilities.sorter -------------------------------------------------------------------------
-// vals: Float64 images of the literal array (<= 12 entries); scales: descending.  Pair products are
+// vals: Float64 images of the N entries of the literal array; scales: descending.  Pair products are
 // formed in the array's element type and converted to T: for T-valued inputs that is one rounding of
 // the exact product, for Float64 inputs (Q12/Q31) T(Float64 product) — both equal from_d(a*b).
-template <class P, int NMAX>
-__device__ __forceinline__ void sorter_dev(const double (&vals)[NMAX], int n, const double* scales, int n_scales,
-                                           Num<P>* prod_out, int* idx_out) {
-  for (int j = 0; j < n_scales; ++j) {
-    double s[NMAX + 1];
+// The N values are sorted once by a register sorting network (imc_sortnet.h); each candidate scale is then put in its
+// place (after every value <= it, where the reference's sort of `vals U {scale}` leaves it) with static indices.
+template <class P, int N>
+__device__ __forceinline__ void sorter_dev(const double (&vals)[N], const double* scales, int n_scales, Num<P>* prod_out, int* idx_out) {
+  constexpr int M = N + 1;
+  double v[N];
 #pragma unroll
-    for (int i = 0; i < NMAX; ++i) s[i] = i < n ? vals[i] : 0.0;
-    s[n] = scales[j];
-    int m = n + 1;
-    for (int i = 1; i < m; ++i) {  // insertion sort, ascending
-      double key = s[i];
-      int k = i - 1;
-      while (k >= 0 && s[k] > key) { s[k + 1] = s[k]; --k; }
-      s[k + 1] = key;
-    }
+  for (int i = 0; i < N; ++i) v[i] = vals[i];
+  sortnet::sort(v);
+  for (int j = 0; j < n_scales; ++j) {
+    const double sc = scales[j];
+    int pos = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) pos += v[i] <= sc ? 1 : 0;
+    double s[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = i < pos ? v[i < N ? i : N - 1] : (i == pos ? sc : v[i > 0 ? i - 1 : 0]);
     Num<P> product = Num<P>::from_d(1.0);
-    for (int i = 0; i < m / 2; ++i) product *= Num<P>::from_d(s[i] * s[m - 1 - i]);
-    if (m & 1) product *= Num<P>::from_d(s[m / 2]);
+#pragma unroll
+    for (int i = 0; i < M / 2; ++i) product *= Num<P>::from_d(s[i] * s[M - 1 - i]);
+    if (M & 1) product *= Num<P>::from_d(s[M / 2]);
     if (!is_inf(product) && !is_nan(product)) { *prod_out = product; *idx_out = j; return; }
   }
   *prod_out = Num<P>();

@@ -255,7 +255,7 @@ __global__ void k_update(MeshDev<P> m, typename P::comp_t dt_, int linearized, i
   double vals[6] = {(double)m.ds, (double)m.alpha, beta.d(), (double)m.c, dt.d(), sa.d()};
   double sc1 = 1.0;
   N prod; int idx;
-  sorter_dev<P, 6>(vals, 6, &sc1, 1, &prod, &idx);
+  sorter_dev<P, 6>(vals, &sc1, 1, &prod, &idx);
   N f = N::from_d(1.0 / (1.0 + prod.d()));                                         // :39 / :52
   f.store(m.fleck, i);
   // per-cell quantities the tracking loop recomputes every segment in the reference, formed once
@@ -333,22 +333,18 @@ __global__ void k_src_energies(MeshDev<P> m, SrcArrays<P> s, SrcLayout L, typena
   const double dt = (double)dt_, a = (double)m.a, c = (double)m.c, ds = (double)m.ds;
   N prod; int idx;
   if (e < L.n_surf()) {
-    double vals[9]; int n;
     if (L.geom == 1) {                                                            // :60-61
       double ts = Num<P>::load(m.tsurf[e == 0 ? 2 : 3], 0).d();
-      double v[9] = {a, c, ts, ts, ts, ts, dt, 0.25, 0.0};
-      for (int k = 0; k < 9; ++k) vals[k] = v[k];
-      n = 8;
+      const double vals[8] = {a, c, ts, ts, ts, ts, dt, 0.25};
+      sorter_dev<P, 8>(vals, m.scales_d, m.ns, &prod, &idx);
     } else {                                                                      // :86-93
       int side; long long i = e;
       if (i < L.nx) side = 0; else if ((i -= L.nx) < L.nx) side = 1; else if ((i -= L.nx) < L.ny) side = 2; else { i -= L.ny; side = 3; }
       double ts = Num<P>::load(m.tsurf[side], i).d();
       double width = side < 2 ? Num<P>::load(m.dx, i).d() : Num<P>::load(m.dy, i).d();
-      double v[9] = {a, c, ts, ts, ts, ts, width, dt, 0.25};
-      for (int k = 0; k < 9; ++k) vals[k] = v[k];
-      n = 9;
+      const double vals[9] = {a, c, ts, ts, ts, ts, width, dt, 0.25};
+      sorter_dev<P, 9>(vals, m.scales_d, m.ns, &prod, &idx);
     }
-    sorter_dev<P, 9>(vals, n, m.scales_d, m.ns, &prod, &idx);
     prod.store(s.e, e); s.ks[e] = (signed char)idx;
     (prod / (idx >= 0 ? N(m.scales[idx]) : N())).store(s.q, e);
     return;
@@ -360,26 +356,22 @@ __global__ void k_src_energies(MeshDev<P> m, SrcArrays<P> s, SrcLayout L, typena
   double dy = L.geom == 2 ? N::load(m.dy, yi).d() : 0.0;
   double rs = N::load(m.radsource, i).d();
   {                                                                               // body :67 / :102
-    double vals[12] = {f, sa, a, c, t, t, t, t, dx, dt, ds, 0.0};
-    int n = 11;
-    if (L.geom == 2) { vals[9] = dy; vals[10] = dt; vals[11] = ds; n = 12; }
-    sorter_dev<P, 12>(vals, n, m.scales_d, m.ns, &prod, &idx);
+    if (L.geom == 2) { const double vals[12] = {f, sa, a, c, t, t, t, t, dx, dy, dt, ds}; sorter_dev<P, 12>(vals, m.scales_d, m.ns, &prod, &idx); }
+    else { const double vals[11] = {f, sa, a, c, t, t, t, t, dx, dt, ds}; sorter_dev<P, 11>(vals, m.scales_d, m.ns, &prod, &idx); }
     long long eb = L.body0() + i;
     prod.store(s.e, eb); s.ks[eb] = (signed char)idx;
     (prod / (idx >= 0 ? N(m.scales[idx]) : N())).store(s.q, eb);
   }
   {                                                                               // radiation source :68 / :103
-    double vals[4] = {rs, dx, dt, 0.0};
-    int n = 3;
-    if (L.geom == 2) { vals[2] = dy; vals[3] = dt; n = 4; }
-    sorter_dev<P, 4>(vals, n, m.scales_d, m.ns, &prod, &idx);
+    if (L.geom == 2) { const double vals[4] = {rs, dx, dy, dt}; sorter_dev<P, 4>(vals, m.scales_d, m.ns, &prod, &idx); }
+    else { const double vals[3] = {rs, dx, dt}; sorter_dev<P, 3>(vals, m.scales_d, m.ns, &prod, &idx); }
     long long er = L.rad0() + i;
     prod.store(s.e, er); s.ks[er] = (signed char)idx;
     (prod / (idx >= 0 ? N(m.scales[idx]) : N())).store(s.q, er);
   }
   {                                                                               // emitted energy density :69-70 / :104-105
     double vals[10] = {f, sa, a, c, t, t, t, t, dt, ds};
-    sorter_dev<P, 10>(vals, 10, m.scales_d, m.ns, &prod, &idx);
+    sorter_dev<P, 10>(vals, m.scales_d, m.ns, &prod, &idx);
     for (int k = 0; k < m.ns; ++k) {
       N v = (k == idx) ? prod : N();
       v.store(m.emittedenergy, i + m.nc * k);
@@ -1843,7 +1835,7 @@ __global__ void k_tally_finish(MeshDev<P> m, TallyScratch<P> s, typename P::comp
   if (t_is_zero) {                                                                 // :29-32 (Q11)
     double vals[10] = {N::load(m.fleck, i).d(), N::load(m.sa, i).d(), (double)m.a, (double)m.c, t, t, t, t, dt.d(), (double)m.ds};
     double sc1 = 1.0; int idx;
-    sorter_dev<P, 10>(vals, 10, &sc1, 1, &mat, &idx);
+    sorter_dev<P, 10>(vals, &sc1, 1, &mat, &idx);
   }
   int xi = (int)(m.geom == 1 ? i : i % m.nx), yi = (int)(m.geom == 1 ? 0 : i / m.nx);
   N vol = m.geom == 1 ? N::load(m.dx, xi) : N::load(m.dx, xi) * N::load(m.dy, yi);
