@@ -100,7 +100,7 @@ struct EngineT : EngineBase {
   DBuf<S> src_e, src_q, src_nrg, src_qem;
   DBuf<signed char> src_ks;
   DBuf<int> src_cnt;
-  DBuf<long long> src_offs, scan_tiles, scan_tiles2, scan_total;
+  DBuf<long long> src_offs, src_block_entry, scan_tiles, scan_tiles2, scan_total;
   DBuf<SrcScalars> src_sc;
   DBuf<Cc> sums;  // device slots for jl_sum results
   // jl_sum scratch
@@ -449,7 +449,11 @@ struct EngineT : EngineBase {
     IMC_RC(ensure_capacity(n_part + n_local));
     if (n_local > 0) {
       IMC_CK(cudaMemsetAsync(over_flag.p, 0, sizeof(unsigned long long), stream));
-      k_src_emit<P><<<grid_for(n_local, 256), 256, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, n_part, n_local, (int)rank, (int)world, dt, rng_args(step, true), over_flag.p);
+      const long long n_blocks = (n_local + EMIT_THREADS - 1) / EMIT_THREADS;
+      IMC_CK(src_block_entry.ensure((size_t)n_blocks + 1));
+      k_src_block_entries<<<grid_for(n_blocks + 1, 256), 256, 0, stream>>>(src_offs.p, L.total(), n_local, (int)rank, (int)world, n_blocks, src_block_entry.p); ++n_launch;
+      k_src_emit<P><<<(unsigned)n_blocks, EMIT_THREADS, 0, stream>>>(m, pb[cur].view(), s, L, src_offs.p, src_block_entry.p, n_part, n_local, (int)rank, (int)world, dt,
+                                                                    rng_args(step, true), over_flag.p);
       ++n_launch;
       IMC_CK(cudaGetLastError());
       if (cfg.rng_mode == IMC_RNG_TAPE) {   // only a tape can run out

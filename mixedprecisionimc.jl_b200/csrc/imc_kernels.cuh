@@ -535,19 +535,37 @@ __device__ __forceinline__ void emit_one(const MeshDev<P>& m, const Parts<P>& p,
   if (d.over()) atomicAdd(over_flag, 1ull);
 }
 
-// thread per new particle: the entry is found by binary search in the scan of the counts — robust for any count
-// distribution (one surface entry of a 1-D deck emits millions of particles, a cold body cell emits CELLMIN).  Measured
-// alternatives, all slower or equal (the search is a chain of ~25 dependent loads, hidden by 32 warps per SM): thread per
-// entry (16x slower on Marshak), one search per warp + shuffle window (3.2 vs 3.06 ms), one search per block (3.5 ms)
+// thread per new particle: the entry (source cell or surface element) of particle ordinal j is the last e with
+// offs[e] <= j.  A full binary search in the scan of the counts is 25 dependent loads over 268 MB (4096^2 mesh: 64 % of
+// the kernel's instructions, 79 % of its stall samples), so it is done once per BLOCK by a small pre-kernel
+// (k_src_block_entries: entry of each block's first particle); inside the block the ordinals are consecutive, so every
+// thread searches only between its block's entry and the next block's — a window of a few hundred entries at most
+// (one entry when a hot surface element emits the whole block), resident in L1.  Robust for any count distribution.
+// Measured alternatives of round 1, all slower or equal: thread per entry (16x slower on Marshak), one search per warp +
+// shuffle window, one search per block inside the kernel.
+constexpr int EMIT_THREADS = 256;
+static __global__ void k_src_block_entries(const long long* __restrict__ offs, long long n_entries, long long n_local, int rank, int world,
+                                           long long n_blocks, long long* __restrict__ block_entry) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_blocks) return;
+  if (b == n_blocks) { block_entry[b] = n_entries - 1; return; }
+  const long long j = rank + (b * EMIT_THREADS) * (long long)world;
+  long long lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const long long mid = (lo + hi + 1) >> 1;
+    if (offs[mid] <= j) lo = mid; else hi = mid - 1;
+  }
+  block_entry[b] = lo;
+}
 template <class P>
-__global__ void k_src_emit(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
-                           long long base, long long n_local, int rank, int world, typename P::comp_t dt_,
+__global__ void __launch_bounds__(EMIT_THREADS) k_src_emit(MeshDev<P> m, Parts<P> p, SrcArrays<P> s, SrcLayout L, const long long* __restrict__ offs,
+                           const long long* __restrict__ block_entry, long long base, long long n_local, int rank, int world, typename P::comp_t dt_,
                            RngArgs rng, unsigned long long* over_flag) {
-  long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long l = (long long)blockIdx.x * EMIT_THREADS + threadIdx.x;
   if (l >= n_local) return;
   long long j = rank + l * (long long)world;  // global ordinal in the reference's emission order
-  // entry = last e with offs[e] <= j
-  long long lo = 0, hi = L.total() - 1;
+  // entry = last e with offs[e] <= j, between the entries of this block's and the next block's first particle
+  long long lo = block_entry[blockIdx.x], hi = block_entry[blockIdx.x + 1];
   while (lo < hi) {
     long long mid = (lo + hi + 1) >> 1;
     if (offs[mid] <= j) lo = mid; else hi = mid - 1;
