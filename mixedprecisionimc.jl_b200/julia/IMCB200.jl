@@ -190,6 +190,12 @@ function fetch_history!(mesh)
     return n[]
 end
 
+"""Restart point inside the library (imc_checkpoint, include/imc.h): `checkpoint!(mesh, :save)` copies the engine's whole
+mutable state — what `deepcopy(mesh), deepcopy(particles)` would keep in the reference — in device memory, `:restore` makes it
+current again, `:drop` frees it.  The host restores its own `simvars.t`, `simvars.dt` and `STEP[]`."""
+checkpoint!(mesh, op::Symbol) = check(engine(mesh), ccall((:imc_checkpoint, libimc), Cint, (Ptr{Cvoid}, Int32), engine(mesh),
+                                                         Int32(op === :save ? 0 : op === :restore ? 1 : 2)))
+
 module EnergyCheck
     import ..IMCB200: engine, check, libimc, EnergyStats, STEP
     function energychecker(inputs, mesh, simvars, particles)                  # imc_energycheck.jl:10

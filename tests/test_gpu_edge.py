@@ -153,3 +153,19 @@ def test_fused_step_equals_staged_calls(gpu_lib, oracle_lib, deck):
         assert np.array_equal(ia, ib) and np.array_equal(pa, pb)
         for name in ("temp", "matenergydens", "radenergydens", "energydep", "fleck"):
             assert np.array_equal(a.engine.field(name), other.engine.field(name)), name
+
+
+@pytest.mark.parametrize("precision,nx,ny,tally", [
+    ("FLOAT32", 1536, 8, "atomic"),    # Nc = 12288: Float32 accumulators fill 48 KB exactly — the counter slots must be budgeted too
+    ("FLOAT32", 1536, 1, "atomic"), ("FLOAT32", 3072, 1, "atomic"), ("FLOAT32", 6144, 1, "atomic"),
+    ("FLOAT64", 768, 1, "atomic"), ("FLOAT64", 1536, 1, "atomic"), ("FLOAT64", 3072, 2, "atomic"),
+    ("FLOAT32", 768, 8, "fixed"), ("FLOAT32", 3072, 2, "fixed"), ("FLOAT64", 6144, 1, "fixed"),
+])
+def test_accumulator_sets_at_the_shared_memory_limit(gpu_lib, oracle_lib, precision, nx, ny, tally):
+    """Mesh sizes whose shared-memory accumulator sets total exactly 48 KB (or a power-of-two fraction of it): the launch
+    must budget the per-thread counter slots inside the limit (round 1 requested 48 KB + 64 B and failed with
+    cudaErrorInvalidValue); particles and event counts stay bit-identical to the oracle."""
+    inputs = degenerate_2d(precision, nx, ny, ("REFLECT", "VACUUM", "REFLECT", "VACUUM"), n_input=3000)
+    mode = {"atomic": lib.TALLY_ATOMIC, "fixed": lib.TALLY_FIXED}[tally]
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=2, precision=precision, tally_mode=mode)
+    assert_step_parity(a, b, out, precision)
