@@ -145,9 +145,24 @@ IMC_HD bool sign_bit(double x) {
 // Julia's min(x, y) for floats: NaN-propagating; min(-0.0, 0.0) = -0.0.
 // Device, Float16/Float32: one FMNMX.NAN — PTX min.NaN.f32 returns NaN if either input is NaN and orders
 // -0.0 < +0.0 (PTX ISA "min": "if both inputs are 0.0 then +0.0 > -0.0"); checked on B200 by tests/test_gpu_parity.py.
+// the generic definition (host, and the reference the device fast paths are self-tested against)
+template <class P> IMC_HD Num<P> jl_min_generic(Num<P> a, Num<P> b) {
+  if (a.v != a.v) return a;
+  if (b.v != b.v) return b;
+  if (a.v < b.v) return a;
+  if (b.v < a.v) return b;
+  return Num<P>(sign_bit((double)a.v) ? a.v : b.v);
+}
 template <class P> IMC_HD Num<P> jl_min(Num<P> a, Num<P> b) {
 #if defined(__CUDA_ARCH__)
   if constexpr (P::id != 2) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a.v), "f"(b.v)); return Num<P>(r); }
+  else {
+    // Float64: PTX has no min.NaN.f64.  min.f64 (DMNMX) returns the other operand when one is NaN and orders -0 < +0;
+    // the NaN is put back by two selects (a's NaN first, like the generic code).  Checked against jl_min_generic on the
+    // device over special values and random pairs (imc_cuda_selftest_min, tests/test_gpu_parity.py).
+    const double r = fmin(a.v, b.v);
+    return Num<P>(a.v != a.v ? a.v : (b.v != b.v ? b.v : r));
+  }
 #endif
   if (a.v != a.v) return a;
   if (b.v != b.v) return b;
@@ -158,9 +173,10 @@ template <class P> IMC_HD Num<P> jl_min(Num<P> a, Num<P> b) {
 }
 // the smaller of two non-negative values, or the one that is not NaN when exactly one is (the NaN guards of
 // imc_transport.jl:551-557 around min(dist_bx, dist_by)); both NaN -> NaN
+template <class P> IMC_HD Num<P> min_nonnan_generic(Num<P> a, Num<P> b) { return a.v != a.v ? b : (b.v != b.v ? a : jl_min_generic(a, b)); }
 template <class P> IMC_HD Num<P> min_nonnan(Num<P> a, Num<P> b) {
 #if defined(__CUDA_ARCH__)
-  if constexpr (P::id != 2) return Num<P>(fminf(a.v, b.v));
+  if constexpr (P::id != 2) return Num<P>(fminf(a.v, b.v)); else return Num<P>(fmin(a.v, b.v));
 #endif
   return a.v != a.v ? b : (b.v != b.v ? a : jl_min(a, b));
 }

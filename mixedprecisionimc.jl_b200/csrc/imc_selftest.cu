@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "imc_fastdiv.cuh"
+#include "imc_num.h"
 
 namespace imc {
 
@@ -52,7 +53,50 @@ __global__ void k_selftest_div(uint64_t seed, long long per_thread, int mode, un
   atomicAdd(tested, n);
 }
 
+// jl_min / min_nonnan device fast paths (imc_num.h) against the generic definitions, Float64 and Float32: every pair of a
+// table of special values (signed zeros, NaNs of both signs, infinities, subnormals, extremes) and random bit patterns
+__global__ void k_selftest_min(uint64_t seed, long long per_thread, unsigned long long* mismatches, unsigned long long* tested) {
+  const uint64_t special[16] = {0x0000000000000000ull, 0x8000000000000000ull, 0x7ff8000000000000ull, 0xfff8000000000000ull, 0x7ff0000000000000ull,
+                                0xfff0000000000000ull, 0x0000000000000001ull, 0x8000000000000001ull, 0x3ff0000000000000ull, 0xbff0000000000000ull,
+                                0x7fefffffffffffffull, 0xffefffffffffffffull, 0x7ff0000000000001ull, 0x0010000000000000ull, 0x3fe0000000000000ull, 0x4000000000000000ull};
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t s = mix64(seed ^ (tid * 0x2545F4914F6CDD1Dull));
+  unsigned long long bad = 0, n = 0;
+  for (long long it = 0; it < per_thread; ++it) {
+    s = mix64(s); uint64_t ua = s; s = mix64(s); uint64_t ub = s;
+    if (it < 256) { ua = special[(it >> 4) & 15]; ub = special[it & 15]; }      // all 256 special pairs first
+    else if ((s & 7) == 0) ub = ua ^ ((s >> 8) & 1 ? 0x8000000000000000ull : 1ull);   // equal magnitudes / neighbours
+    const double a = __longlong_as_double((long long)ua), b = __longlong_as_double((long long)ub);
+    const float af = __uint_as_float((uint32_t)(ua >> 32)), bf = __uint_as_float((uint32_t)(ub >> 32));
+    auto same64 = [](double x, double y) { return __double_as_longlong(x) == __double_as_longlong(y) || (x != x && y != y); };
+    auto same32 = [](float x, float y) { return __float_as_uint(x) == __float_as_uint(y) || (x != x && y != y); };
+    if (!same64(jl_min(Num<F64>(a), Num<F64>(b)).v, jl_min_generic(Num<F64>(a), Num<F64>(b)).v)) ++bad;
+    if (!same64(min_nonnan(Num<F64>(a), Num<F64>(b)).v, min_nonnan_generic(Num<F64>(a), Num<F64>(b)).v)) ++bad;
+    if (!same32(jl_min(Num<F32>(af), Num<F32>(bf)).v, jl_min_generic(Num<F32>(af), Num<F32>(bf)).v)) ++bad;
+    if (!same32(min_nonnan(Num<F32>(af), Num<F32>(bf)).v, min_nonnan_generic(Num<F32>(af), Num<F32>(bf)).v)) ++bad;
+    n += 4;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+  atomicAdd(tested, n);
+}
+
 }  // namespace imc
+
+extern "C" int imc_cuda_selftest_min(int device, uint64_t seed, long long per_thread, unsigned long long* mismatches, unsigned long long* tested) {
+  using namespace imc;
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, 2 * sizeof(unsigned long long)) != cudaSuccess) return -4;
+  cudaMemset(d, 0, 2 * sizeof(unsigned long long));
+  k_selftest_min<<<148 * 4, 256>>>(seed, per_thread, d, d + 1);
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned long long h[2] = {0, 0};
+  cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (mismatches) *mismatches = h[0];
+  if (tested) *tested = h[1];
+  return e == cudaSuccess ? 0 : -3;
+}
 
 extern "C" int imc_cuda_selftest_div(int device, uint64_t seed, long long per_thread, unsigned long long* mismatches,
                                      unsigned long long* tested, float first_bad[4]) {

@@ -19,6 +19,10 @@ cases = [
     ("marshak rw f32 atomic", decks.marshak(precision="FLOAT32", n_cells=64, nonuniform=True, randomwalk="TRUE", n_input=2000, n_max=30000, dx_min=2e-4, pairwise="FALSE"), dict(tally_mode=lib.TALLY_ATOMIC)),
     ("suolson f32 fixed refill", decks.suolson(precision="FLOAT32", n_input=1500, n_max=20000), dict(tally_mode=lib.TALLY_FIXED, track_mode=lib.TRACK_REFILL)),
     ("nonuniform multiscale f32 atomic", decks.nonuniform_1d(precision="FLOAT32", n_input=2000, pairwise="FALSE"), dict(tally_mode=lib.TALLY_ATOMIC)),
+    # round 2: MC_RW under the refill schedule, the block reducer for long sequential sums, the restart point
+    ("marshak rw f32 refill fixed", decks.marshak(precision="FLOAT32", n_cells=64, nonuniform=True, randomwalk="TRUE", n_input=2000, n_max=30000, dx_min=2e-4, pairwise="FALSE"), dict(tally_mode=lib.TALLY_FIXED, track_mode=lib.TRACK_REFILL)),
+    ("suolson f16 sequential exact (seqblock)", decks.suolson(precision="FLOAT16", n_input=30000, n_max=200000, pairwise="FALSE"), dict()),
+    ("crooked f64 refill atomic", decks.crooked_pipe(precision="FLOAT64", n_input=3000, n_max=60000, cellmin=1, mesh_cells=(160, 160), pairwise="FALSE"), dict(track_mode=lib.TRACK_REFILL)),
 ]
 for name, inputs, cfg in cases:
     sim = driver.setup(inputs, g, **cfg)
@@ -26,6 +30,7 @@ for name, inputs, cfg in cases:
     sim.engine.history_enable(2)
     for _ in range(3):
         r = sim.advance()
+    sim.engine.checkpoint("save"); sim.advance(); sim.engine.checkpoint("restore"); sim.engine.checkpoint("drop")
     sim.engine.field_native("temp"); sim.engine.particles(); sim.fetch_history()
     print(name, r["transport"]["segments"], r["transport"]["variant"], r["transport"]["tally_mode"], flush=True)
 print("done")

@@ -294,6 +294,18 @@ def test_cached_reciprocal_division_is_ieee_exact(gpu_lib):
     assert n.value > 1e11 and bad.value == 0, (n.value, bad.value, list(fb))
 
 
+def test_device_min_fast_paths_match_the_generic_definition(gpu_lib):
+    """imc_num.h: Julia's NaN-propagating min (and the NaN-skipping one of imc_transport.jl:551-557) as DMNMX / FMNMX on the
+    device against the branchy generic definition, over all pairs of 16 special values (signed zeros, NaNs, infinities,
+    subnormals, extremes) and random bit patterns, Float64 and Float32."""
+    import ctypes as C
+    f = gpu_lib.dll.imc_cuda_selftest_min
+    f.argtypes = [C.c_int, C.c_uint64, C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    bad, n = C.c_ulonglong(), C.c_ulonglong()
+    assert f(0, 20261018, 20000, C.byref(bad), C.byref(n)) == 0
+    assert n.value > 1e10 and bad.value == 0, (n.value, bad.value)
+
+
 @pytest.mark.parametrize("deck,precision", [("suolson", "FLOAT16"), ("suolson", "FLOAT64"), ("crooked", "FLOAT32")])
 def test_engine_side_history_on_gpu(gpu_lib, deck, precision):
     """imc_history_* on the device: snapshots recorded at the end of every tally equal the per-step downloads."""
