@@ -854,7 +854,9 @@ __device__ __forceinline__ int seg1d(const TrackArgs<P>& a, Hist1<P>& h, D& d, T
   d.next_segment(a.rng, seg);
   const CellProp1<P> cp = a.m.cp1[h.cell];
   const N w(P::unpack(cp.w)), dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
-  N dist_b = h.mu > zero ? (w - h.x) / h.mu : nabs(h.x / h.mu);                     // :77-83
+  const bool fwd = h.mu > zero;
+  const N qb = (fwd ? w - h.x : h.x) / h.mu;
+  N dist_b = fwd ? qb : nabs(qb);                                                   // :77-83
   N dist_col = d.randexp(seg) / sig_col;                                            // :87
   N dist_cen = (c_light * (dt - h.t)) * ds;                                         // :89
   N dist = jl_min(jl_min(dist_b, dist_col), dist_cen);                              // :92
@@ -1154,10 +1156,16 @@ struct DynD {
   static __device__ __forceinline__ DynD w(double x) { DynD r; r.v = x; r.wide = true; return r; }
   __device__ __forceinline__ Num<P> narrow() const { return Num<P>::from_d(v); }
 };
+// One code path for both cases (the lanes of a warp hold first-segment histories, still of type T, next to later ones that are
+// Float64 already): the operation is done in Float64 and the result rounded to T when both operands are T.  For + - * / of two
+// T values that equals T's own operation — a binary64 intermediate has more than 2p + 2 digits for p = 24 (and Float16 operations
+// are Float32 operations rounded once more, as in Julia), so the second rounding is innocuous.
 #define IMC_DYN_OP(name, op)                                                                         \
   template <class P> __device__ __forceinline__ DynD<P> name(DynD<P> a, DynD<P> b) {                \
-    if (a.wide || b.wide) return DynD<P>::w(a.v op b.v);                                            \
-    return DynD<P>(a.narrow() op b.narrow());                                                        \
+    DynD<P> r; r.wide = a.wide || b.wide;                                                           \
+    const double v = a.v op b.v;                                                                    \
+    if constexpr (P::id == 2) r.v = v; else r.v = r.wide ? v : (double)P::rnd((float)v);            \
+    return r;                                                                                       \
   }
 IMC_DYN_OP(dyn_add, +)
 IMC_DYN_OP(dyn_sub, -)
@@ -1280,7 +1288,9 @@ __device__ __forceinline__ int seg_rw(const TrackArgs<P>& a, HistRW<P>& h, Dr& d
   ++h.nseg;                                                                         // :265
   const CellProp1<P> cp = a.m.cp1[h.cell];
   const N dx(P::unpack(cp.dx)), sig_col(P::unpack(cp.sig_col)), neg_saf(P::unpack(cp.neg_saf));
-  const D dist_b = h.mu > zero ? dyn_div(dyn_sub(D(dx), h.x), D(h.mu)) : dyn_abs(dyn_div(h.x, D(h.mu)));   // :269-275 (no distancescale)
+  const bool fwd = h.mu > zero;
+  const D qb = dyn_div(fwd ? dyn_sub(D(dx), h.x) : h.x, D(h.mu));
+  const D dist_b = fwd ? qb : dyn_abs(qb);                                          // :269-275 (no distancescale)
   const double rex = d.randexp64(a.rng);
   const D dist_col = D::w((rex < 0 ? -rex : rex) / sig_col.d());                    // :279 (Float64)
   const D dist_cen = dyn_mul(D(c_light), dyn_sub(D(dt), h.t));                      // :281
