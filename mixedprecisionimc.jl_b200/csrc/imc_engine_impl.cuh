@@ -713,15 +713,7 @@ struct EngineT : EngineBase {
       a.timeline = timeline.p;
     }
     a.refill_min = refill_min_env();
-    {   // visiting order of the dynamic schedule's queue (k_track_refill)
-      static const long long want = getenv("IMC_QUEUE_MULT") ? atoll(getenv("IMC_QUEUE_MULT")) : 1;
-      a.queue_chunks = (unsigned long long)((n_part + QUEUE_CHUNK - 1) / QUEUE_CHUNK);
-      auto gcd = [](unsigned long long x, unsigned long long y) { while (y) { unsigned long long t = x % y; x = y; y = t; } return x; };
-      unsigned long long mult = a.queue_chunks > 1 ? (unsigned long long)std::max<long long>(want, 1) % a.queue_chunks : 1ull;
-      if (mult == 0) mult = 1;
-      while (mult > 1 && gcd(mult, a.queue_chunks) != 1) { if (++mult >= a.queue_chunks) mult = 1; }
-      a.queue_mult = mult;
-    }
+    a.queue_chunks = (unsigned long long)((n_part + QUEUE_CHUNK - 1) / QUEUE_CHUNK);   // tickets of the dynamic schedule's queue (k_track_refill)
     if (n_part > 0) {
       int blocks_per_sm = 2048 / TRACK_THREADS;
       if (smem > 0) blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(blocks_per_sm, (200 * 1024) / (smem + COUNTER_SMEM_BYTES)));

@@ -797,7 +797,7 @@ struct TrackArgs {
   unsigned* ev_extra;         // [n] extra-stream words consumed so far
   // dynamic schedule
   unsigned long long* queue;  // next unclaimed chunk ticket
-  unsigned long long queue_chunks, queue_mult;   // chunks of QUEUE_CHUNK particles; ticket -> chunk multiplier (coprime to queue_chunks)
+  unsigned long long queue_chunks;   // chunks of QUEUE_CHUNK particles in the list
   int refill_min;             // refill when at least this many lanes of a warp are idle
   // optional timeline of the dynamic schedule (IMC_TRACK_TIMING=1): [0] first block start, [1] first time a warp found the
   // queue empty, [2] last block exit (globaltimer ns)
@@ -1405,6 +1405,8 @@ __global__ void __launch_bounds__(TRACK_THREADS, (GEOM == 3 ? 3 : track_min_bloc
   int st = ST_EMPTY;
   bool drained = false;
   long long cbase = 0; int crem = 0;   // the warp's chunk of the particle list: next index, particles left (warp-uniform)
+  unsigned long long tnext = 0;        // lane 0: the ticket claimed ahead
+  if (lane == 0) tnext = atomicAdd(a.queue, 1ull);
   if (a.timeline && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); atomicMin(a.timeline, t); }
   Hist1<P> h1; Hist2<P> h2; HistRW<P> hr; Dr d;   // the two that GEOM does not use are never touched
   while (true) {
@@ -1417,17 +1419,17 @@ __global__ void __launch_bounds__(TRACK_THREADS, (GEOM == 3 ? 3 : track_min_bloc
       }
       if (!drained) {
         // the warp works through a private chunk of QUEUE_CHUNK consecutive particles (coalesced loads) and claims the
-        // next one with a ticket from the global queue; chunk = ticket * queue_mult mod n_chunks visits the particle
-        // list in a scattered order (queue_mult coprime to n_chunks; 1 = list order)
+        // next one with a ticket from the global queue.  The ticket for the chunk AFTER the next is requested at once
+        // (lane 0 keeps it), so the latency of the atomic is covered by a whole chunk of tracking.
         if (crem == 0) {
-          unsigned long long t = 0;
-          if (lane == 0) t = atomicAdd(a.queue, 1ull);
+          unsigned long long t = tnext;
+          if (lane == 0) tnext = atomicAdd(a.queue, 1ull);
           t = __shfl_sync(IMC_FULL_MASK, t, 0);
           if (t >= a.queue_chunks) {
             if (a.timeline && lane == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tt)); atomicMin(a.timeline + 1, tt); }
             drained = true;
           } else {
-            cbase = (long long)((t * a.queue_mult) % a.queue_chunks) * QUEUE_CHUNK;
+            cbase = (long long)t * QUEUE_CHUNK;
             crem = (int)min((long long)QUEUE_CHUNK, a.n - cbase);
           }
         }
