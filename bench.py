@@ -381,11 +381,30 @@ def main():
     tdt = {np.float16: torch.float16, np.float32: torch.float32, np.float64: torch.float64}
     pin = {k: torch.empty(nc, dtype=tdt[sim_dt[k]]).pin_memory().numpy() for k in sim_dt}
 
+    dev_state = {}
+
     def step_e2e():
-        eng.set_state_native(temp=pin["temp"], matenergydens=pin["matenergydens"], radenergydens=pin["radenergydens"])  # H2D
+        if world == 1:
+            eng.set_state_native(temp=pin["temp"], matenergydens=pin["matenergydens"], radenergydens=pin["radenergydens"])  # H2D
+            r = step_resident()
+            for k in pin:                                                                                                   # D2H
+                eng.field_native(k, out=pin[k])
+            return r
+        # N GPUs: the per-cell state is replicated, so it crosses PCIe ONCE (rank 0, from pinned memory), is broadcast over
+        # NVLink, and every engine takes it from device memory; rank 0 alone reads the step's result back
+        for k in pin:
+            t = dev_state.get(k)
+            if t is None or t.dtype != tdt[pin[k].dtype.type]:
+                t = dev_state[k] = torch.empty(nc, dtype=tdt[pin[k].dtype.type], device=dev)
+            if rank == 0:
+                t.copy_(torch.from_numpy(pin[k]), non_blocking=True)                                                        # H2D
+            dist.broadcast(t, src=0)
+        torch.cuda.current_stream().synchronize()
+        eng.set_state_native(temp=dev_state["temp"], matenergydens=dev_state["matenergydens"], radenergydens=dev_state["radenergydens"])
         r = step_resident()
-        for k in pin:                                                                                                   # D2H
-            eng.field_native(k, out=pin[k])
+        if rank == 0:
+            for k in pin:                                                                                                   # D2H
+                eng.field_native(k, out=pin[k])
         return r
 
     import copy
@@ -485,7 +504,8 @@ def main():
                     "ms_per_step": 1e3 * wall_e_g / args.steps, "host_wall_ms_per_step": 1e3 * host_wall_e_g / args.steps,
                     "segments_per_step": seg_e_g / args.steps,
                     "path": "imc_set_state_native (pinned Array{T} -> device) + the step + imc_get_field_native x3 (device -> pinned Array{T}); "
-                            "the same K time steps as `value`, restarted from imc_checkpoint"},
+                            "the same K time steps as `value`, restarted from imc_checkpoint"
+                            + ("; N > 1: the replicated state crosses PCIe once on rank 0 and is broadcast over NVLink, rank 0 reads the result" if world > 1 else "")},
             "gpu_launches": launches, "schedule_per_step": variants,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic_from_profile(args.workload, mesh, particles, seg / max(args.steps, 1)),
                          "traffic_source": "profiles/traffic.json: dram__bytes of the committed ncu capture of this kernel, scaled by segments per launch",

@@ -221,7 +221,9 @@ int imc_set_state(imc_handle h, const double* temp, const double* matenergydens,
  * the shim passes pointer(mesh.x) straight through.  imc_field_elsize returns the element size in bytes:
  * sizeof(T) (2 / 4 / 8) for every field except IMC_FIELD_TEMP, which is 8 once the reference's mesh.temp has
  * turned Float64 (after the first LINEARIZED tally, imc_tally.jl:72) and sizeof(T) before.
- * `bytes` must equal n_elements * elsize.  Host buffers may be pageable or pinned. */
+ * `bytes` must equal n_elements * elsize.  The caller's buffers may be pageable or pinned host memory, or device memory of
+ * this process (the copies use unified addressing): a multi-GPU host uploads the replicated state once, broadcasts it over
+ * NVLink and hands every engine a device pointer (bench.py does for its end-to-end loop). */
 int32_t imc_field_elsize(imc_handle h, int32_t field);
 int imc_get_field_native(imc_handle h, int32_t field, void* dst, int64_t bytes);
 int imc_set_state_native(imc_handle h, const void* temp, const void* matenergydens, const void* radenergydens);

@@ -1010,11 +1010,11 @@ struct EngineT : EngineBase {
     IMC_RC(use_device());
     if (f == IMC_FIELD_TEMP) {
       if (bytes != nc * field_elsize(f)) { err = "get_field_native: size"; return IMC_ERR_ARG; }
-      if (temp_wide) IMC_CK(cudaMemcpyAsync(dst, temp.p, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+      if (temp_wide) IMC_CK(cudaMemcpyAsync(dst, temp.p, (size_t)bytes, cudaMemcpyDefault, stream));
       else {
         IMC_CK(stage_t.ensure((size_t)nc));
         k_from_f64<P><<<grid_for(nc, 256), 256, 0, stream>>>(temp.p, nc, stage_t.p); ++n_launch;
-        IMC_CK(cudaMemcpyAsync(dst, stage_t.p, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+        IMC_CK(cudaMemcpyAsync(dst, stage_t.p, (size_t)bytes, cudaMemcpyDefault, stream));
       }
       IMC_CK(cudaStreamSynchronize(stream));
       return IMC_OK;
@@ -1023,7 +1023,7 @@ struct EngineT : EngineBase {
     const S* src = field_ptr(f, &len);
     if (!src) { err = "get_field_native: unknown field"; return IMC_ERR_ARG; }
     if (bytes != len * (long long)sizeof(S)) { err = "get_field_native: size"; return IMC_ERR_ARG; }
-    IMC_CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, stream));
+    IMC_CK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, stream));
     IMC_CK(cudaStreamSynchronize(stream));
     return IMC_OK;
   }
@@ -1031,15 +1031,15 @@ struct EngineT : EngineBase {
     if (!have_mesh) { err = "set_state before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     if (temp_) {
-      if (temp_wide) IMC_CK(cudaMemcpyAsync(temp.p, temp_, nc * sizeof(double), cudaMemcpyHostToDevice, stream));
+      if (temp_wide) IMC_CK(cudaMemcpyAsync(temp.p, temp_, nc * sizeof(double), cudaMemcpyDefault, stream));
       else {
         IMC_CK(stage_t.ensure((size_t)nc));
-        IMC_CK(cudaMemcpyAsync(stage_t.p, temp_, nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+        IMC_CK(cudaMemcpyAsync(stage_t.p, temp_, nc * sizeof(S), cudaMemcpyDefault, stream));
         k_to_f64<P><<<grid_for(nc, 256), 256, 0, stream>>>(stage_t.p, nc, temp.p); ++n_launch;
       }
     }
-    if (mat) IMC_CK(cudaMemcpyAsync(matenergydens.p, mat, nc * sizeof(S), cudaMemcpyHostToDevice, stream));
-    if (rad) IMC_CK(cudaMemcpyAsync(radenergydens.p, rad, nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+    if (mat) IMC_CK(cudaMemcpyAsync(matenergydens.p, mat, nc * sizeof(S), cudaMemcpyDefault, stream));
+    if (rad) IMC_CK(cudaMemcpyAsync(radenergydens.p, rad, nc * sizeof(S), cudaMemcpyDefault, stream));
     IMC_CK(cudaGetLastError());
     IMC_CK(cudaStreamSynchronize(stream));
     return IMC_OK;

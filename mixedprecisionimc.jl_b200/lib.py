@@ -362,9 +362,14 @@ class Engine:
         return out
 
     def set_state_native(self, temp=None, matenergydens=None, radenergydens=None):
+        """Upload fields in their own element type.  Each argument is a flat numpy array (host memory, pinned or not) or a
+        contiguous torch tensor (host or CUDA memory of this process: the engine copies with unified addressing)."""
         def ptr(a, name):
             if a is None:
                 return None
+            if hasattr(a, "data_ptr"):      # torch tensor
+                assert a.numel() == self.nc and a.element_size() == np.dtype(self.field_dtype(name)).itemsize and a.is_contiguous(), name
+                return C.c_void_p(a.data_ptr())
             assert a.size == self.nc and a.dtype == self.field_dtype(name) and a.flags["C_CONTIGUOUS"], name
             return a.ctypes.data_as(C.c_void_p)
         self._check(self.lib.dll.imc_set_state_native(self._h, ptr(temp, "temp"), ptr(matenergydens, "matenergydens"),
