@@ -581,8 +581,21 @@ struct EngineT : EngineBase {
     IMC_CK(cudaGetLastError());
     return IMC_OK;
   }
-  // event-based schedule: one segment per launch, survivors compacted into the next launch's index list
+  template <int TK>
+  void launch_event_tk(TrackArgs<P>& a, unsigned grid, size_t smem, long long n_active, int first) {
+    if (geom == 1) k_track_event<P, 1, TK><<<grid, TRACK_THREADS, smem, stream>>>(a, n_active, first);
+    else k_track_event<P, 2, TK><<<grid, TRACK_THREADS, smem, stream>>>(a, n_active, first);
+  }
+  void launch_event_kernel(TrackArgs<P>& a, unsigned grid, size_t smem, long long n_active, int first) {
+    if (a.tally.mode == IMC_TALLY_ATOMIC && !a.tally.use_smem) launch_event_tk<TK_ATOMIC_G>(a, grid, smem, n_active, first);
+    else if (a.tally.mode == IMC_TALLY_ATOMIC) launch_event_tk<TK_ATOMIC_S>(a, grid, smem, n_active, first);
+    else if (a.tally.mode == IMC_TALLY_FIXED && !a.tally.use_smem) launch_event_tk<TK_FIXED_G>(a, grid, smem, n_active, first);
+    else launch_event_tk<TK_FIXED_S>(a, grid, smem, n_active, first);
+  }
+  // event-based schedule: ev_batch segments per particle per launch, survivors compacted into the next launch's index list
   int launch_event(TrackArgs<P>& a, size_t smem) {
+    static const int batch_env = getenv("IMC_EVENT_BATCH") ? atoi(getenv("IMC_EVENT_BATCH")) : 64;
+    a.ev_batch = batch_env < 1 ? 1 : batch_env;
     IMC_CK(ev_list[0].ensure((size_t)n_part)); IMC_CK(ev_list[1].ensure((size_t)n_part));
     IMC_CK(ev_nseg.ensure((size_t)n_part)); IMC_CK(ev_extra.ensure((size_t)n_part)); IMC_CK(ev_count.ensure(1));
     a.ev_nseg = ev_nseg.p; a.ev_extra = ev_extra.p; a.ev_count = ev_count.p;
@@ -594,8 +607,7 @@ struct EngineT : EngineBase {
       a.ev_out = ev_list[(it + 1) & 1].p;
       IMC_CK(cudaMemsetAsync(ev_count.p, 0, sizeof(unsigned long long), stream));
       unsigned grid = (unsigned)std::min<long long>((n_active + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * IMC_TRACK_MIN_BLOCKS);
-      if (geom == 1) k_track_event<P, 1><<<grid, TRACK_THREADS, smem, stream>>>(a, n_active, it == 0);
-      else k_track_event<P, 2><<<grid, TRACK_THREADS, smem, stream>>>(a, n_active, it == 0);
+      launch_event_kernel(a, grid, smem, n_active, it == 0);
       ++n_launch; ++it;
       IMC_CK(cudaGetLastError());
       unsigned long long cnt = 0;
@@ -684,10 +696,10 @@ struct EngineT : EngineBase {
     if (variant == IMC_TRACK_EVENT && !event_ok) variant = IMC_TRACK_AUTO;
     if (variant == IMC_TRACK_AUTO) {
       // measured selection: the two history schedules are probed on the first two calls and re-probed every
-      // 32 calls; the fastest known variant runs in between.  The event-based variant joins the probe only when
-      // IMC_AUTO_PROBE_EVENT=1: measured on B200 it is 17x (Su-Olson) to 40x (crooked pipe) slower, because the
-      // last few long histories need thousands of nearly empty launches.
-      static const bool probe_event = getenv("IMC_AUTO_PROBE_EVENT") && atoi(getenv("IMC_AUTO_PROBE_EVENT")) != 0;
+      // 32 / 256 calls; the event-based schedule (64 segments per particle per launch, survivors compacted) is probed once,
+      // on the third call (IMC_AUTO_PROBE_EVENT=0 skips it).  Measured on B200: crooked pipe refill 73 ms, event 98 ms,
+      // static 130 ms; Su-Olson static 2.6 ms, event 2.8 ms.  The fastest known variant runs in between.
+      static const bool probe_event = !(getenv("IMC_AUTO_PROBE_EVENT") && atoi(getenv("IMC_AUTO_PROBE_EVENT")) == 0);
       // the losing schedule is re-measured every 32 calls while it is within 30 % of the winner, every 256 calls otherwise
       // (a lost probe costs one slow step: static is 1.7-2x slower than refill on the crooked pipe)
       const bool close = rate_static > 0 && rate_refill > 0 && std::min(rate_static, rate_refill) > 0.7 * std::max(rate_static, rate_refill);

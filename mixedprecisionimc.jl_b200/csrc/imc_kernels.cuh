@@ -795,6 +795,7 @@ struct TrackArgs {
   unsigned long long* ev_count;  // [0] = entries written to ev_out
   int* ev_nseg;               // [n] segments tracked so far
   unsigned* ev_extra;         // [n] extra-stream words consumed so far
+  int ev_batch;               // segments per particle per launch
   // dynamic schedule
   unsigned long long* queue;  // next unclaimed chunk ticket
   unsigned long long queue_chunks;   // chunks of QUEUE_CHUNK particles in the list
@@ -1089,17 +1090,21 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track2
   cn.commit<TK>(a.tally);
 }
 
-// ---- event-based schedule: every launch advances each in-flight particle by ONE segment -----------------
-// State is re-read and re-written every segment (B_hist per segment instead of per history) and the direction
-// vector / Philox block are recomputed, in exchange for warps whose lanes all do the same amount of work.
-// Survivors are appended to the next launch's index list with one warp-aggregated atomic.  Philox only (the
-// replay tape has per-particle cursors); EXACT tallies use the history schedules.
-template <class P, int GEOM>
+// ---- event-based schedule: every launch advances each in-flight particle by up to `ev_batch` segments ----------
+// A launch loads the state of every particle still in flight, tracks it until it ends or has done ev_batch segments,
+// writes the state of the unfinished ones back and appends them to the next launch's index list with one warp-aggregated
+// atomic (stream compaction by event: the next launch starts with full warps again).  The price against the
+// history schedules is B_hist per ev_batch segments instead of per history, the direction vector and the Philox block
+// recomputed at every reload, and one launch + one count read-back per batch; ev_batch = 1 is the textbook
+// one-segment-per-launch form (17-40x slower here: the longest histories need thousands of nearly empty launches).
+// Philox only (the replay tape has per-particle cursors); EXACT tallies use the history schedules.
+template <class P, int GEOM, int TK>
 __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_event(TrackArgs<P> a, long long n_active, int first) {
   extern __shared__ __align__(16) unsigned char smem[];
   Counters cn; cn.init(reinterpret_cast<unsigned long long*>(smem));
-  Tally<P> tal(a.tally, smem + COUNTER_SMEM_BYTES);
+  Tally<P, TK> tal(a.tally, smem + COUNTER_SMEM_BYTES);
   tal.zero();
+  using Dr = HistDraw<P, false>;
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n_round = (n_active + 31) & ~31ll;
@@ -1108,22 +1113,22 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_
     long long pi = 0;
     if (i < n_active) {
       pi = a.ev_in ? (long long)a.ev_in[i] : i;
-      Hist1<P> h1; Hist2<P> h2; HistDraw<P, false> d;
+      Hist1<P> h1; Hist2<P> h2; Dr d;
       bool ok;
-      if constexpr (GEOM == 1) ok = load1d<P, HistDraw<P, false>, TK_RUNTIME>(a, pi, h1, d, cn); else ok = load2d<P, HistDraw<P, false>, TK_RUNTIME>(a, pi, h2, d, cn);
+      if constexpr (GEOM == 1) ok = load1d<P, Dr, TK>(a, pi, h1, d, cn); else ok = load2d<P, Dr, TK>(a, pi, h2, d, cn);
       if (ok) {
         const int done = first ? 0 : a.ev_nseg[pi];
         if (!first) d.resume(a.p.id[pi], (unsigned)done, a.ev_extra[pi]);
-        int ev;
+        int ev = -1;
         if constexpr (GEOM == 1) {
           h1.nseg = done;
-          ev = seg1d(a, h1, d, tal, cn);
-          if (ev >= 0) store1d<P, HistDraw<P, false>, TK_RUNTIME>(a, h1, d, ev, cn);
+          for (int k = 0; k < a.ev_batch && ev < 0; ++k) ev = seg1d(a, h1, d, tal, cn);
+          if (ev >= 0) store1d<P, Dr, TK>(a, h1, d, ev, cn);
           else { h1.t.store(a.p.t, pi); h1.x.store(a.p.x, pi); h1.mu.store(a.p.mu, pi); h1.E.store(a.p.E, pi); a.p.cx[pi] = h1.cell; a.ev_nseg[pi] = h1.nseg; }
         } else {
           h2.nseg = done;
-          ev = seg2d(a, h2, d, tal, cn);
-          if (ev >= 0) store2d<P, HistDraw<P, false>, TK_RUNTIME>(a, h2, d, ev, cn);
+          for (int k = 0; k < a.ev_batch && ev < 0; ++k) ev = seg2d(a, h2, d, tal, cn);
+          if (ev >= 0) store2d<P, Dr, TK>(a, h2, d, ev, cn);
           else { h2.t.store(a.p.t, pi); h2.x.store(a.p.x, pi); h2.y.store(a.p.y, pi); get_mu(h2, cn).store(a.p.mu, pi); h2.E.store(a.p.E, pi);
                  a.p.cx[pi] = h2.xi; a.p.cy[pi] = h2.yi; a.ev_nseg[pi] = h2.nseg; }
         }
@@ -1139,7 +1144,7 @@ __global__ void __launch_bounds__(TRACK_THREADS, track_min_blocks<P>()) k_track_
     }
   }
   tal.flush();
-  cn.commit(a.tally);
+  cn.commit<TK>(a.tally);
 }
 
 // ======================================================================================
