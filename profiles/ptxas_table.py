@@ -1,8 +1,8 @@
 """Turns `nvcc -Xptxas -v` logs (one per precision translation unit) into the register / spill / shared-memory table of
-profiles/r1_ptxas.md.
+profiles/r2_ptxas.md.
 
     for p in f16 f32 f64; do nvcc <the flags of __graft_entry__.NVCC_FLAGS> -Xptxas -v -c mixedprecisionimc.jl_b200/csrc/imc_engine_$p.cu -o /dev/null 2> build/ptxas_$p.log; done
-    python profiles/ptxas_table.py build/ptxas_f16.log build/ptxas_f32.log build/ptxas_f64.log > profiles/r1_ptxas.md
+    python profiles/ptxas_table.py build/ptxas_f16.log build/ptxas_f32.log build/ptxas_f64.log > profiles/r2_ptxas.md
 """
 import re
 import subprocess
