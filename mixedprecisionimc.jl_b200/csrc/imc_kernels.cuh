@@ -1710,6 +1710,28 @@ __global__ void __launch_bounds__(EXACT_BLOCK_THREADS) k_exact_reduce_block(cons
     if (!exact_block_segment(len, 1)) continue;
     const int depth = jl_sum_depth_dev(len);
     const int slots = 1 << depth;
+    if (slots >= EXACT_BLOCK_THREADS / 8) {
+      // many leaves (>= 128: 10^5 records and more in this cell): one THREAD per leaf.  Each leaf is summed left to right as the
+      // recursion does, the leaves are independent chains, and 1024 of them run at once; a warp per leaf (below) walks one
+      // chain with 32 lanes in lockstep, 40 cycles per record (census of the 10^8-particle Su-Olson deck: 3.5 ms vs 0.3 ms).
+      // A thread's loads are 8 bytes at an 8 KB stride; the 32-byte sectors it pulls stay in L1 for its next three records.
+      for (int slot = threadIdx.x; slot < slots; slot += blockDim.x) {
+        long long first = 0, last = len - 1;
+        int d = 0; bool mine = true;
+        while (last - first >= 1024) {
+          const long long mid = first + ((last - first) >> 1);
+          if ((slot >> (depth - 1 - d)) & 1) first = mid + 1; else last = mid;
+          ++d;
+        }
+        if (d < depth && (slot & ((1 << (depth - d)) - 1)) != 0) mine = false;
+        if (mine) {
+          N v = N::from_d(vals[b + first]);
+          for (long long i = b + first + 1; i <= b + last; ++i) v = v + N::from_d(vals[i]);
+          part[slot] = v.v;
+        }
+        valid[slot] = mine ? 1 : 0;
+      }
+    } else
     for (int slot = wid; slot < slots; slot += nw) {     // walk from the root to this slot's leaf (uniform in the warp)
       long long first = 0, last = len - 1;
       int d = 0; bool mine = true;
