@@ -185,7 +185,10 @@ struct EngineT : EngineBase {
   DBuf<double> dgather;
   GatherList gl{};
   void gl_reset() { gl.count = 0; }
-  int gl_add(const void* p, int kind) { gl.p[gl.count] = p; gl.kind[gl.count] = kind; return gl.count++; }
+  int gl_add(const void* p, int kind) {
+    if (gl.count >= GATHER_MAX) return -1;   // callers request at most 6 + IMC_MAX_SCALES values
+    gl.p[gl.count] = p; gl.kind[gl.count] = kind; return gl.count++;
+  }
   int gl_read() {   // results in hpin[0 .. count)
     if (!hpin) { IMC_CK(cudaMallocHost((void**)&hpin, GATHER_MAX * sizeof(double))); IMC_CK(dgather.alloc(GATHER_MAX)); }
     k_gather_scalars<P><<<1, GATHER_MAX, 0, stream>>>(gl, dgather.p); ++n_launch;
