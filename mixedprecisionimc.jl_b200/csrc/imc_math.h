@@ -105,12 +105,37 @@ IMC_HD float scale_f(float p, int n) {
   return (p * pow2_f(n1)) * pow2_f(n2);
 }
 
+// Coefficient tables of the double-precision polynomials.  On sm_100a a 64-bit literal operand costs two UMOVs at every use
+// (DFMA takes no 64-bit immediate and no constant-bank operand), i.e. a Horner step is three issue slots instead of one;
+// from a __constant__ table two coefficients arrive per LDCU.128.  The host side (and the CPU oracle) reads the same
+// values from a plain array: the initialisers are the same constant expressions, so both sides hold the same bits.
+#if defined(__CUDACC__)
+#define IMC_DTAB(name, n, ...) static __constant__ double name##_c[n] = {__VA_ARGS__}; static const double name##_h[n] = {__VA_ARGS__};
+#else
+#define IMC_DTAB(name, n, ...) static const double name##_h[n] = {__VA_ARGS__};
+#endif
+#if defined(__CUDA_ARCH__)
+#define IMC_DT(name) name##_c
+#else
+#define IMC_DT(name) name##_h
+#endif
+// p = t[0]; p = fma(p, x, t[i]) for i = 1 .. N-1
+#define IMC_HORNER_D(p, x, name, N) do { p = IMC_DT(name)[0]; _Pragma("unroll") for (int i_ = 1; i_ < (N); ++i_) p = fma_d(p, x, IMC_DT(name)[i_]); } while (0)
+
 // =======================================================================================
 // double precision
 // =======================================================================================
-#define IMC_LN2_HI_D 6.93147180369123816490e-01 /* 0x3fe62e42fee00000: 32 trailing zero bits */
-#define IMC_LN2_LO_D 1.90821492927058770002e-10
-#define IMC_LOG2E_D 1.44269504088896338700e+00
+IMC_DTAB(EXPQ, 12, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5)
+IMC_DTAB(LOGP, 12, 1.0 / 25.0, 1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0)
+IMC_DTAB(SINP, 9, -1.0 / 121645100408832000.0, 1.0 / 355687428096000.0, -1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0)
+IMC_DTAB(COSP, 9, 1.0 / 2432902008176640000.0, -1.0 / 6402373705728000.0, 1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0)
+IMC_DTAB(ATANP, 22, 1.0 / 45.0, -1.0 / 43.0, 1.0 / 41.0, -1.0 / 39.0, 1.0 / 37.0, -1.0 / 35.0, 1.0 / 33.0, -1.0 / 31.0, 1.0 / 29.0, -1.0 / 27.0, 1.0 / 25.0, -1.0 / 23.0, 1.0 / 21.0, -1.0 / 19.0, 1.0 / 17.0, -1.0 / 15.0, 1.0 / 13.0, -1.0 / 11.0, 1.0 / 9.0, -1.0 / 7.0, 1.0 / 5.0, -1.0 / 3.0)
+
+// scalar constants of the range reductions, through the same tables (DK: exp / log, DS: sin / cos)
+IMC_DTAB(DK, 4, 1.44269504088896338700e+00, 6.93147180369123816490e-01 /* 0x3fe62e42fee00000: ln2 to 32 bits */, 1.90821492927058770002e-10, 0.0)
+#define IMC_LOG2E_D IMC_DT(DK)[0]
+#define IMC_LN2_HI_D IMC_DT(DK)[1]
+#define IMC_LN2_LO_D IMC_DT(DK)[2]
 
 // Shared core of exp/expm1: x = n ln2 + r, |r| <= 0.3466; returns em = expm1(r) (~0.5 ulp).
 IMC_HD double exp_core_d(double x, int* n_out) {
@@ -120,18 +145,7 @@ IMC_HD double exp_core_d(double x, int* n_out) {
   double r = hi - lo;
   double c = (hi - r) - lo;  // rounding error of r
   // q = 1/2 + r/6 + ... + r^11/13!
-  double q = 1.0 / 6227020800.0;
-  q = fma_d(q, r, 1.0 / 479001600.0);
-  q = fma_d(q, r, 1.0 / 39916800.0);
-  q = fma_d(q, r, 1.0 / 3628800.0);
-  q = fma_d(q, r, 1.0 / 362880.0);
-  q = fma_d(q, r, 1.0 / 40320.0);
-  q = fma_d(q, r, 1.0 / 5040.0);
-  q = fma_d(q, r, 1.0 / 720.0);
-  q = fma_d(q, r, 1.0 / 120.0);
-  q = fma_d(q, r, 1.0 / 24.0);
-  q = fma_d(q, r, 1.0 / 6.0);
-  q = fma_d(q, r, 0.5);
+  double q; IMC_HORNER_D(q, r, EXPQ, 12);
   double em = fma_d(r * r, q, r);
   em = fma_d(c, em, em + c);  // first-order correction: expm1(r + c) ~ em + c (1 + em)
   *n_out = (int)fn;
@@ -175,18 +189,7 @@ IMC_HD void exp_expm1_d(double x, double* e, double* em1) {
   if (!(x <= 709.0 && x >= -37.0)) { *e = exp_d(x); *em1 = expm1_d(x); return; }
   double ax = x < 0 ? -x : x;
   if (rint_d(x * IMC_LOG2E_D) == 0.0) {  // n = 0: r = x, c = 0, scale 2^0 (see exp_expm1_f)
-    double q = 1.0 / 6227020800.0;
-    q = fma_d(q, x, 1.0 / 479001600.0);
-    q = fma_d(q, x, 1.0 / 39916800.0);
-    q = fma_d(q, x, 1.0 / 3628800.0);
-    q = fma_d(q, x, 1.0 / 362880.0);
-    q = fma_d(q, x, 1.0 / 40320.0);
-    q = fma_d(q, x, 1.0 / 5040.0);
-    q = fma_d(q, x, 1.0 / 720.0);
-    q = fma_d(q, x, 1.0 / 120.0);
-    q = fma_d(q, x, 1.0 / 24.0);
-    q = fma_d(q, x, 1.0 / 6.0);
-    q = fma_d(q, x, 0.5);
+    double q; IMC_HORNER_D(q, x, EXPQ, 12);
     double em0 = fma_d(x * x, q, x);
     *e = 1.0 + em0;
     *em1 = (ax < 5.551115123125783e-17) ? x : em0;
@@ -219,18 +222,7 @@ IMC_HD double log_d(double x) {
   double s = f / (2.0 + f);
   double z = s * s;
   // R = 2 z (1/3 + z/5 + z^2/7 + ... ) : log(m) = 2 s + s R
-  double p = 1.0 / 25.0;
-  p = fma_d(p, z, 1.0 / 23.0);
-  p = fma_d(p, z, 1.0 / 21.0);
-  p = fma_d(p, z, 1.0 / 19.0);
-  p = fma_d(p, z, 1.0 / 17.0);
-  p = fma_d(p, z, 1.0 / 15.0);
-  p = fma_d(p, z, 1.0 / 13.0);
-  p = fma_d(p, z, 1.0 / 11.0);
-  p = fma_d(p, z, 1.0 / 9.0);
-  p = fma_d(p, z, 1.0 / 7.0);
-  p = fma_d(p, z, 1.0 / 5.0);
-  p = fma_d(p, z, 1.0 / 3.0);
+  double p; IMC_HORNER_D(p, z, LOGP, 12);
   double R = 2.0 * (z * p);
   double hfsq = 0.5 * f * f;
   double dk = (double)e;
@@ -238,36 +230,22 @@ IMC_HD double log_d(double x) {
   return fma_d(s, hfsq + R, dk * IMC_LN2_LO_D) - hfsq + f + dk * IMC_LN2_HI_D;
 }
 
-#define IMC_PIO2_1_D 1.57079632673412561417e+00 /* first 33 bits of pi/2 */
-#define IMC_PIO2_2_D 6.07710050630396597660e-11 /* next 33 bits */
-#define IMC_PIO2_3_D 2.02226624871116645580e-21 /* next 33 bits */
-#define IMC_PIO2_4_D 8.47842766036889956997e-32 /* tail */
-#define IMC_2OPI_D 6.36619772367581382433e-01
+IMC_DTAB(DS, 6, 6.36619772367581382433e-01 /* 2/pi */, 1.57079632673412561417e+00 /* first 33 bits of pi/2 */, 6.07710050630396597660e-11 /* next 33 bits */,
+         2.02226624871116645580e-21 /* next 33 bits */, 8.47842766036889956997e-32 /* tail */, 0.0)
+#define IMC_2OPI_D IMC_DT(DS)[0]
+#define IMC_PIO2_1_D IMC_DT(DS)[1]
+#define IMC_PIO2_2_D IMC_DT(DS)[2]
+#define IMC_PIO2_3_D IMC_DT(DS)[3]
+#define IMC_PIO2_4_D IMC_DT(DS)[4]
 
 IMC_HD double sin_kernel_d(double r) {
   double z = r * r;
-  double p = -1.0 / 121645100408832000.0;  // -1/19!
-  p = fma_d(p, z, 1.0 / 355687428096000.0);
-  p = fma_d(p, z, -1.0 / 1307674368000.0);
-  p = fma_d(p, z, 1.0 / 6227020800.0);
-  p = fma_d(p, z, -1.0 / 39916800.0);
-  p = fma_d(p, z, 1.0 / 362880.0);
-  p = fma_d(p, z, -1.0 / 5040.0);
-  p = fma_d(p, z, 1.0 / 120.0);
-  p = fma_d(p, z, -1.0 / 6.0);
+  double p; IMC_HORNER_D(p, z, SINP, 9);
   return fma_d(r * z, p, r);
 }
 IMC_HD double cos_kernel_d(double r) {
   double z = r * r;
-  double p = 1.0 / 2432902008176640000.0;  // 1/20!
-  p = fma_d(p, z, -1.0 / 6402373705728000.0);
-  p = fma_d(p, z, 1.0 / 20922789888000.0);
-  p = fma_d(p, z, -1.0 / 87178291200.0);
-  p = fma_d(p, z, 1.0 / 479001600.0);
-  p = fma_d(p, z, -1.0 / 3628800.0);
-  p = fma_d(p, z, 1.0 / 40320.0);
-  p = fma_d(p, z, -1.0 / 720.0);
-  p = fma_d(p, z, 1.0 / 24.0);
+  double p; IMC_HORNER_D(p, z, COSP, 9);
   double hz = 0.5 * z;
   double w = 1.0 - hz;
   return w + (((1.0 - w) - hz) + (z * z) * p);
@@ -297,8 +275,9 @@ IMC_HD void sincos_d(double x, double* s, double* c) {
 
 #define IMC_PI_HI_D 3.14159265358979311600e+00
 #define IMC_PI_LO_D 1.22464679914735317723e-16
-#define IMC_PIO2_HI_D 1.57079632679489655800e+00
-#define IMC_PIO2_LO_D 6.12323399573676603587e-17
+IMC_DTAB(DH, 2, 1.57079632679489655800e+00, 6.12323399573676603587e-17)   // pi/2 = hi + lo
+#define IMC_PIO2_HI_D IMC_DT(DH)[0]
+#define IMC_PIO2_LO_D IMC_DT(DH)[1]
 #define IMC_PIO4_HI_D 7.85398163397448278999e-01
 #define IMC_PIO4_LO_D 3.06161699786838301793e-17
 
@@ -311,28 +290,7 @@ IMC_HD double atan01_d(double t) {
     base_lo = IMC_PIO4_LO_D;
   }
   double z = u * u;
-  double p = 1.0 / 45.0;
-  p = fma_d(p, z, -1.0 / 43.0);
-  p = fma_d(p, z, 1.0 / 41.0);
-  p = fma_d(p, z, -1.0 / 39.0);
-  p = fma_d(p, z, 1.0 / 37.0);
-  p = fma_d(p, z, -1.0 / 35.0);
-  p = fma_d(p, z, 1.0 / 33.0);
-  p = fma_d(p, z, -1.0 / 31.0);
-  p = fma_d(p, z, 1.0 / 29.0);
-  p = fma_d(p, z, -1.0 / 27.0);
-  p = fma_d(p, z, 1.0 / 25.0);
-  p = fma_d(p, z, -1.0 / 23.0);
-  p = fma_d(p, z, 1.0 / 21.0);
-  p = fma_d(p, z, -1.0 / 19.0);
-  p = fma_d(p, z, 1.0 / 17.0);
-  p = fma_d(p, z, -1.0 / 15.0);
-  p = fma_d(p, z, 1.0 / 13.0);
-  p = fma_d(p, z, -1.0 / 11.0);
-  p = fma_d(p, z, 1.0 / 9.0);
-  p = fma_d(p, z, -1.0 / 7.0);
-  p = fma_d(p, z, 1.0 / 5.0);
-  p = fma_d(p, z, -1.0 / 3.0);
+  double p; IMC_HORNER_D(p, z, ATANP, 22);
   double a = fma_d(u * z, p, u);  // atan(u)
   return base_hi + (a + base_lo);
 }
@@ -567,8 +525,8 @@ IMC_HD void sincos_f(float x, float* s, float* c) {
   if (!(x - x == 0.0f)) { *s = x - x; *c = x - x; return; }
   float fq = rint_f(x * 0.636619772367581382433f);
   // reduce in double: exact enough for any float x of moderate size, one rounding to float
-  double rd = fma_d((double)fq, -1.57079632679489655800e+00, (double)x);
-  rd = fma_d((double)fq, -6.12323399573676603587e-17, rd);
+  double rd = fma_d((double)fq, -IMC_PIO2_HI_D, (double)x);
+  rd = fma_d((double)fq, -IMC_PIO2_LO_D, rd);
   float r = (float)rd;
   float lo = (float)(rd - (double)r);
   int q = (int)fq & 3;
