@@ -183,7 +183,10 @@ int imc_source(imc_handle h, double dt, int64_t n_input, double cellmin, int64_t
 /* Transport.MC / MC_RW / MC2D (imc_transport.jl:13-210, :212-479, :483-732). */
 int imc_transport(imc_handle h, double dt, int64_t step, imc_transport_stats* out);
 
-/* Clean.clean (imc_clean.jl:6-19): stable removal of dead particles. */
+/* Clean.clean (imc_clean.jl:6-19): stable removal of dead particles.  *n_alive = length(particles) afterwards.
+ * The CUDA engine may leave a few dead entries in its list on populations above 2^22 (they are skipped by every
+ * kernel and removed once they exceed 1/32 of the list, or before imc_get_particles); counts, order, ids and all
+ * results are those of the compacted list.  Never with replay tapes, EXACT tallies or outcome records. */
 int imc_clean(imc_handle h, int64_t* n_alive);
 
 /* Tally.tally (imc_tally.jl:11-149) = imc_tally_local (census radiation tally into the reduce

@@ -433,7 +433,7 @@ struct EngineT : EngineBase {
     }
     IMC_RC(jl_sum(s.q_em, nc * ns, sums.p + 6));
     IMC_RC(jl_flush());
-    long long n_census = n_census_global >= 0 ? n_census_global : n_part;
+    long long n_census = n_census_global >= 0 ? n_census_global : n_part - n_holes;
     int wide_counts = (P::id == 0) && (std::max<int64_t>(n_input, cfg.n_max) > 65504);
     k_src_total<P><<<1, 1, 0, stream>>>(s, L, sums.p, src_sc.p, n_input, n_census, cfg.n_max, cellmin, wide_counts); ++n_launch;
     k_src_counts<P><<<grid_for(L.total(), 256), 256, 0, stream>>>(m, s, L, src_sc.p, cellmin, wide_counts); ++n_launch;
@@ -467,10 +467,10 @@ struct EngineT : EngineBase {
       }
     }
     n_part += n_local;
-    n_global_after_source = (n_census_global >= 0 ? (long long)n_census_global : n_part - n_local) + total;
+    n_global_after_source = (n_census_global >= 0 ? (long long)n_census_global : n_part - n_local - n_holes) + total;
     if (out) {
       out->totalenergy = totalenergy; out->emitted_sum = (double)h_emsum; out->n_source = (int64_t)hsc.nsrc;
-      out->n_new_global = total; out->n_new_local = n_local; out->n_particles = n_part;
+      out->n_new_global = total; out->n_new_local = n_local; out->n_particles = n_part - n_holes;
     }
     if (hsc.bad) { err = "non-finite particle count or unrepresentable energy (reference would throw)"; return IMC_ERR_NUMERIC; }
     return IMC_OK;
@@ -684,7 +684,7 @@ struct EngineT : EngineBase {
     dep_perm = geom == 2 && tforce == 2 && mode != IMC_TALLY_EXACT && !a.tally.use_smem;
     a.m.tsx = dep_perm ? ny : 1; a.m.tsy = dep_perm ? 1 : nx;
     // outcome records for replay checks (small populations only)
-    bool record = n_part <= (1ll << 22);
+    bool record = n_part <= (1ll << 22) && n_holes == 0;   // list positions must be particle ordinals
     if (record) {
       IMC_CK(out_event.ensure((size_t)std::max<long long>(n_part, 1)));
       IMC_CK(out_nseg.ensure((size_t)std::max<long long>(n_part, 1)));
@@ -841,25 +841,52 @@ struct EngineT : EngineBase {
   }
 
   // ---- Clean.clean ---------------------------------------------------------------------------
-  int clean(int64_t* n_alive) override {
-    IMC_RC(use_device());
-    if (n_part == 0) { if (n_alive) *n_alive = 0; return IMC_OK; }
-    long long blocks = (n_part + COMPACT_THREADS - 1) / COMPACT_THREADS;
+  // Lazy compaction.  Every kernel that walks the particle list skips the entries whose dead flag is set, so removing them is
+  // only worth a pass over the whole population when enough of them have piled up: on the 10^8-particle Su-Olson decks a
+  // handful of histories end per step, and the stable compaction that removes them copies all 10^8 survivors (1.9 of the step's
+  // 5 ms).  clean() therefore always counts the survivors (that is length(particles) for the caller) and compacts when the dead
+  // entries exceed 1/32 of the list; until then they stay as holes: n_part is the list length, n_part - n_holes the population.
+  // Order, ids and therefore every result are unchanged.  Not used where list positions carry meaning: replay tapes (slot =
+  // position), EXACT tallies (per-particle record counts) and lists small enough for outcome records (get_outcomes).
+  long long n_holes = 0;
+  static long long lazy_min_env() { const char* e = getenv("IMC_LAZY_CLEAN_MIN"); return e ? atoll(e) : (1ll << 22); }   // tests: 0 (always) / a huge value (never)
+  bool lazy_clean_ok() const {
+    return cfg.rng_mode != IMC_RNG_TAPE && resolve_tally_mode() != IMC_TALLY_EXACT && last_mode != IMC_TALLY_EXACT && n_part > lazy_min_env();
+  }
+  int count_alive(long long blocks, long long* total) {
     IMC_CK(blk_cnt.ensure((size_t)blocks));
     IMC_CK(scan_total.ensure(1));
-    Parts<P> src = pb[cur].view(), dst = pb[cur ^ 1].view();
-    k_alive_count<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, n_part, geom, blk_cnt.p); ++n_launch;
+    k_alive_count<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(pb[cur].view(), n_part, geom, blk_cnt.p); ++n_launch;
     k_scan_small<<<1, 1024, 0, stream>>>(blk_cnt.p, blocks, scan_total.p); ++n_launch;
     IMC_CK(cudaGetLastError());
-    long long total = 0;
     gl_reset(); gl_add(scan_total.p, GK_RAW8);
     IMC_RC(gl_read());
-    total = raw_ll(hpin[0]);
-    if (total == n_part) { if (n_alive) *n_alive = n_part; return IMC_OK; }   // nobody died (Su-Olson: most steps): the list is already compact
-    k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(src, dst, n_part, geom, blk_cnt.p); ++n_launch;
+    *total = raw_ll(hpin[0]);
+    return IMC_OK;
+  }
+  int compact(long long blocks, long long total) {   // blk_cnt holds the scanned block counts of count_alive
+    k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(pb[cur].view(), pb[cur ^ 1].view(), n_part, geom, blk_cnt.p); ++n_launch;
     IMC_CK(cudaGetLastError());
-    n_part = total;
+    n_part = total; n_holes = 0;
     cur ^= 1;
+    return IMC_OK;
+  }
+  int materialize() {   // before anything that exposes list positions
+    if (n_holes == 0) return IMC_OK;
+    const long long blocks = (n_part + COMPACT_TILE - 1) / COMPACT_TILE;
+    long long total = 0;
+    IMC_RC(count_alive(blocks, &total));
+    return compact(blocks, total);
+  }
+  int clean(int64_t* n_alive) override {
+    IMC_RC(use_device());
+    if (n_part == 0) { n_holes = 0; if (n_alive) *n_alive = 0; return IMC_OK; }
+    const long long blocks = (n_part + COMPACT_TILE - 1) / COMPACT_TILE;
+    long long total = 0;
+    IMC_RC(count_alive(blocks, &total));
+    if (total == n_part) { n_holes = 0; if (n_alive) *n_alive = n_part; return IMC_OK; }   // nobody died: the list is already compact
+    if (lazy_clean_ok() && (n_part - total) * 32 <= n_part) { n_holes = n_part - total; if (n_alive) *n_alive = total; return IMC_OK; }
+    IMC_RC(compact(blocks, total));
     if (n_alive) *n_alive = n_part;
     return IMC_OK;
   }
@@ -890,7 +917,8 @@ struct EngineT : EngineBase {
     ta.copies = ta.use_smem ? smem_copies(smem, 0) : 1;
     smem = ta.use_smem ? smem * ta.copies : 0;
     int blocks_per_sm = 2048 / TRACK_THREADS;
-    unsigned grid = (unsigned)std::min<long long>((n_part + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
+    const long long groups = (n_part + 3) / 4;   // a thread takes four consecutive particles
+    unsigned grid = (unsigned)std::min<long long>((groups + TRACK_THREADS - 1) / TRACK_THREADS, (long long)sm_count * blocks_per_sm);
     k_census_tally<P><<<grid, TRACK_THREADS, smem, stream>>>(m, pb[cur].view(), n_part, ta); ++n_launch;
     IMC_CK(cudaGetLastError());
     return IMC_OK;
@@ -1130,10 +1158,11 @@ struct EngineT : EngineBase {
     return IMC_OK;
   }
 
-  int64_t num_particles() override { return n_part; }
+  int64_t num_particles() override { return n_part - n_holes; }
   int64_t launches() override { return n_launch; }
   int get_particles(double* slots, uint64_t* ids, int64_t capacity) override {
     IMC_RC(use_device());
+    IMC_RC(materialize());
     if (capacity < n_part) { err = "get_particles: capacity"; return IMC_ERR_ARG; }
     if (n_part == 0) return IMC_OK;
     int nsl = geom == 1 ? 9 : 10;
@@ -1151,7 +1180,7 @@ struct EngineT : EngineBase {
     if (!have_mesh) { err = "set_particles before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     if (n < 0) { err = "set_particles: n < 0"; return IMC_ERR_ARG; }
-    n_part = 0;
+    n_part = 0; n_holes = 0;
     IMC_RC(ensure_capacity(n));
     if (n == 0) return IMC_OK;
     int nsl = geom == 1 ? 9 : 10;
@@ -1206,7 +1235,7 @@ struct EngineT : EngineBase {
   }
   // ---- restart point in device memory (include/imc.h imc_checkpoint) ------------------------------------------
   struct CkptHost {
-    long long n_part; bool temp_wide, red_fixed, dep_perm; double fx_mul_dep, fx_mul_rad, fx_mul_lost, rad_total_h;
+    long long n_part, n_holes; bool temp_wide, red_fixed, dep_perm; double fx_mul_dep, fx_mul_rad, fx_mul_lost, rad_total_h;
     int last_mode; double totalenergy, totalenergydep, radenergyold; uint64_t iterations; long long n_transport_calls;
     double rate_static, rate_refill, rate_event; long long hist_n, hist_dropped; double last_global_segments; long long n_global_after_source;
   };
@@ -1240,7 +1269,7 @@ struct EngineT : EngineBase {
       IMC_CK(ckpt_blob.ensure(total));
       size_t off = 0;
       for (auto& it : items) { IMC_CK(cudaMemcpyAsync(ckpt_blob.p + off, it.first, it.second, cudaMemcpyDeviceToDevice, stream)); off += (it.second + 255) & ~(size_t)255; }
-      ckpt_host = CkptHost{n_part, temp_wide, red_fixed, dep_perm, fx_mul_dep, fx_mul_rad, fx_mul_lost, rad_total_h, last_mode, totalenergy,
+      ckpt_host = CkptHost{n_part, n_holes, temp_wide, red_fixed, dep_perm, fx_mul_dep, fx_mul_rad, fx_mul_lost, rad_total_h, last_mode, totalenergy,
                            totalenergydep, radenergyold, iterations, n_transport_calls, rate_static, rate_refill, rate_event, hist_n, hist_dropped, last_global_segments, n_global_after_source};
       IMC_CK(cudaStreamSynchronize(stream));
       ckpt_valid = true;
@@ -1250,7 +1279,7 @@ struct EngineT : EngineBase {
     if (!ckpt_valid) { err = "checkpoint: nothing saved"; return IMC_ERR_STATE; }
     IMC_RC(ensure_capacity(ckpt_host.n_part));
     const CkptHost& c = ckpt_host;
-    n_part = c.n_part; temp_wide = c.temp_wide; red_fixed = c.red_fixed; dep_perm = c.dep_perm;
+    n_part = c.n_part; n_holes = c.n_holes; temp_wide = c.temp_wide; red_fixed = c.red_fixed; dep_perm = c.dep_perm;
     fx_mul_dep = c.fx_mul_dep; fx_mul_rad = c.fx_mul_rad; fx_mul_lost = c.fx_mul_lost; rad_total_h = c.rad_total_h; last_mode = c.last_mode;
     totalenergy = c.totalenergy; totalenergydep = c.totalenergydep; radenergyold = c.radenergyold; iterations = c.iterations;
     n_transport_calls = c.n_transport_calls; rate_static = c.rate_static; rate_refill = c.rate_refill; rate_event = c.rate_event;

@@ -1515,6 +1515,9 @@ __global__ void k_sample_planck(RngArgs r, long long n, double* __restrict__ out
 // Clean.clean — stable compaction
 // ======================================================================================
 constexpr int COMPACT_THREADS = 512;
+constexpr int COMPACT_ITEMS = 8;                                // sub-tiles of COMPACT_THREADS particles per block
+constexpr int COMPACT_TILE = COMPACT_THREADS * COMPACT_ITEMS;   // particles per block: one count per 4096 particles keeps the
+                                                                // single-block scan of the counts short (24 k entries for 10^8 particles)
 
 template <class P>
 __device__ __forceinline__ bool particle_alive(const Parts<P>& p, long long i, int geom) {
@@ -1522,36 +1525,55 @@ __device__ __forceinline__ bool particle_alive(const Parts<P>& p, long long i, i
   return geom == 1 ? (P::unpack(p.E0[i]) != (typename P::comp_t)-1) : (P::unpack(p.E[i]) != (typename P::comp_t)-1);
 }
 
+// survivors per block of COMPACT_TILE particles: the eight flag loads of a thread are independent and coalesced
 template <class P>
-__global__ void k_alive_count(Parts<P> p, long long n, int geom, long long* __restrict__ block_counts) {
+__global__ void __launch_bounds__(COMPACT_THREADS) k_alive_count(Parts<P> p, long long n, int geom, long long* __restrict__ block_counts) {
   __shared__ int warp_cnt[COMPACT_THREADS / 32];
-  long long i = (long long)blockIdx.x * COMPACT_THREADS + threadIdx.x;
-  bool alive = i < n && particle_alive(p, i, geom);
-  unsigned b = __ballot_sync(IMC_FULL_MASK, alive);
-  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
+  const long long base = (long long)blockIdx.x * COMPACT_TILE + threadIdx.x;
+  bool alive[COMPACT_ITEMS];
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) { const long long i = base + (long long)k * COMPACT_THREADS; alive[k] = i < n && particle_alive(p, i, geom); }
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) c += __popc(__ballot_sync(IMC_FULL_MASK, alive[k]));
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
-    int s = 0;
-    for (int w = 0; w < COMPACT_THREADS / 32; ++w) s += warp_cnt[w];
-    block_counts[blockIdx.x] = s;
+    int t = 0;
+    for (int w = 0; w < COMPACT_THREADS / 32; ++w) t += warp_cnt[w];
+    block_counts[blockIdx.x] = t;
   }
 }
 
+// stable: sub-tile by sub-tile, inside a sub-tile by warp, inside a warp by lane
 template <class P>
-__global__ void k_compact(Parts<P> src, Parts<P> dst, long long n, int geom, const long long* __restrict__ block_offs) {
-  __shared__ int warp_cnt[COMPACT_THREADS / 32];
-  long long i = (long long)blockIdx.x * COMPACT_THREADS + threadIdx.x;
-  bool alive = i < n && particle_alive(src, i, geom);
-  unsigned b = __ballot_sync(IMC_FULL_MASK, alive);
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) warp_cnt[wid] = __popc(b);
-  __syncthreads();
-  if (!alive) return;
-  long long o = block_offs[blockIdx.x] + __popc(b & ((1u << lane) - 1));
-  for (int w = 0; w < wid; ++w) o += warp_cnt[w];
-  dst.t[o] = src.t[i]; dst.x[o] = src.x[i]; dst.mu[o] = src.mu[i]; dst.E[o] = src.E[i]; dst.E0[o] = src.E0[i];
-  dst.cx[o] = src.cx[i]; dst.ks[o] = src.ks[i]; dst.id[o] = src.id[i];
-  if (geom == 2) { dst.y[o] = src.y[i]; dst.cy[o] = src.cy[i]; } else dst.origin[o] = src.origin[i];
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(Parts<P> src, Parts<P> dst, long long n, int geom, const long long* __restrict__ block_offs) {
+  __shared__ int warp_cnt[2][COMPACT_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long out = block_offs[blockIdx.x];
+  const long long i0 = (long long)blockIdx.x * COMPACT_TILE + threadIdx.x;
+  bool alive_k[COMPACT_ITEMS];                       // the eight flag loads of a thread are in flight together
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) { const long long i = i0 + (long long)k * COMPACT_THREADS; alive_k[k] = i < n && particle_alive(src, i, geom); }
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) {
+    const long long i = i0 + (long long)k * COMPACT_THREADS;
+    const bool alive = alive_k[k];
+    const unsigned b = __ballot_sync(IMC_FULL_MASK, alive);
+    int* wc = warp_cnt[k & 1];                       // double-buffered: one barrier per sub-tile
+    if (lane == 0) wc[wid] = __popc(b);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < COMPACT_THREADS / 32; ++w) { const int cw = wc[w]; total += cw; before += w < wid ? cw : 0; }
+    if (alive) {
+      const long long o = out + before + __popc(b & ((1u << lane) - 1));
+      dst.t[o] = src.t[i]; dst.x[o] = src.x[i]; dst.mu[o] = src.mu[i]; dst.E[o] = src.E[i]; dst.E0[o] = src.E0[i];
+      dst.cx[o] = src.cx[i]; dst.ks[o] = src.ks[i]; dst.id[o] = src.id[i];
+      if (geom == 2) { dst.y[o] = src.y[i]; dst.cy[o] = src.cy[i]; } else dst.origin[o] = src.origin[i];
+    }
+    out += total;
+  }
 }
 
 // ======================================================================================
@@ -1562,61 +1584,97 @@ __global__ void k_compact(Parts<P> src, Parts<P> dst, long long n, int geom, con
 // lanes of a warp mostly hold the same cell: runs of consecutive lanes with equal cells are summed with a segmented
 // shuffle scan and the last lane of each run issues the one atomic (Float64 sums in ATOMIC mode, exact integer sums in
 // FIXED mode — both order-free to the tolerance / exactly, like the per-lane atomics they replace).
+// four consecutive elements of a particle field with one load (8-byte fields: two 16-byte loads); i is a multiple of 4 and
+// the field arrays come from cudaMalloc, so the address is aligned
+template <class T> struct alignas(sizeof(T) * 4 > 16 ? 16 : sizeof(T) * 4) Pack4 { T v[4]; };
+template <class T> __device__ __forceinline__ Pack4<T> load4(const T* __restrict__ p, long long i) { return *reinterpret_cast<const Pack4<T>*>(p + i); }
+
 template <class P>
 __global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Parts<P> p, long long n, TallyArgs ta) {
   using N = Num<P>;
+  using S = typename P::store_t;
   extern __shared__ __align__(16) unsigned char smem[];
   Tally<P> tal(ta, smem);
   tal.zero();
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long n_round = (n + 31) & ~31ll;
   const int lane = threadIdx.x & 31;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    const bool alive = i < n && particle_alive(p, i, m.geom);
-    if (ta.mode == IMC_TALLY_EXACT) {   // one record per particle, in particle order (Q19)
-      if (i < n) {
-        if (!alive) { ta.rec_key[i] = 0x7fffffffu; ta.rec_val[i] = 0.0; }
-        else {
-          N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
-          int cx = p.cx[i];
-          if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale), i);
-          else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale), i); }
-        }
-      }
-      continue;
-    }
-    int cell = -1;
-    double v = 0.0; long long q = 0;
-    if (alive) {
+  if (ta.mode == IMC_TALLY_EXACT) {   // one record per particle, in particle order (Q19)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      if (!particle_alive(p, i, m.geom)) { ta.rec_key[i] = 0x7fffffffu; ta.rec_val[i] = 0.0; continue; }
       N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
       int cx = p.cx[i];
-      N d;
-      if (m.geom == 1) { cell = cx; d = E / (N::load(m.dx, cx) * scale); }
-      else { int cy = p.cy[i]; cell = cx + m.nx * cy; d = E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale); }
-      v = d.d();
-      if (ta.mode == IMC_TALLY_FIXED) q = __double2ll_rn(v * ta.fx_mul);
+      if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale), i);
+      else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale), i); }
     }
-    // runs of equal cells: head = first lane of a run; segmented inclusive scan from the head
+    return;
+  }
+  // ATOMIC / FIXED.  A thread takes FOUR consecutive particles (vector loads of every field it needs) and sums the runs of
+  // equal cells among them in registers; the run still open at the end then joins the runs of the neighbouring lanes through
+  // one segmented shuffle scan, and the last lane of each run issues the one atomic.  A run that ends inside a thread is
+  // deposited at once (rare: the list is close to cell order).  Float64 partial sums in ATOMIC mode, exact integers in FIXED.
+  const bool fixed = ta.mode == IMC_TALLY_FIXED;
+  auto deposit = [&](int cell, double v, long long q) {
+    if (fixed) {
+      if (ta.use_smem) smem_add64(&tal.s_fx[cell], (unsigned long long)q);
+      else atomicAdd(reinterpret_cast<unsigned long long*>(ta.g_fx) + cell, (unsigned long long)q);
+    } else {
+      if (ta.use_smem) atomicAdd(&tal.s_acc[cell], (typename AccType<P>::type)v);
+      else atomicAdd(ta.g_acc + cell, v);
+    }
+  };
+  const long long n4 = (n + 3) >> 2;
+  const long long n4_round = (n4 + 31) & ~31ll;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n4_round; g += stride) {
+    int cell = -1;               // the thread's open run
+    double v = 0.0; long long q = 0;
+    if (g < n4) {
+      const long long i0 = g << 2;
+      S e4[4], f4[4]; int cx4[4], cy4[4]; unsigned char k4[4];
+      if (i0 + 3 < n) {
+        const Pack4<S> pe = load4(p.E, i0); const Pack4<int> pc = load4(p.cx, i0); const Pack4<unsigned char> pk = load4(p.ks, i0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { e4[j] = pe.v[j]; f4[j] = pe.v[j]; cx4[j] = pc.v[j]; k4[j] = pk.v[j]; cy4[j] = 0; }
+        if (m.geom == 1) { const Pack4<S> pf = load4(p.E0, i0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f4[j] = pf.v[j]; }
+        else { const Pack4<int> py = load4(p.cy, i0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cy4[j] = py.v[j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long i = i0 + j;
+          const bool in = i < n;
+          e4[j] = in ? p.E[i] : P::pack((typename P::comp_t)-1); f4[j] = in ? (m.geom == 1 ? p.E0[i] : p.E[i]) : P::pack((typename P::comp_t)-1);
+          cx4[j] = in ? p.cx[i] : 0; k4[j] = in ? p.ks[i] : (unsigned char)0; cy4[j] = (in && m.geom == 2) ? p.cy[i] : 0;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (P::unpack(f4[j]) == (typename P::comp_t)-1) continue;   // dead (slot 8: startenergy in 1-D, energy in 2-D)
+        const N E(P::unpack(e4[j])), scale(m.scales[k4[j]]);
+        int cj; N d;
+        if (m.geom == 1) { cj = cx4[j]; d = E / (N::load(m.dx, cx4[j]) * scale); }
+        else { cj = cx4[j] + m.nx * cy4[j]; d = E / ((N::load(m.dx, cx4[j]) * N::load(m.dy, cy4[j])) * scale); }
+        const double vj = d.d();
+        const long long qj = fixed ? __double2ll_rn(vj * ta.fx_mul) : 0;
+        if (cj == cell) { v += vj; q += qj; }
+        else { if (cell >= 0) deposit(cell, v, q); cell = cj; v = vj; q = qj; }
+      }
+    }
+    // runs of equal cells over adjacent lanes: head = first lane of a run; segmented inclusive scan from the head
     const int prev = __shfl_up_sync(IMC_FULL_MASK, cell, 1);
     const unsigned heads = __ballot_sync(IMC_FULL_MASK, lane == 0 || prev != cell);
     const int head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
     const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-    if (ta.mode == IMC_TALLY_FIXED) {
+    if (fixed) {
 #pragma unroll
       for (int dlt = 1; dlt < 32; dlt <<= 1) { const long long tq = __shfl_up_sync(IMC_FULL_MASK, q, dlt); if (lane - dlt >= head) q += tq; }
     } else {
 #pragma unroll
       for (int dlt = 1; dlt < 32; dlt <<= 1) { const double tv = __shfl_up_sync(IMC_FULL_MASK, v, dlt); if (lane - dlt >= head) v += tv; }
     }
-    if (tail && cell >= 0) {
-      if (ta.mode == IMC_TALLY_FIXED) {
-        if (ta.use_smem) smem_add64(&tal.s_fx[cell], (unsigned long long)q);
-        else atomicAdd(reinterpret_cast<unsigned long long*>(ta.g_fx) + cell, (unsigned long long)q);
-      } else {
-        if (ta.use_smem) atomicAdd(&tal.s_acc[cell], (typename AccType<P>::type)v);
-        else atomicAdd(ta.g_acc + cell, v);
-      }
-    }
+    if (tail && cell >= 0) deposit(cell, v, q);
   }
   tal.flush();
 }

@@ -169,3 +169,46 @@ def test_accumulator_sets_at_the_shared_memory_limit(gpu_lib, oracle_lib, precis
     mode = {"atomic": lib.TALLY_ATOMIC, "fixed": lib.TALLY_FIXED}[tally]
     a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=2, precision=precision, tally_mode=mode)
     assert_step_parity(a, b, out, precision)
+
+
+@pytest.mark.parametrize("deck", ["suolson", "nonuniform_1d", "small_2d", "crooked"])
+def test_lazy_compaction_changes_no_result(gpu_lib, oracle_lib, deck, monkeypatch):
+    """Clean.clean on large populations leaves a few dead entries in the list instead of copying every survivor
+    (imc_engine_impl.cuh, "Lazy compaction"); IMC_LAZY_CLEAN_MIN=0 switches that on for a small deck.  Counts, statistics and
+    particles stay bit-identical to the oracle (which always compacts, imc_clean.jl:6-20), the FIXED tallies bit-identical to
+    the engine's own always-compacting run — and the lazy run really skipped compactions (fewer kernel launches)."""
+    precision = "FLOAT64" if deck == "nonuniform_1d" else "FLOAT32"
+    if deck == "suolson":              # three histories end in eight steps: the holes pile up from step to step
+        inputs = decks.suolson(precision=precision, n_input=4000, n_max=60000)
+    elif deck == "nonuniform_1d":      # 0.05 % of the histories end per step
+        inputs = decks.nonuniform_1d(precision=precision, n_input=3000)
+    elif deck == "small_2d":           # 10-30 % per step: above the 1/32 threshold, compaction every step
+        inputs = decks.small_2d(precision=precision, n_input=3000, bcs=("REFLECT",) * 4)
+    else:
+        inputs = decks.crooked_pipe(precision=precision, n_input=4000, n_max=60000, cellmin=2)   # most histories end inside the step: compaction every step
+    # 1. against the oracle, float tallies (AUTO), every step's fields handed over as in the other parity tests
+    monkeypatch.setenv("IMC_LAZY_CLEAN_MIN", "0")
+    a, b, out = run_pair(inputs, gpu_lib, oracle_lib, steps=8, precision=precision)
+    assert_step_parity(a, b, out, precision)              # exports the particles: the holes are removed first
+    died = sum(r[0]["transport"]["n_absorbed"] + r[0]["transport"]["n_escaped"] for r in out)
+    assert died > 0
+    # 2. lazy against always-compacting on the engine alone, FIXED tallies: every number of the run bit-identical
+    runs = {}
+    for name, env in (("lazy", "0"), ("eager", str(1 << 62))):
+        monkeypatch.setenv("IMC_LAZY_CLEAN_MIN", env)
+        sim = driver.setup(inputs, gpu_lib, tally_mode=lib.TALLY_FIXED, track_mode=lib.TRACK_REFILL)   # one tracking launch per step: the launch counts compare
+        sim.save_history = False
+        recs = [sim.advance() for _ in range(8)]
+        launches = sim.engine.kernel_launches()
+        runs[name] = (sim, recs, launches, sim.engine.particles())
+    (la, lrec, ll, (lp, lid)), (ea, erec, el, (ep, eid)) = runs["lazy"], runs["eager"]
+    for r1, r2 in zip(lrec, erec):
+        for stage in ("source", "tally", "energy"):
+            assert r1[stage] == r2[stage], (stage, r1[stage], r2[stage])
+        for k in ("segments", "histories", "n_census", "n_absorbed", "n_escaped", "lostenergy"):
+            assert r1["transport"][k] == r2["transport"][k], k
+    assert np.array_equal(lid, eid) and np.array_equal(lp, ep)
+    for name in ("temp", "matenergydens", "radenergydens", "energydep"):
+        assert np.array_equal(la.engine.field(name), ea.engine.field(name)), name
+    if deck in ("suolson", "nonuniform_1d"):
+        assert ll < el, (ll, el)
