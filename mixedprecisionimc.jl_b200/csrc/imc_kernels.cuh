@@ -1514,6 +1514,9 @@ __global__ void k_sample_planck(RngArgs r, long long n, double* __restrict__ out
 // ======================================================================================
 // Clean.clean — stable compaction
 // ======================================================================================
+#ifndef IMC_COMPACT_MIN_BLOCKS
+#define IMC_COMPACT_MIN_BLOCKS 4
+#endif
 constexpr int COMPACT_THREADS = 512;
 constexpr int COMPACT_ITEMS = 8;                                // sub-tiles of COMPACT_THREADS particles per block
 constexpr int COMPACT_TILE = COMPACT_THREADS * COMPACT_ITEMS;   // particles per block: one count per 4096 particles keeps the
@@ -1545,29 +1548,36 @@ __global__ void __launch_bounds__(COMPACT_THREADS) k_alive_count(Parts<P> p, lon
   }
 }
 
-// stable: sub-tile by sub-tile, inside a sub-tile by warp, inside a warp by lane
+// stable: sub-tile by sub-tile, inside a sub-tile by warp, inside a warp by lane.  The eight flag loads of a thread are in
+// flight together, every (sub-tile, warp) count goes to shared memory behind ONE barrier, and the copies of the survivors
+// follow with all destinations known (with 7 % survivors, as on the crooked pipe, the kernel is a chain of dependent memory
+// round trips: one sub-tile per barrier made it eight chains long).
 template <class P>
-__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(Parts<P> src, Parts<P> dst, long long n, int geom, const long long* __restrict__ block_offs) {
-  __shared__ int warp_cnt[2][COMPACT_THREADS / 32];
+__global__ void __launch_bounds__(COMPACT_THREADS, IMC_COMPACT_MIN_BLOCKS) k_compact(Parts<P> src, Parts<P> dst, long long n, int geom, const long long* __restrict__ block_offs) {
+  constexpr int WARPS = COMPACT_THREADS / 32;
+  __shared__ int warp_cnt[COMPACT_ITEMS][WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  long long out = block_offs[blockIdx.x];
   const long long i0 = (long long)blockIdx.x * COMPACT_TILE + threadIdx.x;
-  bool alive_k[COMPACT_ITEMS];                       // the eight flag loads of a thread are in flight together
+  unsigned alive_mask = 0u;
 #pragma unroll
-  for (int k = 0; k < COMPACT_ITEMS; ++k) { const long long i = i0 + (long long)k * COMPACT_THREADS; alive_k[k] = i < n && particle_alive(src, i, geom); }
+  for (int k = 0; k < COMPACT_ITEMS; ++k) { const long long i = i0 + (long long)k * COMPACT_THREADS; alive_mask |= (i < n && particle_alive(src, i, geom)) ? (1u << k) : 0u; }
+  unsigned long long pre = 0ull;   // survivors in lower lanes of the same warp and sub-tile: eight 5-bit fields
 #pragma unroll
   for (int k = 0; k < COMPACT_ITEMS; ++k) {
-    const long long i = i0 + (long long)k * COMPACT_THREADS;
-    const bool alive = alive_k[k];
-    const unsigned b = __ballot_sync(IMC_FULL_MASK, alive);
-    int* wc = warp_cnt[k & 1];                       // double-buffered: one barrier per sub-tile
-    if (lane == 0) wc[wid] = __popc(b);
-    __syncthreads();
+    const unsigned b = __ballot_sync(IMC_FULL_MASK, (alive_mask >> k) & 1u);
+    pre |= (unsigned long long)__popc(b & ((1u << lane) - 1)) << (5 * k);
+    if (lane == 0) warp_cnt[k][wid] = __popc(b);
+  }
+  __syncthreads();
+  if (alive_mask == 0u) return;
+  long long out = block_offs[blockIdx.x];
+#pragma unroll 1
+  for (int k = 0; k < COMPACT_ITEMS; ++k) {
     int before = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < COMPACT_THREADS / 32; ++w) { const int cw = wc[w]; total += cw; before += w < wid ? cw : 0; }
-    if (alive) {
-      const long long o = out + before + __popc(b & ((1u << lane) - 1));
+    for (int w = 0; w < WARPS; ++w) { const int cw = warp_cnt[k][w]; total += cw; before += w < wid ? cw : 0; }
+    if ((alive_mask >> k) & 1u) {
+      const long long i = i0 + (long long)k * COMPACT_THREADS, o = out + before + (int)((pre >> (5 * k)) & 31ull);
       dst.t[o] = src.t[i]; dst.x[o] = src.x[i]; dst.mu[o] = src.mu[i]; dst.E[o] = src.E[i]; dst.E0[o] = src.E0[i];
       dst.cx[o] = src.cx[i]; dst.ks[o] = src.ks[i]; dst.id[o] = src.id[i];
       if (geom == 2) { dst.y[o] = src.y[i]; dst.cy[o] = src.cy[i]; } else dst.origin[o] = src.origin[i];
