@@ -416,6 +416,7 @@ struct EngineT : EngineBase {
     if (step < 0 || step >= (1ll << 24)) { err = "time-step index outside [0, 2^24): particle ids are step << 40 | ordinal and the Philox counter carries the step in 28 bits"; return IMC_ERR_ARG; }
     IMC_RC(use_device());
     Cc dt = P::from_d(dt_), cellmin = P::from_d(cellmin_);
+    alive_known = false;
     SrcArrays<P> s; s.e = src_e.p; s.q = src_q.p; s.ks = src_ks.p; s.cnt = src_cnt.p; s.nrg = src_nrg.p; s.q_em = src_qem.p;
     k_src_energies<P><<<grid_for(L.n_surf() + nc, 128), 128, 0, stream>>>(m, s, L, dt); ++n_launch;
     IMC_CK(cudaGetLastError());
@@ -659,6 +660,7 @@ struct EngineT : EngineBase {
     if (cfg.randomwalk && !have_rw) { err = "random-walk tables not set (imc_rw_table)"; return IMC_ERR_STATE; }
     if (cfg.rng_mode == IMC_RNG_TAPE && n_part > tt_slots) { err = "transport tape has fewer slots than particles"; return IMC_ERR_TAPE; }
     if (n_part >= (1ll << 32)) { err = "more than 2^32 particles on one GPU"; return IMC_ERR_ARG; }
+    alive_known = false;
     int mode = resolve_tally_mode();
     if ((mode == IMC_TALLY_FIXED) != red_fixed) {  // representation change: start from a clean buffer
       IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream));
@@ -837,6 +839,7 @@ struct EngineT : EngineBase {
       out->variant = variant; out->tally_mode = mode; out->kernel_ms = ms;
     }
     if (over) { err = "transport tape exhausted"; return IMC_ERR_TAPE; }
+    alive_known = true; alive_after_transport = (long long)cnt(RB_CENSUS);
     return IMC_OK;
   }
 
@@ -853,12 +856,20 @@ struct EngineT : EngineBase {
   bool lazy_clean_ok() const {
     return cfg.rng_mode != IMC_RNG_TAPE && resolve_tally_mode() != IMC_TALLY_EXACT && last_mode != IMC_TALLY_EXACT && n_part > lazy_min_env();
   }
-  int count_alive(long long blocks, long long* total) {
+  // The survivors of a transport call are its census outcomes (every tracked history ends in exactly one outcome, and the
+  // other three set the dead flag), so clean() right after transport() knows length(particles) without counting: no
+  // launch and no synchronisation when nothing has to move, and no synchronisation before the compaction otherwise.
+  bool alive_known = false; long long alive_after_transport = 0;
+  int count_blocks(long long blocks) {   // per-block survivor counts, scanned (device side only)
     IMC_CK(blk_cnt.ensure((size_t)blocks));
     IMC_CK(scan_total.ensure(1));
     k_alive_count<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(pb[cur].view(), n_part, geom, blk_cnt.p); ++n_launch;
     k_scan_small<<<1, 1024, 0, stream>>>(blk_cnt.p, blocks, scan_total.p); ++n_launch;
     IMC_CK(cudaGetLastError());
+    return IMC_OK;
+  }
+  int count_alive(long long blocks, long long* total) {
+    IMC_RC(count_blocks(blocks));
     gl_reset(); gl_add(scan_total.p, GK_RAW8);
     IMC_RC(gl_read());
     *total = raw_ll(hpin[0]);
@@ -867,7 +878,7 @@ struct EngineT : EngineBase {
   int compact(long long blocks, long long total) {   // blk_cnt holds the scanned block counts of count_alive
     k_compact<P><<<(unsigned)blocks, COMPACT_THREADS, 0, stream>>>(pb[cur].view(), pb[cur ^ 1].view(), n_part, geom, blk_cnt.p); ++n_launch;
     IMC_CK(cudaGetLastError());
-    n_part = total; n_holes = 0;
+    n_part = total; n_holes = 0; alive_known = false;
     cur ^= 1;
     return IMC_OK;
   }
@@ -883,9 +894,12 @@ struct EngineT : EngineBase {
     if (n_part == 0) { n_holes = 0; if (n_alive) *n_alive = 0; return IMC_OK; }
     const long long blocks = (n_part + COMPACT_TILE - 1) / COMPACT_TILE;
     long long total = 0;
-    IMC_RC(count_alive(blocks, &total));
+    const bool counted = !alive_known;
+    if (alive_known) total = alive_after_transport; else IMC_RC(count_alive(blocks, &total));
+    alive_known = false;
     if (total == n_part) { n_holes = 0; if (n_alive) *n_alive = n_part; return IMC_OK; }   // nobody died: the list is already compact
     if (lazy_clean_ok() && (n_part - total) * 32 <= n_part) { n_holes = n_part - total; if (n_alive) *n_alive = total; return IMC_OK; }
+    if (!counted) IMC_RC(count_blocks(blocks));
     IMC_RC(compact(blocks, total));
     if (n_alive) *n_alive = n_part;
     return IMC_OK;
@@ -1180,7 +1194,7 @@ struct EngineT : EngineBase {
     if (!have_mesh) { err = "set_particles before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
     if (n < 0) { err = "set_particles: n < 0"; return IMC_ERR_ARG; }
-    n_part = 0; n_holes = 0;
+    n_part = 0; n_holes = 0; alive_known = false;
     IMC_RC(ensure_capacity(n));
     if (n == 0) return IMC_OK;
     int nsl = geom == 1 ? 9 : 10;
@@ -1279,7 +1293,7 @@ struct EngineT : EngineBase {
     if (!ckpt_valid) { err = "checkpoint: nothing saved"; return IMC_ERR_STATE; }
     IMC_RC(ensure_capacity(ckpt_host.n_part));
     const CkptHost& c = ckpt_host;
-    n_part = c.n_part; n_holes = c.n_holes; temp_wide = c.temp_wide; red_fixed = c.red_fixed; dep_perm = c.dep_perm;
+    n_part = c.n_part; n_holes = c.n_holes; alive_known = false; temp_wide = c.temp_wide; red_fixed = c.red_fixed; dep_perm = c.dep_perm;
     fx_mul_dep = c.fx_mul_dep; fx_mul_rad = c.fx_mul_rad; fx_mul_lost = c.fx_mul_lost; rad_total_h = c.rad_total_h; last_mode = c.last_mode;
     totalenergy = c.totalenergy; totalenergydep = c.totalenergydep; radenergyold = c.radenergyold; iterations = c.iterations;
     n_transport_calls = c.n_transport_calls; rate_static = c.rate_static; rate_refill = c.rate_refill; rate_event = c.rate_event;
