@@ -14,9 +14,11 @@
 // Arithmetic is Num<P>: one rounding per Julia operation, Float64 where the reference leaks into
 // Float64.  Compiled with -fmad=false.  Particle state is structure-of-arrays.
 #pragma once
+#include <type_traits>
 #include "imc_device.cuh"
 #include "imc_fastdiv.cuh"
 #include "imc_warp_reduce.cuh"
+#include "imc_warp_runs.cuh"
 
 namespace imc {
 
@@ -1599,46 +1601,27 @@ __global__ void __launch_bounds__(COMPACT_THREADS, IMC_COMPACT_MIN_BLOCKS) k_com
 template <class T> struct alignas(sizeof(T) * 4 > 16 ? 16 : sizeof(T) * 4) Pack4 { T v[4]; };
 template <class T> __device__ __forceinline__ Pack4<T> load4(const T* __restrict__ p, long long i) { return *reinterpret_cast<const Pack4<T>*>(p + i); }
 
-template <class P>
-__global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Parts<P> p, long long n, TallyArgs ta) {
+// the ATOMIC / FIXED body of k_census_tally; V = double (float tallies) or long long (FIXED)
+template <class P, class V>
+__device__ __forceinline__ void census_groups(const MeshDev<P>& m, const Parts<P>& p, long long n, const TallyArgs& ta, Tally<P>& tal) {
   using N = Num<P>;
   using S = typename P::store_t;
-  extern __shared__ __align__(16) unsigned char smem[];
-  Tally<P> tal(ta, smem);
-  tal.zero();
+  constexpr bool fixed = std::is_integral<V>::value;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  if (ta.mode == IMC_TALLY_EXACT) {   // one record per particle, in particle order (Q19)
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      if (!particle_alive(p, i, m.geom)) { ta.rec_key[i] = 0x7fffffffu; ta.rec_val[i] = 0.0; continue; }
-      N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
-      int cx = p.cx[i];
-      if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale), i);
-      else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale), i); }
-    }
-    return;
-  }
-  // ATOMIC / FIXED.  A thread takes FOUR consecutive particles (vector loads of every field it needs) and sums the runs of
-  // equal cells among them in registers; the run still open at the end then joins the runs of the neighbouring lanes through
-  // one segmented shuffle scan, and the last lane of each run issues the one atomic.  A run that ends inside a thread is
-  // deposited at once (rare: the list is close to cell order).  Float64 partial sums in ATOMIC mode, exact integers in FIXED.
-  const bool fixed = ta.mode == IMC_TALLY_FIXED;
-  auto deposit = [&](int cell, double v, long long q) {
-    if (fixed) {
-      if (ta.use_smem) smem_add64(&tal.s_fx[cell], (unsigned long long)q);
-      else atomicAdd(reinterpret_cast<unsigned long long*>(ta.g_fx) + cell, (unsigned long long)q);
+  auto deposit = [&](int cell, V x) {
+    if constexpr (fixed) {
+      if (ta.use_smem) smem_add64(&tal.s_fx[cell], (unsigned long long)x);
+      else atomicAdd(reinterpret_cast<unsigned long long*>(ta.g_fx) + cell, (unsigned long long)x);
     } else {
-      if (ta.use_smem) atomicAdd(&tal.s_acc[cell], (typename AccType<P>::type)v);
-      else atomicAdd(ta.g_acc + cell, v);
+      if (ta.use_smem) atomicAdd(&tal.s_acc[cell], (typename AccType<P>::type)x);
+      else atomicAdd(ta.g_acc + cell, x);
     }
   };
   const long long n4 = (n + 3) >> 2;
   const long long n4_round = (n4 + 31) & ~31ll;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n4_round; g += stride) {
-    int cell = -1;               // the thread's open (last) run
-    double v = 0.0; long long q = 0;
-    int cell_f = -1;             // its first run, when a run ended inside the thread (joins the previous lane's run below)
-    double v_f = 0.0; long long q_f = 0;
+    ThreadRuns<V> r;
     if (g < n4) {
       const long long i0 = g << 2;
       S e4[4], f4[4]; int cx4[4], cy4[4]; unsigned char k4[4];
@@ -1668,47 +1651,44 @@ __global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Pa
         int cj; N d;
         if (m.geom == 1) { cj = cx4[j]; d = E / (N::load(m.dx, cx4[j]) * scale); }
         else { cj = cx4[j] + m.nx * cy4[j]; d = E / ((N::load(m.dx, cx4[j]) * N::load(m.dy, cy4[j])) * scale); }
-        const double vj = d.d();
-        const long long qj = fixed ? __double2ll_rn(vj * ta.fx_mul) : 0;
-        if (cj == cell) { v += vj; q += qj; }
-        else {
-          if (cell >= 0) {
-            if (cell_f < 0) { cell_f = cell; v_f = v; q_f = q; }   // the first run that ends inside the thread
-            else deposit(cell, v, q);                              // a run that starts and ends inside the thread (rare)
-          }
-          cell = cj; v = vj; q = qj;
-        }
+        V vj;
+        if constexpr (fixed) vj = __double2ll_rn(d.d() * ta.fx_mul); else vj = d.d();
+        r.push(cj, vj, deposit);
       }
     }
-    // Runs of equal cells over adjacent lanes.  A lane whose four particles are one run is a link of a longer run; a lane
-    // with a run end inside it closes the run of the lanes before it with its FIRST run and opens a new one with its LAST
-    // run.  head = first lane of a run of last runs; segmented inclusive scan of the last runs from the head; the lane
-    // where a run ends then takes the first run of the next lane if that continues its cell.
-    const int prev = __shfl_up_sync(IMC_FULL_MASK, cell, 1);
-    const bool joins_prev = lane != 0 && prev == (cell_f >= 0 ? cell_f : cell);   // this lane's first particles continue the previous lane's run
-    const unsigned heads = __ballot_sync(IMC_FULL_MASK, cell_f >= 0 || !joins_prev);
-    const int head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-    if (fixed) {
-#pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) { const long long tq = __shfl_up_sync(IMC_FULL_MASK, q, dlt); if (lane - dlt >= head) q += tq; }
-    } else {
-#pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) { const double tv = __shfl_up_sync(IMC_FULL_MASK, v, dlt); if (lane - dlt >= head) v += tv; }
-    }
-    {   // the next lane's first run, if it continues this lane's cell, ends here
-      const bool give = cell_f >= 0 && joins_prev;
-      const int gc = __shfl_down_sync(IMC_FULL_MASK, give ? 1 : 0, 1);
-      if (fixed) { const long long gq = __shfl_down_sync(IMC_FULL_MASK, q_f, 1); if (lane != 31 && gc) q += gq; }
-      else { const double gv = __shfl_down_sync(IMC_FULL_MASK, v_f, 1); if (lane != 31 && gc) v += gv; }
-    }
-    const bool want = tail && cell >= 0;                 // the run that ends at this lane's last particle
-    const bool want_f = cell_f >= 0 && !joins_prev;      // a first run that continues nothing
+    bool want, want_f;
+    warp_join_runs(lane, r, want, want_f);
     // (Taking turns with plain adds on a warp-private accumulator set — MATCH.ANY groups the lanes that name the same cell —
     // instead of these atomics, which are compare-and-swap loops for floats: measured slower, k_census_tally 0.67 -> 1.05 ms.)
-    if (want) deposit(cell, v, q);
-    if (want_f) deposit(cell_f, v_f, q_f);
+    if (want) deposit(r.cell, r.v);
+    if (want_f) deposit(r.cell_f, r.v_f);
   }
+}
+
+template <class P>
+__global__ void __launch_bounds__(TRACK_THREADS) k_census_tally(MeshDev<P> m, Parts<P> p, long long n, TallyArgs ta) {
+  using N = Num<P>;
+  using S = typename P::store_t;
+  extern __shared__ __align__(16) unsigned char smem[];
+  Tally<P> tal(ta, smem);
+  tal.zero();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  if (ta.mode == IMC_TALLY_EXACT) {   // one record per particle, in particle order (Q19)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      if (!particle_alive(p, i, m.geom)) { ta.rec_key[i] = 0x7fffffffu; ta.rec_val[i] = 0.0; continue; }
+      N E = N::load(p.E, i), scale(m.scales[p.ks[i]]);
+      int cx = p.cx[i];
+      if (m.geom == 1) tal.add(cx, E / (N::load(m.dx, cx) * scale), i);
+      else { int cy = p.cy[i]; tal.add((long long)cx + (long long)m.nx * cy, E / ((N::load(m.dx, cx) * N::load(m.dy, cy)) * scale), i); }
+    }
+    return;
+  }
+  // ATOMIC / FIXED.  A thread takes FOUR consecutive particles (vector loads of every field it needs); the runs of equal
+  // cells among them, and from lane to lane, end in one atomic each (imc_warp_runs.cuh).  Float64 partial sums in ATOMIC
+  // mode, exact integers in FIXED.
+  if (ta.mode == IMC_TALLY_FIXED) census_groups<P, long long>(m, p, n, ta, tal);
+  else census_groups<P, double>(m, p, n, ta, tal);
   tal.flush();
 }
 

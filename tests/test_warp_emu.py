@@ -13,7 +13,8 @@ import __graft_entry__ as entry
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(entry.ROOT, "build", "warp_emu", "libwarp_reduce_host.so")
 SRC = os.path.join(HERE, "warp_emu", "warp_reduce_host.cpp")
-DEPS = [SRC, os.path.join(HERE, "warp_emu", "warp_emu.h"), os.path.join(entry.CSRC, "imc_warp_reduce.cuh"), os.path.join(entry.CSRC, "imc_num.h")]
+DEPS = [SRC, os.path.join(HERE, "warp_emu", "warp_emu.h"), os.path.join(entry.CSRC, "imc_warp_reduce.cuh"), os.path.join(entry.CSRC, "imc_warp_runs.cuh"),
+        os.path.join(entry.CSRC, "imc_num.h")]
 T = {0: np.float16, 1: np.float32, 2: np.float64}
 
 
@@ -44,6 +45,15 @@ def emu():
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         return (dll.warp_reduce_host(2, prec, 0.0, None, vals.ctypes.data_as(dp), len(vals)), dll.plain_jl_sum(prec, vals.ctypes.data_as(dp), len(vals)))
     run.pairwise = pairwise
+    dll.warp_runs_host.restype = C.c_longlong
+    dll.warp_runs_host.argtypes = [C.c_int, C.POINTER(C.c_int), dp, C.c_int, dp]
+
+    def runs(integer, cells, vals, ncell):
+        cells = np.ascontiguousarray(cells, dtype=np.int32); vals = np.ascontiguousarray(vals, dtype=np.float64)
+        sums = np.zeros(ncell)
+        nd = dll.warp_runs_host(integer, cells.ctypes.data_as(C.POINTER(C.c_int)), vals.ctypes.data_as(dp), cells.shape[1], sums.ctypes.data_as(dp))
+        return sums, nd
+    run.runs = runs
     return run
 
 
@@ -99,3 +109,37 @@ def test_pairwise_sum_by_a_warp(emu, prec, n):
     vals = (rng.random(n) * 10.0 ** rng.integers(-3, 2, size=n)).astype(T[prec]).astype(np.float64)
     got, want = emu.pairwise(prec, vals)
     assert bits(got) == bits(want)
+
+
+@pytest.mark.parametrize("integer", [0, 1])
+@pytest.mark.parametrize("per", [1, 4])
+def test_runs_of_equal_cells_end_in_one_deposit(emu, integer, per):
+    """imc_warp_runs.cuh (the census tally's ThreadRuns + warp_join_runs): 32 lanes x `per` consecutive particles with random
+    runs of cells and dead particles in between — the per-cell sums equal the plain sums, and there is exactly one deposit per
+    run of the list except for runs that start and end inside one lane's particles after its first run (deposited at once)
+    and for runs broken by a lane without particles."""
+    rng = np.random.default_rng(31 * per + integer)
+    ncell = 6
+    for trial in range(300):
+        p_change = rng.choice([0.02, 0.1, 0.25, 0.6, 1.0])
+        cells = np.empty((32, per), dtype=np.int32)
+        cur = rng.integers(ncell)
+        for i in range(32 * per):
+            if rng.random() < p_change:
+                cur = rng.integers(ncell)
+            cells[i // per, i % per] = cur
+        dead = rng.random((32, per)) < rng.choice([0.0, 0.1, 0.5])
+        if trial % 7 == 0:
+            dead[rng.integers(32)] = True                      # a lane without particles
+        if trial % 11 == 0:
+            dead[:] = True                                     # nothing alive at all
+        vals = rng.integers(1, 1000, size=(32, per)).astype(np.float64)
+        sums, nd = emu.runs(integer, np.where(dead, -1, cells), vals, ncell)
+        want = np.zeros(ncell)
+        np.add.at(want, cells[~dead], vals[~dead])
+        assert np.array_equal(sums, want), (trial, per, integer)
+        alive_cells = cells[~dead]
+        runs_in_list = 0 if alive_cells.size == 0 else 1 + int(np.count_nonzero(alive_cells[1:] != alive_cells[:-1]))
+        assert nd >= runs_in_list                              # never fewer deposits than runs ...
+        if not dead.any():
+            assert nd <= runs_in_list + 1                      # ... and no more (lane 0's first run cannot join a previous warp)

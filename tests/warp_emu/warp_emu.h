@@ -1,4 +1,4 @@
-// warp_emu.h — the three warp intrinsics imc_warp_reduce.cuh uses, emulated on the host by 32 threads in lockstep.
+// warp_emu.h — the warp intrinsics imc_warp_reduce.cuh and imc_warp_runs.cuh use, emulated on the host by 32 threads in lockstep.
 //
 // TEST INFRASTRUCTURE.  Every lane is a std::thread; an intrinsic is "all lanes publish their operand, wait at a barrier,
 // read what they need, wait again".  That is the semantics of the *_sync intrinsics with a full mask, which is the only way
@@ -47,6 +47,12 @@ inline T __shfl_sync(unsigned, T v, int src) {
   w->bar.arrive_and_wait();
   return out;
 }
+// __shfl_up_sync / __shfl_down_sync: lanes whose source would fall outside the warp keep their own value
+template <class T>
+inline T __shfl_up_sync(unsigned m, T v, unsigned delta) { const int l = warp_emu::g_lane; return __shfl_sync(m, v, l >= (int)delta ? l - (int)delta : l); }
+template <class T>
+inline T __shfl_down_sync(unsigned m, T v, unsigned delta) { const int l = warp_emu::g_lane; return __shfl_sync(m, v, l + (int)delta < 32 ? l + (int)delta : l); }
+inline int __clz(unsigned m) { return m ? __builtin_clz(m) : 32; }
 inline int __ffs(unsigned m) { return m ? __builtin_ctz(m) + 1 : 0; }
 using std::signbit;
 

@@ -2,6 +2,8 @@
 //   g++ -std=c++20 -O1 -fPIC -shared -ffp-contract=off -mf16c -pthread -I<csrc> -o libwarp_reduce_host.so warp_reduce_host.cpp
 #include "warp_emu.h"
 #include "imc_warp_reduce.cuh"
+#include "imc_warp_runs.cuh"
+#include <mutex>
 
 using namespace imc;
 
@@ -31,7 +33,34 @@ static Num<P> jl_rec(const double* a, long long first, long long last) {
   return jl_rec<P>(a, first, mid) + jl_rec<P>(a, mid + 1, last);
 }
 
+// imc_warp_runs.cuh as the census tally uses it: `per` consecutive particles per lane (cell < 0: a dead particle), every
+// deposit added to sums[cell]; returns the number of deposits (one per run of the list is the point of the exercise)
+template <class V>
+static long long runs_host(const int* cells, const double* vals, int per, double* sums) {
+  std::mutex mu;
+  long long deposits = 0;
+  warp_emu::run_warp<int>([&](int lane) {
+    ThreadRuns<V> r;
+    auto deposit = [&](int c, V x) { std::lock_guard<std::mutex> g(mu); sums[c] += (double)x; ++deposits; };
+    for (int j = 0; j < per; ++j) {
+      const int c = cells[lane * per + j];
+      if (c >= 0) r.push(c, (V)vals[lane * per + j], deposit);
+    }
+    bool want, want_f;
+    warp_join_runs(lane, r, want, want_f);
+    if (want) deposit(r.cell, r.v);
+    if (want_f) deposit(r.cell_f, r.v_f);
+    return 0;
+  });
+  return deposits;
+}
+
 extern "C" {
+// integer = 0: double partial sums (float tallies), 1: 64-bit integers (FIXED tallies); vals are whole numbers, so every order of
+// additions gives the same sums
+long long warp_runs_host(int integer, const int* cells, const double* vals, int per, double* sums) {
+  return integer ? runs_host<long long>(cells, vals, per, sums) : runs_host<double>(cells, vals, per, sums);
+}
 // which: 0 = warp_seq_add (the chain as the kernels have always run it), 1 = warp_seq_add_skip, 2 = warp_jl_sum;
 // prec: 0 F16, 1 F32, 2 F64
 double warp_reduce_host(int which, int prec, double v0, const unsigned* keys, const double* vals, long long n) {
