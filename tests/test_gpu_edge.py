@@ -212,3 +212,40 @@ def test_lazy_compaction_changes_no_result(gpu_lib, oracle_lib, deck, monkeypatc
         assert np.array_equal(la.engine.field(name), ea.engine.field(name)), name
     if deck in ("suolson", "nonuniform_1d"):
         assert ll < el, (ll, el)
+
+
+@pytest.mark.parametrize("precision", ["FLOAT16", "FLOAT32", "FLOAT64"])
+@pytest.mark.parametrize("geom", ["1d", "2d"])
+@pytest.mark.parametrize("tally", ["fixed", "atomic"])
+def test_census_tally_is_the_per_cell_sum_over_the_particle_list(gpu_lib, precision, geom, tally):
+    """Tally.tally's radiation energy density (imc_tally.jl:84-113): radenergydens[cell] = sum over the surviving particles of
+    E / (dx [dy] scale).  The kernel reads the list four particles per thread with vector loads and joins runs of equal cells
+    across the lanes of a warp; here its result is recomputed from the exported particle list, for every precision (vector
+    width 8 / 16 / 2 x 16 bytes), both geometries and both accumulator kinds, with populations that are no multiple of 4."""
+    f16 = precision == "FLOAT16"
+    es = (1024.0,) if f16 else (1.0,)
+    if geom == "1d":
+        inputs = decks.nonuniform_1d(precision=precision, n_input=3000) if not f16 else decks.infinite_medium(precision=precision, n_input=3000, n_max=30000, energyscales=es)
+    else:
+        inputs = decks.small_2d(precision=precision, n_input=3000, n_max=60000 if f16 else 100000, bcs=("REFLECT", "VACUUM", "REFLECT", "REFLECT"), energyscales=es)
+    sim = driver.setup(inputs, gpu_lib, tally_mode=lib.TALLY_FIXED if tally == "fixed" else lib.TALLY_ATOMIC)
+    sim.save_history = False
+    tol = {"FLOAT16": 3e-3, "FLOAT32": 1e-6, "FLOAT64": 1e-13}[precision]   # the terms are rounded to T one by one, the sum once
+    if tally == "fixed" and precision == "FLOAT64":
+        tol = 1e-9   # every term is rounded to the fixed-point quantum, 2^-62 of a bound on the largest possible sum (DESIGN.md section 4, FIXED)
+    for _ in range(2):
+        sim.advance()
+        eng = sim.engine
+        slots, _ = eng.particles()
+        rad = eng.field("radenergydens")
+        dx = np.asarray(sim.mesh.dx, dtype=np.float64)
+        want = np.zeros(rad.size)
+        if geom == "1d":
+            cell = slots[:, 2].astype(np.int64) - 1
+            np.add.at(want, cell, slots[:, 6] / (dx[cell] * slots[:, 8]))
+        else:
+            dy = np.asarray(sim.mesh.dy, dtype=np.float64)
+            cx, cy = slots[:, 1].astype(np.int64) - 1, slots[:, 2].astype(np.int64) - 1
+            np.add.at(want, cx + dx.size * cy, slots[:, 7] / ((dx[cx] * dy[cy]) * slots[:, 9]))
+        assert slots.shape[0] > 500 and want.max() > 0
+        assert np.max(np.abs(rad.ravel(order="F") - want)) <= tol * want.max(), (np.max(np.abs(rad.ravel(order="F") - want)), want.max())
