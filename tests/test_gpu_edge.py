@@ -232,7 +232,9 @@ def test_census_tally_is_the_per_cell_sum_over_the_particle_list(gpu_lib, precis
     sim.save_history = False
     tol = {"FLOAT16": 3e-3, "FLOAT32": 1e-6, "FLOAT64": 1e-13}[precision]   # the terms are rounded to T one by one, the sum once
     if tally == "fixed" and precision == "FLOAT64":
-        tol = 1e-9   # every term is rounded to the fixed-point quantum, 2^-62 of a bound on the largest possible sum (FIXED)
+        tol = 1e-8   # every term is rounded to the fixed-point quantum, 2^-62 of a bound on the largest possible sum (FIXED); measured 2e-10
+    if tally == "atomic" and precision == "FLOAT32":
+        tol = 2e-5   # Float32 shared-memory accumulators, ~100 additions per cell in an order that changes from run to run
     for _ in range(2):
         sim.advance()
         eng = sim.engine
