@@ -252,7 +252,8 @@ void* imc_stream(imc_handle h);
  *   1-D: 9 slots  [origin, time, cellindex, position, mu, freq, energy, startenergy, energyscale]
  *   2-D: 10 slots [time, xindex, yindex, xpos, ypos, mu, frq, energy, startenergy, energyscale]
  * indices are 1-based as in Julia; a dead particle has slot 8 == -1.0.  ids (may be NULL) are the
- * engine's 64-bit particle ids (Philox counter). */
+ * engine's 64-bit particle ids (Philox counter).  imc_num_particles is length(particles); when imc_clean has left dead
+ * entries in the engine's list (see there), imc_get_particles removes every flagged entry first. */
 int64_t imc_num_particles(imc_handle h);
 /* diagnostic: CUDA kernels launched by this engine since creation (0 for the oracle) */
 int64_t imc_kernel_launches(imc_handle h);

@@ -847,7 +847,7 @@ struct EngineT : EngineBase {
   // Lazy compaction.  Every kernel that walks the particle list skips the entries whose dead flag is set, so removing them is
   // only worth a pass over the whole population when enough of them have piled up: on the 10^8-particle Su-Olson decks a
   // handful of histories end per step, and the stable compaction that removes them copies all 10^8 survivors (1.9 of the step's
-  // 5 ms).  clean() therefore always counts the survivors (that is length(particles) for the caller) and compacts when the dead
+  // 5 ms).  clean() therefore always knows the survivors (that is length(particles) for the caller) and compacts when the dead
   // entries exceed 1/32 of the list; until then they stay as holes: n_part is the list length, n_part - n_holes the population.
   // Order, ids and therefore every result are unchanged.  Not used where list positions carry meaning: replay tapes (slot =
   // position), EXACT tallies (per-particle record counts) and lists small enough for outcome records (get_outcomes).
