@@ -366,6 +366,7 @@ struct EngineT : EngineBase {
     IMC_CK(cudaGetLastError());
     IMC_CK(cudaStreamSynchronize(stream));
     totalenergy = totalenergydep = radenergyold = 0;
+    echeck_cached = false;
     have_mesh = true;
     return IMC_OK;
   }
@@ -660,7 +661,7 @@ struct EngineT : EngineBase {
     if (cfg.randomwalk && !have_rw) { err = "random-walk tables not set (imc_rw_table)"; return IMC_ERR_STATE; }
     if (cfg.rng_mode == IMC_RNG_TAPE && n_part > tt_slots) { err = "transport tape has fewer slots than particles"; return IMC_ERR_TAPE; }
     if (n_part >= (1ll << 32)) { err = "more than 2^32 particles on one GPU"; return IMC_ERR_ARG; }
-    alive_known = false;
+    alive_known = false; echeck_cached = false;
     int mode = resolve_tally_mode();
     if ((mode == IMC_TALLY_FIXED) != red_fixed) {  // representation change: start from a clean buffer
       IMC_CK(cudaMemsetAsync(red.p, 0, red_n * sizeof(double), stream));
@@ -860,6 +861,9 @@ struct EngineT : EngineBase {
   // other three set the dead flag), so clean() right after transport() knows length(particles) without counting: no
   // launch and no synchronisation when nothing has to move, and no synchronisation before the compaction otherwise.
   bool alive_known = false; long long alive_after_transport = 0;
+  // what energycheck() needs, when the tally_finish() call before it has already read it (nothing may change radenergydens
+  // or the lostenergy slot in between: every other entry point that could clears the flag)
+  bool echeck_cached = false; Cc echeck_rad = 0; double echeck_lost_raw = 0;
   int count_blocks(long long blocks) {   // per-block survivor counts, scanned (device side only)
     IMC_CK(blk_cnt.ensure((size_t)blocks));
     IMC_CK(scan_total.ensure(1));
@@ -909,6 +913,7 @@ struct EngineT : EngineBase {
   int tally_local() override {
     if (!have_mesh) { err = "tally before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
+    echeck_cached = false;
     int mode = red_fixed ? IMC_TALLY_FIXED : (last_mode == IMC_TALLY_EXACT || (resolve_tally_mode() == IMC_TALLY_EXACT && n_transport_calls == 0) ? IMC_TALLY_EXACT : IMC_TALLY_ATOMIC);
     if (mode == IMC_TALLY_EXACT && n_part > (cfg.exact_record_budget > 0 ? cfg.exact_record_budget : (1ll << 28))) mode = IMC_TALLY_ATOMIC;
     IMC_CK(cudaMemsetAsync(red.p + rb_rad0(), 0, nc * sizeof(double), stream));
@@ -967,10 +972,15 @@ struct EngineT : EngineBase {
     gl_add(d_max.p, GK_RAW8); gl_add(d_flag.p, GK_I32);
     gl_add(red.p + rb_sc0() + RB_SEG, GK_RAW8);                                     // summed over ranks by the host
     for (int k = 0; k < ns; ++k) gl_add(sums.p + 16 + k, GK_T);
+    const int i_lost = gl_add(red.p + rb_sc0() + RB_LOST, GK_RAW8);                 // for energycheck (below)
     IMC_RC(gl_read());
     for (int k = 0; k < 3; ++k) h2[k] = (Cc)hpin[k];
     mx = hpin[3]; has_nan = (int)hpin[4]; gseg = hpin[5];
     for (int k = 0; k < ns; ++k) plane[k] = (Cc)hpin[6 + k];
+    // EnergyCheck.energychecker needs sum(radenergydens .* volume) and lostenergy: the first was just formed for this
+    // stage's own statistics and the second sits in the buffer read above, so the call that follows Tally.tally in the
+    // reference's loop needs no launch and no synchronisation of its own
+    if (i_lost >= 0) { echeck_rad = h2[2]; echeck_lost_raw = hpin[i_lost]; echeck_cached = true; }
     N ted;
     for (int k = 0; k < ns; ++k) ted = ted + N(plane[k]);                            // :51 / :55
     totalenergydep = ted.d();
@@ -988,14 +998,18 @@ struct EngineT : EngineBase {
   int energycheck(imc_energy_stats* out) override {
     if (!have_mesh) { err = "energycheck before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
-    k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p); ++n_launch;
-    IMC_CK(cudaGetLastError());
-    IMC_RC(jl_sum(q_rad.p, nc, sums.p + 14));
-    IMC_RC(jl_flush());
     Cc h; double lost_raw;
-    gl_reset(); gl_add(sums.p + 14, GK_T); gl_add(red.p + rb_sc0() + RB_LOST, GK_RAW8);
-    IMC_RC(gl_read());
-    h = (Cc)hpin[0]; lost_raw = hpin[1];
+    if (echeck_cached) { h = echeck_rad; lost_raw = echeck_lost_raw; }   // read by the tally_finish call just before
+    else {
+      k_rad_energy<P><<<grid_for(nc, 256), 256, 0, stream>>>(m, q_rad.p); ++n_launch;
+      IMC_CK(cudaGetLastError());
+      IMC_RC(jl_sum(q_rad.p, nc, sums.p + 14));
+      IMC_RC(jl_flush());
+      gl_reset(); gl_add(sums.p + 14, GK_T); gl_add(red.p + rb_sc0() + RB_LOST, GK_RAW8);
+      IMC_RC(gl_read());
+      h = (Cc)hpin[0]; lost_raw = hpin[1];
+    }
+    echeck_cached = false;
     double lost;
     if (red_fixed) { long long v; memcpy(&v, &lost_raw, 8); lost = (double)v / fx_mul_lost; } else lost = lost_raw;
     N radenergy(h), te = N::from_d(totalenergy), ted = N::from_d(totalenergydep), old = N::from_d(radenergyold), lo = N::from_d(lost);
@@ -1087,6 +1101,7 @@ struct EngineT : EngineBase {
   int set_state_native(const void* temp_, const void* mat, const void* rad) override {
     if (!have_mesh) { err = "set_state before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
+    echeck_cached = false;
     if (temp_) {
       if (temp_wide) IMC_CK(cudaMemcpyAsync(temp.p, temp_, nc * sizeof(double), cudaMemcpyDefault, stream));
       else {
@@ -1158,6 +1173,7 @@ struct EngineT : EngineBase {
   int set_state(const double* temp_, const double* mat, const double* rad) override {
     if (!have_mesh) { err = "set_state before set_mesh"; return IMC_ERR_STATE; }
     IMC_RC(use_device());
+    echeck_cached = false;
     if (temp_) {
       if (temp_wide) IMC_CK(cudaMemcpyAsync(temp.p, temp_, nc * sizeof(double), cudaMemcpyHostToDevice, stream));
       else {  // round through T, keep the Float64 image
@@ -1293,7 +1309,7 @@ struct EngineT : EngineBase {
     if (!ckpt_valid) { err = "checkpoint: nothing saved"; return IMC_ERR_STATE; }
     IMC_RC(ensure_capacity(ckpt_host.n_part));
     const CkptHost& c = ckpt_host;
-    n_part = c.n_part; n_holes = c.n_holes; alive_known = false; temp_wide = c.temp_wide; red_fixed = c.red_fixed; dep_perm = c.dep_perm;
+    n_part = c.n_part; n_holes = c.n_holes; alive_known = false; echeck_cached = false; temp_wide = c.temp_wide; red_fixed = c.red_fixed; dep_perm = c.dep_perm;
     fx_mul_dep = c.fx_mul_dep; fx_mul_rad = c.fx_mul_rad; fx_mul_lost = c.fx_mul_lost; rad_total_h = c.rad_total_h; last_mode = c.last_mode;
     totalenergy = c.totalenergy; totalenergydep = c.totalenergydep; radenergyold = c.radenergyold; iterations = c.iterations;
     n_transport_calls = c.n_transport_calls; rate_static = c.rate_static; rate_refill = c.rate_refill; rate_event = c.rate_event;
